@@ -1,0 +1,82 @@
+/*
+ * vksift_b200_ext.h -- vksiftx_* extension entry points of the B200 build.
+ *
+ * The reference API (include/vulkansift/vulkansift.h) only takes and returns
+ * HOST memory and keeps one pipeline in flight.  These additions let a caller
+ * keep inputs and results resident in HBM (device-timed benchmarks, NCCL
+ * descriptor exchange between GPUs) and read per-stage device timings.  They
+ * are plain C ABI like the rest: pointers and sizes, no CUDA or torch types.
+ * Device pointers are passed as void* and are CUDA device addresses valid on
+ * the instance's GPU.
+ */
+#ifndef VKSIFT_B200_EXT_H
+#define VKSIFT_B200_EXT_H
+
+#include "vulkansift/vulkansift.h"
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+  /* Library build tag, e.g. "vulkansift-b200 0.1 sm_100a". */
+  VKSIFT_EXPORT const char *vksiftx_getVersionString();
+
+  /* CUDA ordinal the instance runs on, and its main stream (a cudaStream_t). */
+  VKSIFT_EXPORT int32_t vksiftx_getDeviceIndex(vksift_Instance instance);
+  VKSIFT_EXPORT void *vksiftx_getStream(vksift_Instance instance);
+
+  /* Same as vksift_detectFeatures (vulkansift.c:315-344) but the image is
+   * already in device memory (row-major u8, width*height bytes, must stay valid
+   * until the buffer is available again).  No host<->device copy is made. */
+  VKSIFT_EXPORT void vksiftx_detectFeaturesDevice(vksift_Instance instance, const void *d_image, const uint32_t image_width,
+                                                  const uint32_t image_height, const uint32_t gpu_buffer_id);
+
+  /* Block until every pipeline of the instance has finished. */
+  VKSIFT_EXPORT void vksiftx_waitIdle(vksift_Instance instance);
+
+  /* Packed device view of a feature buffer: n descriptors [n][128] u8 (row
+   * pitch 128 B) and n 36-byte feature heads (the vksift_Feature fields before
+   * `descriptor`).  Waits for the buffer; pointers stay valid until the next
+   * detect/upload on it.  Any out pointer may be NULL. */
+  VKSIFT_EXPORT void vksiftx_getBufferDeviceView(vksift_Instance instance, const uint32_t gpu_buffer_id, uint32_t *nb_feats, void **d_descriptors,
+                                                 void **d_heads);
+
+  /* Replace the content of a feature buffer by nb_feats descriptors read from
+   * device memory ([nb_feats][128] u8); heads are zeroed.  This is the device
+   * twin of vksift_uploadFeatures (vulkansift.c:398-415) and the landing point
+   * of the NCCL descriptor all-gather. */
+  VKSIFT_EXPORT void vksiftx_uploadDescriptorsDevice(vksift_Instance instance, const void *d_descriptors, const uint32_t nb_feats,
+                                                     const uint32_t gpu_buffer_id);
+
+  /* Device pointer of the last match result: vksift_getMatchesNumber() rows of vksift_Match_2NN. */
+  VKSIFT_EXPORT void *vksiftx_getMatchesDevice(vksift_Instance instance);
+
+  /* Stage timing with CUDA events on the instance stream.  When enabled, every
+   * detect/match records events around its stages; read them back (ms) after
+   * the pipeline finished.  Stage order for detection:
+   *   0 pyramid+DoG, 1 extrema+refine+order, 2 orientation, 3 descriptor (+assemble), 4 whole pipeline
+   * and for matching: 5 prepare (norms), 6 2-NN kernel, 7 whole pipeline. */
+#define VKSIFTX_NB_STAGES 8
+  VKSIFT_EXPORT void vksiftx_setProfiling(vksift_Instance instance, const bool enabled);
+  VKSIFT_EXPORT void vksiftx_getStageTimesMs(vksift_Instance instance, float *times_ms);
+
+  /* Number of kernels this library launched on the instance since creation
+   * (graph nodes count as launches). */
+  VKSIFT_EXPORT uint64_t vksiftx_getKernelLaunchCount(vksift_Instance instance);
+
+  /* Host tables of the instance, for parity tests against the oracle:
+   * effective blur taps per scale (radius[s], taps[s][21]) -- sift_detector.c:52-145 --
+   * and section capacities per octave -- sift_memory.c:40-87. */
+  VKSIFT_EXPORT void vksiftx_getEffectiveTaps(vksift_Instance instance, uint32_t *radius, float *taps);
+  VKSIFT_EXPORT void vksiftx_getSectionCapacities(vksift_Instance instance, const uint32_t gpu_buffer_id, uint32_t *caps);
+
+  /* Matcher implementation switch for verification: 0 = tcgen05 tensor-core
+   * kernel (default, the product path), 1 = SIMT dp4a cross-check kernel. */
+  VKSIFT_EXPORT void vksiftx_setMatcherImpl(vksift_Instance instance, const int32_t impl);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* VKSIFT_B200_EXT_H */

@@ -1,0 +1,217 @@
+"""GPU parity of the detection path: CUDA library (through the C ABI) vs the CPU oracle.
+
+Integer / index work must be bit-exact; because CUDA kernels and oracle share the
+fp32 arithmetic contract of include/vksift_arith.h, float fields are compared
+bit-exactly too (tolerance 0, stricter than BASELINE.json's 1e-4 relative).
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_features_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from vulkansift_b200 import api as a
+    a.load()
+    a.lib.vksift_setLogLevel(a.VKSIFT_LOG_WARNING)
+    return a
+
+
+def _oracle_cfg_from(inst_kwargs):
+    m = {"use_input_upsampling": "use_input_upsampling", "nb_octaves": "nb_octaves",
+         "nb_scales_per_octave": "nb_scales_per_octave", "input_image_blur_level": "input_image_blur_level",
+         "seed_scale_sigma": "seed_scale_sigma", "intensity_threshold": "intensity_threshold",
+         "edge_threshold": "edge_threshold", "max_nb_orientation_per_keypoint": "max_nb_orientation_per_keypoint",
+         "input_image_max_size": "input_image_max_size", "max_nb_sift_per_buffer": "max_nb_sift_per_buffer"}
+    out = {}
+    for k, v in inst_kwargs.items():
+        if k in m:
+            out[m[k]] = int(v) if isinstance(v, bool) else v
+        elif k == "descriptor_format":
+            out["use_vlfeat_format"] = int(v)
+        elif k == "use_hardware_interpolated_blur":
+            out["use_interpolated_blur"] = int(v)
+    return out
+
+
+def _run_pair(api, oracle_mod, image, **kw):
+    inst = api.Instance(**kw)
+    orc = oracle_mod.Oracle(**_oracle_cfg_from(kw))
+    exp = orc.detect(image)
+    inst.detect(image, 0)
+    got = inst.download_features(0)
+    return inst, orc, got, exp
+
+
+def test_host_tables_match_oracle(api, oracle_mod):
+    for kw in ({}, {"nb_scales_per_octave": 5}, {"use_hardware_interpolated_blur": False},
+               {"use_input_upsampling": False, "seed_scale_sigma": 2.2}):
+        inst = api.Instance(**kw)
+        orc = oracle_mod.Oracle(**_oracle_cfg_from(kw))
+        r, t = inst.effective_taps()
+        ro, to = orc.effective_taps()
+        assert np.array_equal(r, ro)
+        assert np.array_equal(t.view(np.uint32), to.view(np.uint32))
+        inst.close()
+
+
+def test_pyramid_and_dog_bit_exact_c1(api, oracle_mod, c1_image):
+    inst, orc, got, exp = _run_pair(api, oracle_mod, c1_image)
+    assert inst.nb_octaves() == orc.nb_octaves == 5
+    ns = 3
+    for o in range(orc.nb_octaves):
+        assert inst.octave_resolution(o) == orc.octave_resolution(o)
+        for s in range(ns + 3):
+            g = inst.download_scale_space_image(o, s)
+            e = orc.gaussian(o, s)
+            bad = np.count_nonzero(g.view(np.uint32) != e.view(np.uint32))
+            assert bad == 0, "Gaussian octave %d scale %d: %d px differ, max abs %g" % (o, s, bad, np.abs(g - e).max())
+        for s in range(ns + 2):
+            g = inst.download_dog_image(o, s)
+            e = orc.dog(o, s)
+            assert np.array_equal(g.view(np.uint32), e.view(np.uint32)), "DoG octave %d scale %d" % (o, s)
+    inst.close()
+
+
+def test_features_bit_exact_c1(api, oracle_mod, c1_image):
+    inst, orc, got, exp = _run_pair(api, oracle_mod, c1_image)
+    assert len(exp) == 601  # calibrated count of the C1 workload
+    assert_features_equal(got, exp, "C1")
+    caps = inst.section_capacities(0)[:orc.nb_octaves]
+    assert np.array_equal(caps, orc.section_capacity())
+    inst.close()
+
+
+@pytest.mark.parametrize("kw", [
+    {"use_input_upsampling": False},
+    {"nb_scales_per_octave": 5},
+    {"descriptor_format": 1},
+    {"use_hardware_interpolated_blur": False},
+    {"max_nb_orientation_per_keypoint": 0},
+    {"max_nb_orientation_per_keypoint": 1},
+    {"nb_octaves": 2},
+    {"intensity_threshold": 0.01, "edge_threshold": 5.0},
+], ids=lambda kw: ",".join("%s=%s" % kv for kv in kw.items()))
+def test_features_bit_exact_config_variants(api, oracle_mod, kw):
+    from vulkansift_b200.synth import blob_image
+    img = blob_image(320, 240, 150, seed=3)
+    inst, orc, got, exp = _run_pair(api, oracle_mod, img, **kw)
+    assert len(exp) > 20
+    assert_features_equal(got, exp, str(kw))
+    inst.close()
+
+
+@pytest.mark.parametrize("wh", [(333, 251), (67, 135), (1000, 37), (32, 32), (129, 257)])
+def test_ragged_sizes(api, oracle_mod, wh):
+    from vulkansift_b200.synth import blob_image
+    w, h = wh
+    img = blob_image(w, h, max(4, w * h // 600), seed=11)
+    inst, orc, got, exp = _run_pair(api, oracle_mod, img)
+    assert inst.nb_octaves() == orc.nb_octaves
+    for o in range(orc.nb_octaves):
+        assert inst.octave_resolution(o) == orc.octave_resolution(o)
+        for s in (0, 3, 5):
+            assert np.array_equal(inst.download_scale_space_image(o, s).view(np.uint32), orc.gaussian(o, s).view(np.uint32)), (o, s)
+    assert_features_equal(got, exp, str(wh))
+    inst.close()
+
+
+def test_constant_and_noise_images(api, oracle_mod):
+    inst = api.Instance()
+    inst.detect(np.full((480, 640), 128, np.uint8), 0)
+    assert inst.features_number(0) == 0
+    assert len(inst.download_features(0)) == 0
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (240, 320), dtype=np.uint8)
+    orc = oracle_mod.Oracle()
+    exp = orc.detect(img)
+    inst.detect(img, 1)
+    assert_features_equal(inst.download_features(1), exp, "noise")
+    inst.close()
+
+
+def test_section_overflow_is_deterministic(api, oracle_mod, c1_image):
+    kw = {"max_nb_sift_per_buffer": 300}
+    inst, orc, got, exp = _run_pair(api, oracle_mod, c1_image, **kw)
+    found, kept = orc.section_counts()
+    assert (found > kept).any(), "workload must overflow at least one section"
+    assert_features_equal(got, exp, "overflow")
+    inst.close()
+
+
+def test_resolution_change_and_two_buffers(api, oracle_mod, c1_image):
+    from vulkansift_b200.synth import blob_image
+    small = blob_image(200, 160, 60, seed=9)
+    inst = api.Instance()
+    orc = oracle_mod.Oracle()
+    inst.detect(c1_image, 0)
+    inst.detect(small, 1)
+    inst.detect(c1_image, 0)
+    assert_features_equal(inst.download_features(1), orc.detect(small), "small")
+    assert_features_equal(inst.download_features(0), orc.detect(c1_image), "c1 again")
+    inst.close()
+
+
+def test_device_resident_input_equals_host_input(api, c1_image):
+    import torch
+    inst = api.Instance()
+    inst.detect(c1_image, 0)
+    a = inst.download_features(0)
+    d = torch.from_numpy(c1_image).cuda()
+    torch.cuda.synchronize()
+    inst.detect_device(d.data_ptr(), c1_image.shape[1], c1_image.shape[0], 1)
+    b = inst.download_features(1)
+    assert_features_equal(b, a, "device input")
+    inst.close()
+
+
+def test_upload_download_round_trip(api, c1_image):
+    inst = api.Instance()
+    inst.detect(c1_image, 0)
+    f = inst.download_features(0)
+    inst.upload_features(f, 1)
+    assert inst.features_number(1) == len(f)
+    g = inst.download_features(1)
+    assert f.tobytes() == g.tobytes()
+    inst.close()
+
+
+def test_error_semantics(api, c1_image):
+    inst = api.Instance(sift_buffer_count=2, input_image_max_size=640 * 480)
+    with pytest.raises(api.VksiftError) as e:
+        inst.detect(c1_image, 2)  # any idx >= NB_BUFF must fail (test_sift_error_handling.cpp:56-57)
+    assert e.value.code == api.VKSIFT_INVALID_INPUT_ERROR
+    with pytest.raises(api.VksiftError):
+        inst.detect(np.zeros((1000, 1000), np.uint8), 0)  # larger than input_image_max_size
+    with pytest.raises(api.VksiftError):
+        inst.detect(np.zeros((16, 16), np.uint8), 0)  # < 1024 pixels
+    with pytest.raises(api.VksiftError):
+        inst.download_scale_space_image(0, 6)
+    with pytest.raises(api.VksiftError):
+        inst.download_dog_image(0, 5)
+    with pytest.raises(api.VksiftError):
+        inst.download_scale_space_image(99, 0)
+    # the instance stays usable after INVALID_INPUT errors
+    inst.detect(c1_image, 0)
+    assert inst.features_number(0) == 601
+    inst.close()
+    # invalid configuration is reported by the return value
+    with pytest.raises(api.VksiftError) as e:
+        api.Instance(seed_scale_sigma=0.5)  # below 2x input blur with upsampling
+    assert e.value.code == api.VKSIFT_INVALID_INPUT_ERROR
+
+
+def test_c2_full_size_matches_oracle(api, oracle_mod):
+    """BASELINE configs[1]: 1920x1080, upsampling, sigma0 1.6 -- full parity at full size."""
+    from vulkansift_b200.synth import blob_image, C2
+    img = blob_image(**C2)
+    inst, orc, got, exp = _run_pair(api, oracle_mod, img)
+    assert inst.nb_octaves() == 7
+    assert 2500 <= len(exp) <= 3600, len(exp)
+    assert_features_equal(got, exp, "C2")
+    g = inst.download_dog_image(0, 2)
+    assert np.array_equal(g.view(np.uint32), orc.dog(0, 2).view(np.uint32))
+    inst.close()

@@ -1,0 +1,137 @@
+"""GPU parity of the 2-NN matcher (tcgen05 path and SIMT cross-check) vs the oracle.
+
+Indices must be identical (integer work bit-exact); distances are sqrtf of exact
+integers on both sides, so they are compared bit-exactly as well.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from vulkansift_b200 import api as a
+    a.load()
+    a.lib.vksift_setLogLevel(a.VKSIFT_LOG_WARNING)
+    return a
+
+
+def _feats(api, desc):
+    f = np.zeros(len(desc), api.FEATURE_DTYPE)
+    f["descriptor"] = desc
+    f["x"] = np.arange(len(desc))
+    return f
+
+
+def _match(api, inst, da, db, impl):
+    inst.set_matcher_impl(impl)
+    inst.upload_features(_feats(api, da), 0)
+    inst.upload_features(_feats(api, db), 1)
+    inst.match(0, 1)
+    assert inst.matches_number() == len(da)
+    return inst.download_matches()
+
+
+def _check(got, exp, what):
+    for name in ("idx_a", "idx_b1", "idx_b2"):
+        bad = np.flatnonzero(got[name] != exp[name])
+        assert len(bad) == 0, "%s: %s differs on %d rows, first row %d got %d expected %d (d1 %g/%g d2 %g/%g)" % (
+            what, name, len(bad), bad[0], got[name][bad[0]], exp[name][bad[0]], got["dist_a_b1"][bad[0]], exp["dist_a_b1"][bad[0]],
+            got["dist_a_b2"][bad[0]], exp["dist_a_b2"][bad[0]])
+    for name in ("dist_a_b1", "dist_a_b2"):
+        assert np.array_equal(got[name].view(np.uint32), exp[name].view(np.uint32)), "%s: %s" % (what, name)
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("shape", [(1, 2), (5, 2), (100, 3), (128, 128), (129, 257), (1000, 777), (3000, 3100)])
+def test_random_descriptors(api, oracle_mod, shape, impl):
+    from vulkansift_b200.synth import random_descriptors
+    na, nb = shape
+    da, db = random_descriptors(na, 100 + na), random_descriptors(nb, 200 + nb)
+    inst = api.Instance(max_nb_sift_per_buffer=4096)
+    got = _match(api, inst, da, db, impl)
+    _check(got, oracle_mod.match_descriptors(da, db), "%s impl %d" % (shape, impl))
+    inst.close()
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+def test_ties_follow_the_shader_rule(api, oracle_mod, impl):
+    """Duplicated B rows force exact ties, including between b=0 and b=1 (Get2NearestNeighbors.comp:69-96)."""
+    rng = np.random.default_rng(7)
+    base = rng.integers(0, 256, (40, 128), dtype=np.uint8)
+    db = np.concatenate([base[:1], base[:1], base, base[::-1], base[:5]])  # b0 == b1, many duplicates
+    da = np.concatenate([base[:20], rng.integers(0, 256, (300, 128), dtype=np.uint8), base[:1]])
+    inst = api.Instance(max_nb_sift_per_buffer=1024)
+    got = _match(api, inst, da, db, impl)
+    _check(got, oracle_mod.match_descriptors(da, db), "ties impl %d" % impl)
+    inst.close()
+
+
+def test_extreme_values(api, oracle_mod):
+    da = np.concatenate([np.zeros((3, 128), np.uint8), np.full((3, 128), 255, np.uint8)])
+    db = np.concatenate([np.full((130, 128), 255, np.uint8), np.zeros((130, 128), np.uint8)])
+    db[5, 3] = 254
+    inst = api.Instance(max_nb_sift_per_buffer=1024)
+    for impl in (1, 0):
+        _check(_match(api, inst, da, db, impl), oracle_mod.match_descriptors(da, db), "extreme impl %d" % impl)
+    inst.close()
+
+
+def test_empty_a_and_too_small_b(api):
+    inst = api.Instance(max_nb_sift_per_buffer=1024)
+    inst.upload_features(np.zeros(0, api.FEATURE_DTYPE), 0)
+    inst.upload_features(_feats(api, np.zeros((4, 128), np.uint8)), 1)
+    inst.match(0, 1)
+    assert inst.matches_number() == 0 and len(inst.download_matches()) == 0
+    inst.upload_features(_feats(api, np.zeros((4, 128), np.uint8)), 0)
+    inst.upload_features(_feats(api, np.zeros((1, 128), np.uint8)), 1)
+    with pytest.raises(api.VksiftError) as e:
+        inst.match(0, 1)
+    assert e.value.code == api.VKSIFT_INVALID_INPUT_ERROR
+    inst.close()
+
+
+def test_detected_features_match_and_ratio_test(api, oracle_mod, c1_image):
+    """The reference example's flow (test_sift_match.cpp:67-107): detect two images, match both ways,
+    cross-check + Lowe ratio 0.75 on true L2 distances."""
+    shifted = np.roll(np.roll(c1_image, 7, axis=1), 5, axis=0)
+    inst = api.Instance()
+    inst.detect(c1_image, 0)
+    inst.detect(shifted, 1)
+    fa, fb = inst.download_features(0), inst.download_features(1)
+    inst.match(0, 1)
+    m01 = inst.download_matches()
+    inst.match(1, 0)
+    m10 = inst.download_matches()
+    _check(m01, oracle_mod.match_features(fa, fb), "detected 0->1")
+    _check(m10, oracle_mod.match_features(fb, fa), "detected 1->0")
+    good = [(m["idx_a"], m["idx_b1"]) for m in m01
+            if m10["idx_b1"][m["idx_b1"]] == m["idx_a"] and m["dist_a_b1"] / m["dist_a_b2"] < 0.75]
+    assert len(good) > 300
+    dx = np.array([fb["x"][b] - fa["x"][a] for a, b in good])
+    dy = np.array([fb["y"][b] - fa["y"][a] for a, b in good])
+    inl = (np.abs(dx - 7) < 1.0) & (np.abs(dy - 5) < 1.0)
+    assert inl.mean() > 0.9
+    inst.close()
+
+
+def test_c4_full_size_10k_x_10k(api, oracle_mod):
+    """BASELINE configs[3].  Full-size: tcgen05 vs SIMT on every row, and vs the oracle on a row sample;
+    size-independent property: d1 <= d2 and both are true minima of a brute-force numpy check on 64 rows."""
+    from vulkansift_b200.synth import random_descriptors
+    da, db = random_descriptors(10000, 1234), random_descriptors(10000, 1235)
+    inst = api.Instance(max_nb_sift_per_buffer=10000)
+    tc = _match(api, inst, da, db, 0)
+    simt = _match(api, inst, da, db, 1)
+    _check(tc, simt, "C4 tcgen05 vs simt")
+    sel = np.arange(0, 10000, 19)
+    exp = oracle_mod.match_descriptors(da[sel], db)
+    sub = tc[sel].copy()
+    sub["idx_a"] = np.arange(len(sel))
+    _check(sub, exp, "C4 sample vs oracle")
+    assert np.all(tc["dist_a_b1"] <= tc["dist_a_b2"])
+    rows = sel[:64]
+    d2 = ((da[rows, None, :].astype(np.int32) - db[None, :, :].astype(np.int32)) ** 2).sum(-1)
+    assert np.array_equal(np.sort(d2, axis=1)[:, 0], np.round(tc["dist_a_b1"][rows].astype(np.float64) ** 2).astype(np.int64))
+    inst.close()

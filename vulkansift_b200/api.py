@@ -1,0 +1,315 @@
+"""ctypes binding of libvulkansift.so, mirroring the reference C API one to one.
+
+Every vksift_* entry point of include/vulkansift/vulkansift.h is exposed under
+its own name through `lib`; `Instance` is a small convenience wrapper that
+keeps the call order of the reference examples (src/examples/test_sift_detect.cpp,
+test_sift_match.cpp): loadVulkan -> createInstance -> detectFeatures ->
+getFeaturesNumber -> downloadFeatures -> matchFeatures -> downloadMatches.
+
+Errors: the reference reports errors of void functions through
+vksift_Config.on_error_callback_function (C++ callers throw from it).  A ctypes
+callback cannot unwind through C frames, so the Python callback records the
+code and the wrapper raises VksiftError right after the C call returns.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvulkansift.so")
+
+VKSIFT_SUCCESS, VKSIFT_INVALID_INPUT_ERROR, VKSIFT_VULKAN_ERROR = 0, 1, 2
+VKSIFT_NO_LOG, VKSIFT_LOG_ERROR, VKSIFT_LOG_WARNING, VKSIFT_LOG_INFO, VKSIFT_LOG_DEBUG = range(5)
+VKSIFT_DESCRIPTOR_FORMAT_UBC, VKSIFT_DESCRIPTOR_FORMAT_VLFEAT = 0, 1
+VKSIFT_PYRAMID_PRECISION_FLOAT32, VKSIFT_PYRAMID_PRECISION_FLOAT16 = 0, 1
+NB_STAGES = 8
+STAGE_NAMES = ("pyramid_dog", "extrema", "orientation", "descriptor", "detect_total", "match_prepare", "match_2nn",
+               "match_total")
+
+FEATURE_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("scale_x", "<f4"), ("scale_y", "<f4"), ("scale_idx", "<u4"),
+                          ("octave_idx", "<i4"), ("sigma", "<f4"), ("orientation", "<f4"), ("intensity", "<f4"),
+                          ("descriptor", "u1", (128,))])
+MATCH_DTYPE = np.dtype([("idx_a", "<u4"), ("idx_b1", "<u4"), ("idx_b2", "<u4"), ("dist_a_b1", "<f4"),
+                        ("dist_a_b2", "<f4")])
+
+ERROR_CALLBACK = C.CFUNCTYPE(None, C.c_int)
+
+
+class ExternalWindowInfo(C.Structure):
+    _fields_ = [("context", C.c_void_p), ("window", C.c_void_p)]
+
+
+class Config(C.Structure):
+    """vksift_Config (include/vulkansift/vulkansift_types.h), 88 bytes."""
+    _fields_ = [("input_image_max_size", C.c_uint32), ("sift_buffer_count", C.c_uint32),
+                ("max_nb_sift_per_buffer", C.c_uint32), ("use_input_upsampling", C.c_bool), ("nb_octaves", C.c_uint8),
+                ("nb_scales_per_octave", C.c_uint8), ("input_image_blur_level", C.c_float),
+                ("seed_scale_sigma", C.c_float), ("intensity_threshold", C.c_float), ("edge_threshold", C.c_float),
+                ("max_nb_orientation_per_keypoint", C.c_uint32), ("descriptor_format", C.c_int),
+                ("gpu_device_index", C.c_int32), ("use_hardware_interpolated_blur", C.c_bool),
+                ("pyramid_precision_mode", C.c_int), ("on_error_callback_function", ERROR_CALLBACK),
+                ("use_gpu_debug_functions", C.c_bool), ("gpu_debug_external_window_info", ExternalWindowInfo)]
+
+
+class VksiftError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        name = {1: "VKSIFT_INVALID_INPUT_ERROR", 2: "VKSIFT_VULKAN_ERROR"}.get(code, str(code))
+        super().__init__("%s in %s" % (name, where))
+
+
+def _load_library():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: build it with `python -m vulkansift_b200.build` (needs nvcc). "
+                          "There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    I, P = C.c_void_p, C.POINTER
+    u32, u8 = C.c_uint32, C.c_uint8
+    sig = {
+        "vksift_loadVulkan": (C.c_int, []),
+        "vksift_unloadVulkan": (None, []),
+        "vksift_getAvailableGPUs": (None, [P(u32), C.c_void_p]),
+        "vksift_setLogLevel": (None, [C.c_int]),
+        "vksift_createInstance": (C.c_int, [P(I), P(Config)]),
+        "vksift_destroyInstance": (None, [P(I)]),
+        "vksift_getDefaultConfig": (Config, []),
+        "vksift_detectFeatures": (None, [I, C.c_void_p, u32, u32, u32]),
+        "vksift_matchFeatures": (None, [I, u32, u32]),
+        "vksift_getFeaturesNumber": (u32, [I, u32]),
+        "vksift_downloadFeatures": (None, [I, C.c_void_p, u32]),
+        "vksift_uploadFeatures": (None, [I, C.c_void_p, u32, u32]),
+        "vksift_getMatchesNumber": (u32, [I]),
+        "vksift_downloadMatches": (None, [I, C.c_void_p]),
+        "vksift_isBufferAvailable": (C.c_bool, [I, u32]),
+        "vksift_getScaleSpaceNbOctaves": (u8, [I]),
+        "vksift_getScaleSpaceOctaveResolution": (None, [I, u8, P(u32), P(u32)]),
+        "vksift_downloadScaleSpaceImage": (None, [I, u8, u8, C.c_void_p]),
+        "vksift_downloadDoGImage": (None, [I, u8, u8, C.c_void_p]),
+        "vksift_presentDebugFrame": (None, [I]),
+        # extensions (include/vksift_b200_ext.h)
+        "vksiftx_getVersionString": (C.c_char_p, []),
+        "vksiftx_getDeviceIndex": (C.c_int32, [I]),
+        "vksiftx_getStream": (C.c_void_p, [I]),
+        "vksiftx_detectFeaturesDevice": (None, [I, C.c_void_p, u32, u32, u32]),
+        "vksiftx_waitIdle": (None, [I]),
+        "vksiftx_getBufferDeviceView": (None, [I, u32, P(u32), P(C.c_void_p), P(C.c_void_p)]),
+        "vksiftx_uploadDescriptorsDevice": (None, [I, C.c_void_p, u32, u32]),
+        "vksiftx_getMatchesDevice": (C.c_void_p, [I]),
+        "vksiftx_setProfiling": (None, [I, C.c_bool]),
+        "vksiftx_getStageTimesMs": (None, [I, P(C.c_float)]),
+        "vksiftx_getKernelLaunchCount": (C.c_uint64, [I]),
+        "vksiftx_getEffectiveTaps": (None, [I, C.c_void_p, C.c_void_p]),
+        "vksiftx_getSectionCapacities": (None, [I, u32, C.c_void_p]),
+        "vksiftx_setMatcherImpl": (None, [I, C.c_int32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib, sorted(sig)
+
+
+lib, EXPORTED_SYMBOLS = _load_library()
+
+_loaded = False
+
+
+def load():
+    """vksift_loadVulkan(): raises VksiftError when no B200-class CUDA device is usable."""
+    global _loaded
+    if not _loaded:
+        r = lib.vksift_loadVulkan()
+        if r != VKSIFT_SUCCESS:
+            raise VksiftError(r, "vksift_loadVulkan")
+        _loaded = True
+
+
+def unload():
+    global _loaded
+    lib.vksift_unloadVulkan()
+    _loaded = False
+
+
+def available_gpus():
+    n = C.c_uint32(0)
+    lib.vksift_getAvailableGPUs(C.byref(n), None)
+    names = (C.c_char * 256 * max(1, n.value))()
+    lib.vksift_getAvailableGPUs(C.byref(n), names)
+    return [names[i].value.decode() for i in range(n.value)]
+
+
+def default_config():
+    return lib.vksift_getDefaultConfig()
+
+
+class Instance:
+    """One vksift_Instance (one GPU).  Keyword arguments override vksift_Config fields."""
+
+    def __init__(self, **overrides):
+        load()
+        self._errors = []
+        self._cb = ERROR_CALLBACK(lambda code: self._errors.append(int(code)))
+        self.config = default_config()
+        for k, v in overrides.items():
+            if not hasattr(self.config, k):
+                raise AttributeError("vksift_Config has no field %r" % k)
+            setattr(self.config, k, v)
+        self.config.on_error_callback_function = self._cb
+        self._h = C.c_void_p(None)
+        r = lib.vksift_createInstance(C.byref(self._h), C.byref(self.config))
+        if r != VKSIFT_SUCCESS:
+            raise VksiftError(r, "vksift_createInstance")
+
+    # -- plumbing
+    def _check(self, where):
+        if self._errors:
+            code = self._errors[0]
+            self._errors.clear()
+            raise VksiftError(code, where)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib.vksift_destroyInstance(C.byref(self._h))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- reference API
+    def detect(self, image, buffer_id=0):
+        """vksift_detectFeatures: image is a (h,w) uint8 numpy array (host memory)."""
+        image = np.ascontiguousarray(image, np.uint8)
+        h, w = image.shape
+        lib.vksift_detectFeatures(self._h, image.ctypes.data, w, h, buffer_id)
+        self._check("vksift_detectFeatures")
+
+    def detect_raw(self, ptr, w, h, buffer_id=0):
+        lib.vksift_detectFeatures(self._h, ptr, w, h, buffer_id)
+        self._check("vksift_detectFeatures")
+
+    def features_number(self, buffer_id=0):
+        n = lib.vksift_getFeaturesNumber(self._h, buffer_id)
+        self._check("vksift_getFeaturesNumber")
+        return n
+
+    def download_features(self, buffer_id=0):
+        n = self.features_number(buffer_id)
+        out = np.zeros(n, FEATURE_DTYPE)
+        lib.vksift_downloadFeatures(self._h, out.ctypes.data, buffer_id)
+        self._check("vksift_downloadFeatures")
+        return out
+
+    def upload_features(self, feats, buffer_id=0):
+        feats = np.ascontiguousarray(feats)
+        assert feats.dtype == FEATURE_DTYPE
+        lib.vksift_uploadFeatures(self._h, feats.ctypes.data, len(feats), buffer_id)
+        self._check("vksift_uploadFeatures")
+
+    def match(self, buffer_a=0, buffer_b=1):
+        lib.vksift_matchFeatures(self._h, buffer_a, buffer_b)
+        self._check("vksift_matchFeatures")
+
+    def matches_number(self):
+        return lib.vksift_getMatchesNumber(self._h)
+
+    def download_matches(self):
+        out = np.zeros(self.matches_number(), MATCH_DTYPE)
+        lib.vksift_downloadMatches(self._h, out.ctypes.data)
+        self._check("vksift_downloadMatches")
+        return out
+
+    def is_buffer_available(self, buffer_id=0):
+        return bool(lib.vksift_isBufferAvailable(self._h, buffer_id))
+
+    def nb_octaves(self):
+        return lib.vksift_getScaleSpaceNbOctaves(self._h)
+
+    def octave_resolution(self, octave):
+        w, h = C.c_uint32(0), C.c_uint32(0)
+        lib.vksift_getScaleSpaceOctaveResolution(self._h, octave, C.byref(w), C.byref(h))
+        self._check("vksift_getScaleSpaceOctaveResolution")
+        return w.value, h.value
+
+    def _download_layer(self, fn, name, octave, scale):
+        if 0 <= octave < self.nb_octaves():
+            w, h = self.octave_resolution(octave)
+        else:
+            w, h = 1, 1
+        out = np.zeros((h, w), np.float32)
+        fn(self._h, octave, scale, out.ctypes.data)
+        self._check(name)
+        return out
+
+    def download_scale_space_image(self, octave, scale):
+        return self._download_layer(lib.vksift_downloadScaleSpaceImage, "vksift_downloadScaleSpaceImage", octave, scale)
+
+    def download_dog_image(self, octave, scale):
+        return self._download_layer(lib.vksift_downloadDoGImage, "vksift_downloadDoGImage", octave, scale)
+
+    def present_debug_frame(self):
+        lib.vksift_presentDebugFrame(self._h)
+
+    # -- extensions
+    @property
+    def device_index(self):
+        return lib.vksiftx_getDeviceIndex(self._h)
+
+    @property
+    def stream(self):
+        return lib.vksiftx_getStream(self._h)
+
+    def detect_device(self, dev_ptr, w, h, buffer_id=0):
+        lib.vksiftx_detectFeaturesDevice(self._h, dev_ptr, w, h, buffer_id)
+        self._check("vksiftx_detectFeaturesDevice")
+
+    def wait_idle(self):
+        lib.vksiftx_waitIdle(self._h)
+
+    def buffer_device_view(self, buffer_id=0):
+        n, d, hd = C.c_uint32(0), C.c_void_p(None), C.c_void_p(None)
+        lib.vksiftx_getBufferDeviceView(self._h, buffer_id, C.byref(n), C.byref(d), C.byref(hd))
+        self._check("vksiftx_getBufferDeviceView")
+        return n.value, d.value, hd.value
+
+    def upload_descriptors_device(self, dev_ptr, n, buffer_id=0):
+        lib.vksiftx_uploadDescriptorsDevice(self._h, dev_ptr, n, buffer_id)
+        self._check("vksiftx_uploadDescriptorsDevice")
+
+    def matches_device(self):
+        return lib.vksiftx_getMatchesDevice(self._h)
+
+    def set_profiling(self, enabled=True):
+        lib.vksiftx_setProfiling(self._h, bool(enabled))
+
+    def stage_times_ms(self):
+        t = (C.c_float * NB_STAGES)()
+        lib.vksiftx_getStageTimesMs(self._h, t)
+        return dict(zip(STAGE_NAMES, [float(v) for v in t]))
+
+    def kernel_launch_count(self):
+        return int(lib.vksiftx_getKernelLaunchCount(self._h))
+
+    def effective_taps(self):
+        n = self.config.nb_scales_per_octave + 3
+        radius = np.zeros(n, np.uint32)
+        taps = np.zeros((n, 21), np.float32)
+        lib.vksiftx_getEffectiveTaps(self._h, radius.ctypes.data, taps.ctypes.data)
+        return radius, taps
+
+    def section_capacities(self, buffer_id=0):
+        caps = np.zeros(16, np.uint32)
+        lib.vksiftx_getSectionCapacities(self._h, buffer_id, caps.ctypes.data)
+        self._check("vksiftx_getSectionCapacities")
+        return caps
+
+    def set_matcher_impl(self, impl):
+        lib.vksiftx_setMatcherImpl(self._h, int(impl))

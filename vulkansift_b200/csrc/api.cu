@@ -1,0 +1,1151 @@
+/*
+ * api.cu -- the vksift_* C ABI on CUDA.
+ *
+ * Mirrors the behaviour of the reference's src/vulkansift/vulkansift.c (entry
+ * points, validation, blocking rules, error callback) with CUDA plumbing:
+ *   Vulkan instance/loader  -> CUDA runtime initialisation check
+ *   general queue + fences  -> one stream + two events (detect / match)
+ *   staging buffers         -> pinned host buffers, cudaMemcpyAsync
+ *   pre-recorded cmd buffer -> a launch plan rebuilt when the resolution changes
+ * Feature buffers are packed on the device (sections are applied as counts,
+ * see describe.cu), so the reference's pack step (sift_memory.c:957-1047)
+ * has nothing to move.
+ */
+#include "vksift_internal.h"
+
+#include <cassert>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace vks
+{
+
+/* ---- logger (vkenv/logger.c:55-84) --------------------------------------- */
+static int g_log_level = VKSIFT_LOG_INFO;
+static bool g_api_loaded = false;
+
+void log_msg(int level, const char *tag, const char *fmt, ...)
+{
+  if (level > g_log_level || level == VKSIFT_NO_LOG)
+    return;
+  static const char *names[] = {"", "ERROR", "WARNING", "INFO", "DEBUG"};
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  fprintf(level <= VKSIFT_LOG_WARNING ? stderr : stdout, "[%s][%s] %s\n", names[level], tag, buf);
+}
+
+static const char TAG[] = "VulkanSift";
+
+/* ---- instance state -------------------------------------------------------- */
+struct FeatureBuffer
+{
+  FeatHead *heads = nullptr; /* packed [max] */
+  uint8_t *desc = nullptr;   /* packed [max][128] */
+  DetectCounters *cnt = nullptr;
+  uint32_t *host_counts = nullptr; /* pinned+mapped: [0]=n, [1..16]=found, [17..32]=kept */
+  uint32_t *host_counts_dev = nullptr;
+  uint32_t cap[VKS_MAX_OCT] = {0};
+  uint32_t n_oct = 0;
+  uint32_t cur_w = 0, cur_h = 0;
+  bool uploaded = false; /* content came from vksift_uploadFeatures (is_packed in the reference) */
+  uint32_t n_uploaded = 0;
+};
+
+struct Pyramid
+{
+  uint32_t n_oct = 0;
+  uint32_t w[VKS_MAX_OCT] = {0}, h[VKS_MAX_OCT] = {0}, pitch[VKS_MAX_OCT] = {0};
+  float *G[VKS_MAX_OCT] = {nullptr};
+  float *D[VKS_MAX_OCT] = {nullptr};
+  size_t alloc_floats_g[VKS_MAX_OCT] = {0};
+  size_t alloc_floats_d[VKS_MAX_OCT] = {0};
+};
+
+enum
+{
+  EV_D0 = 0, /* detect start */
+  EV_D1,     /* after pyramid */
+  EV_D2,     /* after extrema+order */
+  EV_D3,     /* after orientation */
+  EV_D4,     /* after descriptors */
+  EV_M0,
+  EV_M1,
+  EV_M2,
+  EV_COUNT
+};
+
+} // namespace vks
+
+using namespace vks;
+
+struct vksift_Instance_T
+{
+  vksift_Config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_detect_done = nullptr, ev_match_done = nullptr;
+  bool detect_pending = false, match_pending = false;
+  uint32_t detect_buffer = 0, match_a = 0, match_b = 0;
+
+  uint32_t max_image_size = 0;
+  uint32_t max_octaves = 0;
+  uint32_t cur_w = 0, cur_h = 0;
+  ScalePlan scales;
+  Pyramid pyr;
+  std::vector<BlurStep> steps;
+
+  uint8_t *h_image = nullptr; /* pinned */
+  uint8_t *d_image = nullptr;
+
+  std::vector<FeatureBuffer> buffers;
+  Candidate *cand = nullptr;
+  uint32_t cand_cap = 0;
+  FeatHead *prim = nullptr;
+  float *ori = nullptr;
+  uint32_t *n_ori = nullptr;
+  uint32_t *feat_src = nullptr;
+  uint32_t ori_stride = 4;
+
+  uint8_t *d_aos = nullptr; /* device AoS staging for feature up/download */
+  MatchWorkspace *match_ws = nullptr;
+  vksift_Match_2NN *d_matches = nullptr;
+  uint32_t nb_matches = 0;
+  int matcher_impl = 0;
+
+  bool profiling = false;
+  cudaEvent_t ev[EV_COUNT] = {nullptr};
+  bool ev_detect_valid = false, ev_match_valid = false;
+  uint64_t launches = 0;
+};
+
+namespace
+{
+
+struct DeviceGuard
+{
+  int prev = -1;
+  explicit DeviceGuard(int dev)
+  {
+    cudaGetDevice(&prev);
+    if (prev != dev)
+      cudaSetDevice(dev);
+    else
+      prev = -1;
+  }
+  ~DeviceGuard()
+  {
+    if (prev >= 0)
+      cudaSetDevice(prev);
+  }
+};
+
+#define CU_TRY(expr)                                                                                                                                 \
+  do                                                                                                                                                 \
+  {                                                                                                                                                  \
+    cudaError_t e__ = (expr);                                                                                                                        \
+    if (e__ != cudaSuccess)                                                                                                                          \
+    {                                                                                                                                                \
+      LOGE(TAG, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e__), __FILE__, __LINE__, #expr);                                                    \
+      return false;                                                                                                                                  \
+    }                                                                                                                                                \
+  } while (0)
+
+void default_error_callback(vksift_Result r)
+{
+  LOGD(TAG, r == VKSIFT_INVALID_INPUT_ERROR ? "Aborting after invalid input error..." : "Aborting after device error...");
+  abort();
+}
+
+/* ---- validation (vulkansift.c:541-661) ------------------------------------ */
+bool config_valid(const vksift_Config *c)
+{
+  bool ok = true;
+  auto need = [&](bool cond, const char *msg) {
+    if (!cond)
+    {
+      LOGE(TAG, "%s", msg);
+      ok = false;
+    }
+  };
+  const bool seed_ok = ((c->use_input_upsampling ? 2.f : 1.f) * c->input_image_blur_level) <= c->seed_scale_sigma;
+  need(c->input_image_max_size >= 1024, "Invalid configuration: input image size must be greater than or equal to 1024");
+  need(c->sift_buffer_count > 0, "Invalid configuration: number of SIFT buffers must be greater than zero");
+  need(c->max_nb_sift_per_buffer > 0, "Invalid configuration: number of SIFT features per buffers must be greater than zero");
+  need(c->nb_scales_per_octave > 0, "Invalid configuration: number of scales per octave must be greater than zero");
+  need(c->nb_scales_per_octave + 3 <= VKS_MAX_LAYERS, "Invalid configuration: too many scales per octave for this build");
+  need(c->input_image_blur_level >= 0.f, "Invalid configuration: input image blur level cannot be negative");
+  need(c->seed_scale_sigma >= 0, "Invalid configuration: seed scale blur level cannot be negative");
+  need(seed_ok, "Invalid configuration: the input image blur level (2x if upscaling activated) must be less than the seed scale blur level");
+  need(c->intensity_threshold >= 0.f, "Invalid configuration: the DoG intensity threshold cannot be negative");
+  need(c->edge_threshold >= 0.f, "Invalid configuration: the DoG edge threshold cannot be negative");
+  need(c->on_error_callback_function != NULL, "Invalid configuration: the error callback function must not be NULL");
+  switch (c->pyramid_precision_mode)
+  {
+  case VKSIFT_PYRAMID_PRECISION_FLOAT32:
+    break;
+  case VKSIFT_PYRAMID_PRECISION_FLOAT16:
+    need(false, "Invalid configuration: VKSIFT_PYRAMID_PRECISION_FLOAT16 is not available in this build yet");
+    break;
+  default:
+    need(false, "Invalid configuration: invalid scale-space pyramid format precision specified");
+    break;
+  }
+  return ok;
+}
+
+bool buffer_idx_valid(vksift_Instance inst, uint32_t idx)
+{
+  /* the reference tests '>' (vulkansift.c:588); its own example documents '>=' as the intent (SURVEY B-D5) */
+  if (idx >= inst->buffers.size())
+  {
+    LOGE(TAG, "Provided target buffer index is (%u) but the number of reserved buffers is (%zu).", idx, inst->buffers.size());
+    return false;
+  }
+  return true;
+}
+
+bool resolution_valid(vksift_Instance inst, uint32_t w, uint32_t h)
+{
+  const uint32_t size = w * h;
+  if (size > inst->max_image_size)
+  {
+    LOGE(TAG, "Provided input image size (%u*%u=%u) is greater than the configured maximum image size (%u).", w, h, size, inst->max_image_size);
+    return false;
+  }
+  if (size < 1024u)
+  {
+    LOGE(TAG, "Invalid input image size (%u*%u=%u). Input image size must be greater than or equal to 1024", w, h, size);
+    return false;
+  }
+  return true;
+}
+
+/* ---- memory ---------------------------------------------------------------- */
+bool alloc_pyramid(vksift_Instance inst)
+{
+  Pyramid &p = inst->pyr;
+  const size_t ns = inst->cfg.nb_scales_per_octave;
+  for (uint32_t o = 0; o < p.n_oct; o++)
+  {
+    p.pitch[o] = (p.w[o] + 31u) & ~31u;
+    const size_t layer = (size_t)p.pitch[o] * p.h[o];
+    const size_t need_g = layer * (ns + 3), need_d = layer * (ns + 2);
+    if (need_g > p.alloc_floats_g[o])
+    {
+      if (p.G[o])
+        CU_TRY(cudaFree(p.G[o]));
+      p.G[o] = nullptr;
+      CU_TRY(cudaMalloc(&p.G[o], need_g * sizeof(float)));
+      p.alloc_floats_g[o] = need_g;
+    }
+    if (need_d > p.alloc_floats_d[o])
+    {
+      if (p.D[o])
+        CU_TRY(cudaFree(p.D[o]));
+      p.D[o] = nullptr;
+      CU_TRY(cudaMalloc(&p.D[o], need_d * sizeof(float)));
+      p.alloc_floats_d[o] = need_d;
+    }
+  }
+  return true;
+}
+
+/* Launch plan of the scale space for the current resolution: the CUDA twin of
+ * recScaleSpaceConstructionCmds + recDifferenceOfGaussianCmds (sift_detector.c:893-1079). */
+void build_blur_plan(vksift_Instance inst)
+{
+  const Pyramid &p = inst->pyr;
+  const int ns = inst->cfg.nb_scales_per_octave;
+  inst->steps.clear();
+  for (uint32_t o = 0; o < p.n_oct; o++)
+  {
+    const size_t layer = (size_t)p.pitch[o] * p.h[o];
+    for (int s = (o == 0 ? 0 : 1); s < ns + 3; s++)
+    {
+      BlurStep step;
+      memset(&step, 0, sizeof(step));
+      BlurPass &bp = step.pass[0];
+      bp.w = (int)p.w[o];
+      bp.h = (int)p.h[o];
+      bp.dst_pitch = (int)p.pitch[o];
+      bp.dst_g = p.G[o] + layer * s;
+      if (s == 0)
+      {
+        bp.src = inst->d_image; /* patched per call when the image already lives in HBM */
+        bp.src_kind = inst->cfg.use_input_upsampling ? BLUR_SRC_U8_UP2 : BLUR_SRC_U8;
+        bp.src_w = (int)inst->cur_w;
+        bp.src_h = (int)inst->cur_h;
+        bp.src_pitch = (int)inst->cur_w;
+        bp.dst_d = nullptr;
+      }
+      else
+      {
+        bp.src = p.G[o] + layer * (s - 1);
+        bp.src_kind = BLUR_SRC_LAYER;
+        bp.src_pitch = (int)p.pitch[o];
+        bp.dst_d = p.D[o] + layer * (s - 1);
+      }
+      if (s == ns && o + 1 < p.n_oct)
+      {
+        bp.dst_next = p.G[o + 1];
+        bp.next_pitch = (int)p.pitch[o + 1];
+        bp.next_w = (int)p.w[o + 1];
+        bp.next_h = (int)p.h[o + 1];
+      }
+      bp.radius = (int)inst->scales.radius[s];
+      memcpy(bp.taps, inst->scales.taps[s], sizeof(bp.taps));
+      bp.tiles_x = (bp.w + 63) / 64;
+      bp.tiles_y = (bp.h + 31) / 32;
+      bp.tile_begin = 0;
+      step.n_pass = 1;
+      step.n_tiles = bp.tiles_x * bp.tiles_y;
+      inst->steps.push_back(step);
+    }
+  }
+}
+
+bool set_resolution(vksift_Instance inst, uint32_t w, uint32_t h)
+{
+  inst->cur_w = w;
+  inst->cur_h = h;
+  Pyramid &p = inst->pyr;
+  p.n_oct = plan_octaves(w, h, inst->cfg.use_input_upsampling, inst->max_octaves, p.w, p.h);
+  if (!alloc_pyramid(inst))
+    return false;
+  build_blur_plan(inst);
+  return true;
+}
+
+void update_buffer_sections(vksift_Instance inst, FeatureBuffer &fb)
+{
+  fb.cur_w = inst->cur_w;
+  fb.cur_h = inst->cur_h;
+  fb.n_oct = inst->pyr.n_oct;
+  plan_sections(inst->cfg.max_nb_sift_per_buffer, fb.n_oct, fb.cap);
+}
+
+void fill_detect_params(vksift_Instance inst, const FeatureBuffer &fb, DetectParams *P)
+{
+  memset(P, 0, sizeof(*P));
+  const Pyramid &p = inst->pyr;
+  const vksift_Config &c = inst->cfg;
+  uint32_t off = 0;
+  for (uint32_t o = 0; o < p.n_oct; o++)
+  {
+    P->oct[o].G = p.G[o];
+    P->oct[o].D = p.D[o];
+    P->oct[o].w = (int)p.w[o];
+    P->oct[o].h = (int)p.h[o];
+    P->oct[o].pitch = (int)p.pitch[o];
+    P->oct[o].layer_stride = (int)(p.pitch[o] * p.h[o]);
+    P->cap[o] = fb.cap[o];
+    P->sec_off[o] = off;
+    off += fb.cap[o];
+  }
+  P->n_oct = (int)p.n_oct;
+  P->ns = c.nb_scales_per_octave;
+  P->upsample = c.use_input_upsampling ? 1 : 0;
+  P->sigma0 = c.seed_scale_sigma;
+  P->thr = c.intensity_threshold / c.nb_scales_per_octave; /* sift_detector.c:1136 */
+  P->prefilter = P->thr * 0.8f;                             /* ExtractKeypoints.comp:58 */
+  P->edge_limit = ((c.edge_threshold + 1.f) * (c.edge_threshold + 1.f)) / c.edge_threshold; /* :203 */
+  P->max_ori = c.max_nb_orientation_per_keypoint;
+  P->ori_stride = inst->ori_stride;
+  P->vlfeat = (c.descriptor_format == VKSIFT_DESCRIPTOR_FORMAT_VLFEAT) ? 1 : 0;
+  P->cand_cap = inst->cand_cap;
+  P->max_feats = c.max_nb_sift_per_buffer;
+}
+
+void wait_pipelines(vksift_Instance inst, bool detect, bool match)
+{
+  if (detect && inst->detect_pending)
+  {
+    cudaEventSynchronize(inst->ev_detect_done);
+    inst->detect_pending = false;
+  }
+  if (match && inst->match_pending)
+  {
+    cudaEventSynchronize(inst->ev_match_done);
+    inst->match_pending = false;
+  }
+}
+
+uint32_t buffer_count(vksift_Instance inst, uint32_t idx, bool log_lost)
+{
+  FeatureBuffer &fb = inst->buffers[idx];
+  if (fb.uploaded)
+    return fb.n_uploaded;
+  if (log_lost)
+  {
+    uint32_t lost = 0;
+    for (uint32_t o = 0; o < VKS_MAX_OCT; o++)
+      lost += fb.host_counts[1 + o] - fb.host_counts[1 + VKS_MAX_OCT + o];
+    if (lost > 0)
+      LOGE(TAG,
+           "%u feature(s) lost because the SIFT buffer was full, consider increasing the maximum number of SIFT features per buffer in the "
+           "configuration.",
+           lost);
+  }
+  return fb.host_counts[0];
+}
+
+void destroy_instance(vksift_Instance inst)
+{
+  DeviceGuard g(inst->device);
+  cudaDeviceSynchronize();
+  for (auto &fb : inst->buffers)
+  {
+    cudaFree(fb.heads);
+    cudaFree(fb.desc);
+    cudaFree(fb.cnt);
+    if (fb.host_counts)
+      cudaFreeHost(fb.host_counts);
+  }
+  for (uint32_t o = 0; o < VKS_MAX_OCT; o++)
+  {
+    cudaFree(inst->pyr.G[o]);
+    cudaFree(inst->pyr.D[o]);
+  }
+  if (inst->h_image)
+    cudaFreeHost(inst->h_image);
+  cudaFree(inst->d_image);
+  cudaFree(inst->cand);
+  cudaFree(inst->prim);
+  cudaFree(inst->ori);
+  cudaFree(inst->n_ori);
+  cudaFree(inst->feat_src);
+  cudaFree(inst->d_aos);
+  cudaFree(inst->d_matches);
+  match_workspace_destroy(inst->match_ws);
+  for (int i = 0; i < EV_COUNT; i++)
+    if (inst->ev[i])
+      cudaEventDestroy(inst->ev[i]);
+  if (inst->ev_detect_done)
+    cudaEventDestroy(inst->ev_detect_done);
+  if (inst->ev_match_done)
+    cudaEventDestroy(inst->ev_match_done);
+  if (inst->stream)
+    cudaStreamDestroy(inst->stream);
+  delete inst;
+}
+
+bool create_resources(vksift_Instance inst)
+{
+  const vksift_Config &c = inst->cfg;
+  CU_TRY(cudaStreamCreateWithFlags(&inst->stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreateWithFlags(&inst->ev_detect_done, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&inst->ev_match_done, cudaEventDisableTiming));
+  for (int i = 0; i < EV_COUNT; i++)
+    CU_TRY(cudaEventCreate(&inst->ev[i]));
+
+  uint32_t side = 0;
+  inst->max_octaves = plan_max_octaves(&c, &side);
+  inst->max_image_size = side * side; /* sift_memory.c:641 */
+  plan_gaussian_taps(&inst->scales, &c);
+
+  CU_TRY(cudaHostAlloc(&inst->h_image, inst->max_image_size, cudaHostAllocDefault));
+  CU_TRY(cudaMalloc(&inst->d_image, inst->max_image_size));
+
+  const size_t maxf = c.max_nb_sift_per_buffer;
+  inst->ori_stride = (c.max_nb_orientation_per_keypoint == 0 || c.max_nb_orientation_per_keypoint > VKS_MAX_ORI) ? VKS_MAX_ORI
+                                                                                                                   : c.max_nb_orientation_per_keypoint;
+  inst->cand_cap = c.max_nb_sift_per_buffer;
+  CU_TRY(cudaMalloc(&inst->cand, sizeof(Candidate) * (size_t)inst->cand_cap * (inst->max_octaves ? inst->max_octaves : 1)));
+  CU_TRY(cudaMalloc(&inst->prim, sizeof(FeatHead) * (maxf + 1)));
+  CU_TRY(cudaMalloc(&inst->ori, sizeof(float) * (maxf + 1) * inst->ori_stride));
+  CU_TRY(cudaMalloc(&inst->n_ori, sizeof(uint32_t) * (maxf + 1)));
+  CU_TRY(cudaMalloc(&inst->feat_src, sizeof(uint32_t) * (maxf + 1)));
+  CU_TRY(cudaMalloc(&inst->d_aos, sizeof(vksift_Feature) * maxf));
+  CU_TRY(cudaMalloc(&inst->d_matches, sizeof(vksift_Match_2NN) * maxf));
+  CU_TRY(match_workspace_create(&inst->match_ws, c.max_nb_sift_per_buffer));
+
+  inst->buffers.resize(c.sift_buffer_count);
+  for (auto &fb : inst->buffers)
+  {
+    /* +256 rows: the matcher's TMA boxes and |b|^2 loads may run past the last feature */
+    CU_TRY(cudaMalloc(&fb.heads, sizeof(FeatHead) * (maxf + 256)));
+    CU_TRY(cudaMalloc(&fb.desc, 128 * (maxf + 256)));
+    CU_TRY(cudaMemset(fb.desc, 0, 128 * (maxf + 256)));
+    CU_TRY(cudaMalloc(&fb.cnt, sizeof(DetectCounters)));
+    CU_TRY(cudaMemset(fb.cnt, 0, sizeof(DetectCounters)));
+    CU_TRY(cudaHostAlloc(&fb.host_counts, sizeof(uint32_t) * (1 + 2 * VKS_MAX_OCT), cudaHostAllocMapped));
+    memset(fb.host_counts, 0, sizeof(uint32_t) * (1 + 2 * VKS_MAX_OCT));
+    CU_TRY(cudaHostGetDevicePointer(&fb.host_counts_dev, fb.host_counts, 0));
+  }
+  /* default resolution = square of the maximum size (sift_memory.c:637-640) */
+  if (!set_resolution(inst, side, side))
+    return false;
+  for (auto &fb : inst->buffers)
+    update_buffer_sections(inst, fb);
+  return true;
+}
+
+/* enqueue the whole detection pipeline (sift_detector.c:1369-1393) */
+bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t buf)
+{
+  FeatureBuffer &fb = inst->buffers[buf];
+  cudaStream_t st = inst->stream;
+  DetectParams P;
+  fill_detect_params(inst, fb, &P);
+  const bool prof = inst->profiling;
+
+  if (prof)
+    CU_TRY(cudaEventRecord(inst->ev[EV_D0], st));
+  CU_TRY(cudaMemsetAsync(fb.cnt, 0, sizeof(DetectCounters), st));
+  for (BlurStep &step : inst->steps)
+  {
+    for (int i = 0; i < step.n_pass; i++)
+      if (step.pass[i].src_kind != BLUR_SRC_LAYER)
+        step.pass[i].src = d_image;
+    CU_TRY(launch_blur_step(step, st));
+    inst->launches++;
+  }
+  if (prof)
+    CU_TRY(cudaEventRecord(inst->ev[EV_D1], st));
+  for (int o = 0; o < P.n_oct; o++)
+  {
+    CU_TRY(launch_extrema(P, o, inst->cand, fb.cnt, st));
+    inst->launches++;
+  }
+  CU_TRY(launch_order_primaries(P, inst->cand, fb.cnt, inst->prim, st));
+  inst->launches++;
+  if (prof)
+    CU_TRY(cudaEventRecord(inst->ev[EV_D2], st));
+  CU_TRY(launch_orientation(P, fb.cnt, inst->prim, inst->ori, inst->n_ori, st));
+  inst->launches++;
+  if (prof)
+    CU_TRY(cudaEventRecord(inst->ev[EV_D3], st));
+  CU_TRY(launch_assemble(P, fb.cnt, inst->n_ori, inst->feat_src, fb.host_counts_dev, st));
+  CU_TRY(launch_descriptors(P, fb.cnt, inst->prim, inst->ori, inst->feat_src, fb.heads, fb.desc, st));
+  inst->launches += 2;
+  if (prof)
+  {
+    CU_TRY(cudaEventRecord(inst->ev[EV_D4], st));
+    inst->ev_detect_valid = true;
+  }
+  CU_TRY(cudaEventRecord(inst->ev_detect_done, st));
+  inst->detect_pending = true;
+  inst->detect_buffer = buf;
+  fb.uploaded = false;
+  return true;
+}
+
+bool detect_common(vksift_Instance inst, const uint8_t *host_image, const uint8_t *dev_image, uint32_t w, uint32_t h, uint32_t buf)
+{
+  /* a running detection or matching pipeline is waited for first (vulkansift.c:325-327) */
+  wait_pipelines(inst, true, true);
+  /* vksift_prepareSiftMemoryForDetection (sift_memory.c:891-955) */
+  if (inst->cur_w != w || inst->cur_h != h)
+  {
+    if (!set_resolution(inst, w, h))
+      return false;
+  }
+  FeatureBuffer &fb = inst->buffers[buf];
+  if (fb.cur_w != inst->cur_w || fb.cur_h != inst->cur_h)
+    update_buffer_sections(inst, fb);
+  const uint8_t *src = dev_image;
+  if (host_image)
+  {
+    memcpy(inst->h_image, host_image, (size_t)w * h); /* the caller's buffer is free after return */
+    CU_TRY(cudaMemcpyAsync(inst->d_image, inst->h_image, (size_t)w * h, cudaMemcpyHostToDevice, inst->stream));
+    src = inst->d_image;
+  }
+  return enqueue_detection(inst, src, buf);
+}
+
+} // namespace
+
+/* =========================================================================== */
+extern "C"
+{
+
+  vksift_Config vksift_getDefaultConfig()
+  {
+    /* vulkansift.c:47-64 */
+    vksift_Config c;
+    memset(&c, 0, sizeof(c));
+    c.input_image_max_size = 1920u * 1080u;
+    c.sift_buffer_count = 2u;
+    c.max_nb_sift_per_buffer = 100000u;
+    c.use_input_upsampling = true;
+    c.nb_octaves = 0;
+    c.nb_scales_per_octave = 3u;
+    c.input_image_blur_level = 0.5f;
+    c.seed_scale_sigma = 1.6f;
+    c.intensity_threshold = 0.04f;
+    c.edge_threshold = 10.f;
+    c.max_nb_orientation_per_keypoint = 4;
+    c.descriptor_format = VKSIFT_DESCRIPTOR_FORMAT_UBC;
+    c.gpu_device_index = -1;
+    c.use_hardware_interpolated_blur = true;
+    c.pyramid_precision_mode = VKSIFT_PYRAMID_PRECISION_FLOAT32;
+    c.on_error_callback_function = default_error_callback;
+    c.use_gpu_debug_functions = false;
+    c.gpu_debug_external_window_info.context = NULL;
+    c.gpu_debug_external_window_info.window = NULL;
+    return c;
+  }
+
+  vksift_Result vksift_loadVulkan()
+  {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+    {
+      LOGE(TAG, "vksift_loadVulkan() failure: no CUDA device available (%s).", cudaGetErrorName(e));
+      cudaGetLastError();
+      return VKSIFT_VULKAN_ERROR;
+    }
+    bool any_sm100 = false;
+    for (int i = 0; i < n; i++)
+    {
+      int major = 0;
+      cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i);
+      any_sm100 |= (major == 10);
+    }
+    if (!any_sm100)
+    {
+      LOGE(TAG, "vksift_loadVulkan() failure: this build only carries sm_100a (NVIDIA B200) kernels and no such device is visible.");
+      return VKSIFT_VULKAN_ERROR;
+    }
+    g_api_loaded = true;
+    LOGI(TAG, "vksift_loadVulkan() success (CUDA runtime, %d device(s))", n);
+    return VKSIFT_SUCCESS;
+  }
+
+  void vksift_unloadVulkan() { g_api_loaded = false; }
+
+  void vksift_getAvailableGPUs(uint32_t *gpu_count, VKSIFT_GPU_NAME *gpu_names)
+  {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+      cudaGetLastError();
+      n = 0;
+    }
+    if (gpu_names == NULL)
+    {
+      *gpu_count = (uint32_t)n;
+      return;
+    }
+    for (uint32_t i = 0; i < *gpu_count && i < (uint32_t)n; i++)
+    {
+      cudaDeviceProp prop;
+      memset(gpu_names[i], 0, sizeof(VKSIFT_GPU_NAME));
+      if (cudaGetDeviceProperties(&prop, (int)i) == cudaSuccess)
+        strncpy(gpu_names[i], prop.name, sizeof(VKSIFT_GPU_NAME) - 1);
+    }
+  }
+
+  void vksift_setLogLevel(const vksift_LogLevel level)
+  {
+    switch (level)
+    {
+    case VKSIFT_NO_LOG:
+    case VKSIFT_LOG_ERROR:
+    case VKSIFT_LOG_WARNING:
+    case VKSIFT_LOG_INFO:
+    case VKSIFT_LOG_DEBUG:
+      g_log_level = (int)level;
+      break;
+    default:
+      LOGE(TAG, "vksift_LogLevel in vksift_setLogLevel() is not handled");
+      break;
+    }
+  }
+
+  vksift_Result vksift_createInstance(vksift_Instance *instance_ptr, const vksift_Config *config)
+  {
+    assert(instance_ptr != NULL);
+    assert(*instance_ptr == NULL);
+    assert(config != NULL);
+    if (!g_api_loaded)
+    {
+      LOGE(TAG, "vksift_createInstance() failure: GPU API not available. vksift_loadVulkan() must be called before using this function.");
+      return VKSIFT_VULKAN_ERROR;
+    }
+    if (!config_valid(config))
+    {
+      LOGE(TAG, "vksift_createInstance() failure: Invalid configuration detected.");
+      return VKSIFT_INVALID_INPUT_ERROR;
+    }
+    int n = 0;
+    cudaGetDeviceCount(&n);
+    int dev = config->gpu_device_index;
+    if (dev < 0)
+    {
+      /* automatic selection (vkenv/vulkan_device.c:394-494 scores devices): most SMs wins */
+      int best = -1, best_sms = -1;
+      for (int i = 0; i < n; i++)
+      {
+        int major = 0, sms = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, i);
+        if (major == 10 && sms > best_sms)
+        {
+          best = i;
+          best_sms = sms;
+        }
+      }
+      dev = best;
+    }
+    if (dev < 0 || dev >= n)
+    {
+      LOGE(TAG, "vksift_createInstance() failure: GPU device index %d is not available (%d device(s)).", config->gpu_device_index, n);
+      return VKSIFT_VULKAN_ERROR;
+    }
+    vksift_Instance inst = new vksift_Instance_T();
+    inst->cfg = *config;
+    inst->device = dev;
+    *instance_ptr = inst;
+    DeviceGuard g(dev);
+    if (!create_resources(inst))
+    {
+      LOGE(TAG, "vksift_createInstance() failure: Failed to setup the required device objects");
+      cudaGetLastError();
+      destroy_instance(inst);
+      *instance_ptr = NULL;
+      return VKSIFT_VULKAN_ERROR;
+    }
+    if (config->use_gpu_debug_functions)
+      LOGW(TAG, "use_gpu_debug_functions is accepted but has no effect: CUDA profilers need no frame delimiters.");
+    LOGI(TAG, "vksift_createInstance() success");
+    return VKSIFT_SUCCESS;
+  }
+
+  void vksift_destroyInstance(vksift_Instance *instance_ptr)
+  {
+    assert(instance_ptr != NULL);
+    assert(*instance_ptr != NULL);
+    destroy_instance(*instance_ptr);
+    *instance_ptr = NULL;
+  }
+
+  bool vksift_isBufferAvailable(vksift_Instance inst, const uint32_t gpu_buffer_id)
+  {
+    /* vulkansift.c:295-313 */
+    DeviceGuard g(inst->device);
+    if (inst->detect_pending && gpu_buffer_id == inst->detect_buffer)
+    {
+      if (cudaEventQuery(inst->ev_detect_done) == cudaErrorNotReady)
+        return false;
+      inst->detect_pending = false;
+    }
+    if (inst->match_pending && (gpu_buffer_id == inst->match_a || gpu_buffer_id == inst->match_b))
+    {
+      if (cudaEventQuery(inst->ev_match_done) == cudaErrorNotReady)
+        return false;
+      inst->match_pending = false;
+    }
+    return true;
+  }
+
+  void vksift_detectFeatures(vksift_Instance inst, const uint8_t *image_data, const uint32_t image_width, const uint32_t image_height,
+                             const uint32_t gpu_buffer_id)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id) || !resolution_valid(inst, image_width, image_height))
+    {
+      LOGE(TAG, "vksift_detectFeatures() error: invalid input.");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    bool ok;
+    {
+      DeviceGuard g(inst->device);
+      ok = detect_common(inst, image_data, nullptr, image_width, image_height, gpu_buffer_id);
+    }
+    if (!ok)
+    {
+      LOGE(TAG, "vksift_detectFeatures() error: Failed to start the detection pipeline.");
+      inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
+    }
+  }
+
+  void vksiftx_detectFeaturesDevice(vksift_Instance inst, const void *d_image, const uint32_t image_width, const uint32_t image_height,
+                                    const uint32_t gpu_buffer_id)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id) || !resolution_valid(inst, image_width, image_height) || d_image == NULL)
+    {
+      LOGE(TAG, "vksiftx_detectFeaturesDevice() error: invalid input.");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    bool ok;
+    {
+      DeviceGuard g(inst->device);
+      ok = detect_common(inst, nullptr, (const uint8_t *)d_image, image_width, image_height, gpu_buffer_id);
+    }
+    if (!ok)
+    {
+      LOGE(TAG, "vksiftx_detectFeaturesDevice() error: Failed to start the detection pipeline.");
+      inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
+    }
+  }
+
+  uint32_t vksift_getFeaturesNumber(vksift_Instance inst, const uint32_t gpu_buffer_id)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id))
+    {
+      LOGE(TAG, "vksift_getFeaturesNumber() error: invalid input.");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return 0;
+    }
+    DeviceGuard g(inst->device);
+    if (!vksift_isBufferAvailable(inst, gpu_buffer_id))
+      wait_pipelines(inst, true, true);
+    return buffer_count(inst, gpu_buffer_id, true);
+  }
+
+  void vksift_downloadFeatures(vksift_Instance inst, vksift_Feature *feats_ptr, const uint32_t gpu_buffer_id)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id))
+    {
+      LOGE(TAG, "vksift_downloadFeatures() error: invalid input.");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    bool ok = true;
+    {
+      DeviceGuard g(inst->device);
+      if (!vksift_isBufferAvailable(inst, gpu_buffer_id))
+        wait_pipelines(inst, true, true);
+      FeatureBuffer &fb = inst->buffers[gpu_buffer_id];
+      const uint32_t n = buffer_count(inst, gpu_buffer_id, false);
+      if (n > 0)
+      {
+        auto run = [&]() -> bool {
+          CU_TRY(launch_pack_aos(fb.heads, fb.desc, n, inst->d_aos, inst->stream));
+          inst->launches++;
+          CU_TRY(cudaMemcpyAsync(feats_ptr, inst->d_aos, sizeof(vksift_Feature) * (size_t)n, cudaMemcpyDeviceToHost, inst->stream));
+          CU_TRY(cudaStreamSynchronize(inst->stream));
+          return true;
+        };
+        ok = run();
+      }
+    }
+    if (!ok)
+    {
+      LOGE(TAG, "vksift_downloadFeatures() error when downloading detection results.");
+      inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
+    }
+  }
+
+  void vksift_uploadFeatures(vksift_Instance inst, const vksift_Feature *feats_ptr, const uint32_t nb_feats, const uint32_t gpu_buffer_id)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id) || nb_feats > inst->cfg.max_nb_sift_per_buffer)
+    {
+      if (nb_feats > inst->cfg.max_nb_sift_per_buffer)
+        LOGE(TAG, "Provided features count (%u) is greater than the configured maximum number of features per GPU buffer size (%u).", nb_feats,
+             inst->cfg.max_nb_sift_per_buffer);
+      LOGE(TAG, "vksift_uploadFeatures() error: invalid input.");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    bool ok = true;
+    {
+      DeviceGuard g(inst->device);
+      if (!vksift_isBufferAvailable(inst, gpu_buffer_id))
+        wait_pipelines(inst, true, true);
+      FeatureBuffer &fb = inst->buffers[gpu_buffer_id];
+      auto run = [&]() -> bool {
+        if (nb_feats > 0)
+        {
+          CU_TRY(cudaMemcpyAsync(inst->d_aos, feats_ptr, sizeof(vksift_Feature) * (size_t)nb_feats, cudaMemcpyHostToDevice, inst->stream));
+          CU_TRY(launch_unpack_aos(inst->d_aos, nb_feats, fb.heads, fb.desc, inst->stream));
+          inst->launches++;
+        }
+        CU_TRY(cudaStreamSynchronize(inst->stream)); /* blocking transfer, feats_ptr is free after return */
+        return true;
+      };
+      ok = run();
+      if (ok)
+      {
+        fb.uploaded = true;
+        fb.n_uploaded = nb_feats;
+      }
+    }
+    if (!ok)
+    {
+      LOGE(TAG, "vksift_uploadFeatures() error when uploading SIFT features to GPU memory.");
+      inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
+    }
+  }
+
+  void vksiftx_uploadDescriptorsDevice(vksift_Instance inst, const void *d_descriptors, const uint32_t nb_feats, const uint32_t gpu_buffer_id)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id) || nb_feats > inst->cfg.max_nb_sift_per_buffer || (nb_feats > 0 && d_descriptors == NULL))
+    {
+      LOGE(TAG, "vksiftx_uploadDescriptorsDevice() error: invalid input.");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    bool ok = true;
+    {
+      DeviceGuard g(inst->device);
+      if (!vksift_isBufferAvailable(inst, gpu_buffer_id))
+        wait_pipelines(inst, true, true);
+      FeatureBuffer &fb = inst->buffers[gpu_buffer_id];
+      auto run = [&]() -> bool {
+        if (nb_feats > 0)
+        {
+          CU_TRY(cudaMemcpyAsync(fb.desc, d_descriptors, 128 * (size_t)nb_feats, cudaMemcpyDeviceToDevice, inst->stream));
+          CU_TRY(cudaMemsetAsync(fb.heads, 0, sizeof(FeatHead) * (size_t)nb_feats, inst->stream));
+        }
+        CU_TRY(cudaStreamSynchronize(inst->stream));
+        return true;
+      };
+      ok = run();
+      if (ok)
+      {
+        fb.uploaded = true;
+        fb.n_uploaded = nb_feats;
+      }
+    }
+    if (!ok)
+    {
+      LOGE(TAG, "vksiftx_uploadDescriptorsDevice() error when copying descriptors.");
+      inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
+    }
+  }
+
+  void vksift_matchFeatures(vksift_Instance inst, const uint32_t gpu_buffer_id_A, const uint32_t gpu_buffer_id_B)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id_A) || !buffer_idx_valid(inst, gpu_buffer_id_B))
+    {
+      LOGE(TAG, "vksift_matchFeatures() error: invalid input.");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    bool ok = true, invalid = false;
+    {
+      DeviceGuard g(inst->device);
+      wait_pipelines(inst, true, true); /* vulkansift.c:427-428 */
+      const uint32_t na = buffer_count(inst, gpu_buffer_id_A, false);
+      const uint32_t nb = buffer_count(inst, gpu_buffer_id_B, false);
+      if (nb < 2 && na > 0)
+      {
+        /* the shader reads B[0] and B[1] unconditionally (Get2NearestNeighbors.comp:66-67), SURVEY B-D13 */
+        LOGE(TAG, "vksift_matchFeatures() error: buffer B holds %u feature(s), the 2-nearest-neighbour search needs at least 2.", nb);
+        invalid = true;
+      }
+      else
+      {
+        inst->nb_matches = na; /* sift_memory.c:1056 */
+        FeatureBuffer &A = inst->buffers[gpu_buffer_id_A], &B = inst->buffers[gpu_buffer_id_B];
+        auto run = [&]() -> bool {
+          const bool prof = inst->profiling;
+          if (prof)
+            CU_TRY(cudaEventRecord(inst->ev[EV_M0], inst->stream));
+          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, B.desc, nb, inst->d_matches, inst->stream,
+                              prof ? inst->ev[EV_M1] : nullptr, &inst->launches));
+          if (prof)
+          {
+            if (na == 0)
+              CU_TRY(cudaEventRecord(inst->ev[EV_M1], inst->stream));
+            CU_TRY(cudaEventRecord(inst->ev[EV_M2], inst->stream));
+            inst->ev_match_valid = true;
+          }
+          CU_TRY(cudaEventRecord(inst->ev_match_done, inst->stream));
+          return true;
+        };
+        ok = run();
+        inst->match_pending = ok;
+        inst->match_a = gpu_buffer_id_A;
+        inst->match_b = gpu_buffer_id_B;
+      }
+    }
+    if (invalid)
+    {
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    if (!ok)
+    {
+      LOGE(TAG, "vksift_matchFeatures() error: Failed to start the matching pipeline.");
+      inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
+    }
+  }
+
+  uint32_t vksift_getMatchesNumber(vksift_Instance inst) { return inst->nb_matches; }
+
+  void vksift_downloadMatches(vksift_Instance inst, vksift_Match_2NN *matches)
+  {
+    bool ok = true;
+    {
+      DeviceGuard g(inst->device);
+      wait_pipelines(inst, false, true);
+      if (inst->nb_matches > 0)
+      {
+        auto run = [&]() -> bool {
+          CU_TRY(cudaMemcpyAsync(matches, inst->d_matches, sizeof(vksift_Match_2NN) * (size_t)inst->nb_matches, cudaMemcpyDeviceToHost, inst->stream));
+          CU_TRY(cudaStreamSynchronize(inst->stream));
+          return true;
+        };
+        ok = run();
+      }
+    }
+    if (!ok)
+    {
+      LOGE(TAG, "vksift_downloadMatches() error when downloading SIFT matches from GPU memory.");
+      inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
+    }
+  }
+
+  /* ---- scale-space access (vulkansift.c:463-519) --------------------------- */
+  uint8_t vksift_getScaleSpaceNbOctaves(vksift_Instance inst) { return (uint8_t)inst->pyr.n_oct; }
+
+  void vksift_getScaleSpaceOctaveResolution(vksift_Instance inst, const uint8_t octave, uint32_t *octave_images_width, uint32_t *octave_images_height)
+  {
+    if (octave >= inst->pyr.n_oct)
+    {
+      LOGE(TAG, "vksift_getScaleSpaceOctaveResolution() error: invalid input. Requested octave idx is %d but the current number of octave is %d", octave,
+           inst->pyr.n_oct);
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    *octave_images_width = inst->pyr.w[octave];
+    *octave_images_height = inst->pyr.h[octave];
+  }
+
+  static void download_layer(vksift_Instance inst, const uint8_t octave, const uint8_t scale, bool dog, float *out, const char *fn)
+  {
+    const uint32_t nscales = inst->cfg.nb_scales_per_octave + (dog ? 2u : 3u);
+    if (octave >= inst->pyr.n_oct || scale >= nscales)
+    {
+      if (octave >= inst->pyr.n_oct)
+        LOGE(TAG, "Requested octave idx is %d but the current number of octaves is %d", octave, inst->pyr.n_oct);
+      else
+        LOGE(TAG, "Requested scale idx is %d but the number of %s scales is %d", scale, dog ? "DoG" : "blurred", nscales);
+      LOGE(TAG, "%s() error: invalid input.", fn);
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    bool ok = true;
+    {
+      DeviceGuard g(inst->device);
+      wait_pipelines(inst, true, false);
+      const Pyramid &p = inst->pyr;
+      const size_t layer = (size_t)p.pitch[octave] * p.h[octave];
+      const float *src = (dog ? p.D[octave] : p.G[octave]) + layer * scale;
+      auto run = [&]() -> bool {
+        CU_TRY(cudaMemcpy2DAsync(out, sizeof(float) * p.w[octave], src, sizeof(float) * p.pitch[octave], sizeof(float) * p.w[octave], p.h[octave],
+                                 cudaMemcpyDeviceToHost, inst->stream));
+        CU_TRY(cudaStreamSynchronize(inst->stream));
+        return true;
+      };
+      ok = run();
+    }
+    if (!ok)
+    {
+      LOGE(TAG, "%s() error when downloading a pyramid image from GPU memory.", fn);
+      inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
+    }
+  }
+
+  void vksift_downloadScaleSpaceImage(vksift_Instance inst, const uint8_t octave, const uint8_t scale, float *blurred_image)
+  {
+    download_layer(inst, octave, scale, false, blurred_image, "vksift_downloadScaleSpaceImage");
+  }
+  void vksift_downloadDoGImage(vksift_Instance inst, const uint8_t octave, const uint8_t scale, float *dog_image)
+  {
+    download_layer(inst, octave, scale, true, dog_image, "vksift_downloadDoGImage");
+  }
+
+  void vksift_presentDebugFrame(vksift_Instance inst)
+  {
+    (void)inst;
+    LOGW(TAG, "vksift_presentDebugFrame() was called but this build has no debug presenter (use ncu / compute-sanitizer instead).");
+  }
+
+  /* ---- extensions (include/vksift_b200_ext.h) ------------------------------ */
+  const char *vksiftx_getVersionString() { return "vulkansift-b200 0.1 sm_100a"; }
+  int32_t vksiftx_getDeviceIndex(vksift_Instance inst) { return inst->device; }
+  void *vksiftx_getStream(vksift_Instance inst) { return (void *)inst->stream; }
+
+  void vksiftx_waitIdle(vksift_Instance inst)
+  {
+    DeviceGuard g(inst->device);
+    wait_pipelines(inst, true, true);
+    cudaStreamSynchronize(inst->stream);
+  }
+
+  void vksiftx_getBufferDeviceView(vksift_Instance inst, const uint32_t gpu_buffer_id, uint32_t *nb_feats, void **d_descriptors, void **d_heads)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id))
+    {
+      LOGE(TAG, "vksiftx_getBufferDeviceView() error: invalid input.");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    DeviceGuard g(inst->device);
+    if (!vksift_isBufferAvailable(inst, gpu_buffer_id))
+      wait_pipelines(inst, true, true);
+    if (nb_feats)
+      *nb_feats = buffer_count(inst, gpu_buffer_id, false);
+    if (d_descriptors)
+      *d_descriptors = inst->buffers[gpu_buffer_id].desc;
+    if (d_heads)
+      *d_heads = inst->buffers[gpu_buffer_id].heads;
+  }
+
+  void *vksiftx_getMatchesDevice(vksift_Instance inst) { return inst->d_matches; }
+
+  void vksiftx_setProfiling(vksift_Instance inst, const bool enabled) { inst->profiling = enabled; }
+
+  void vksiftx_getStageTimesMs(vksift_Instance inst, float *t)
+  {
+    DeviceGuard g(inst->device);
+    wait_pipelines(inst, true, true);
+    for (int i = 0; i < VKSIFTX_NB_STAGES; i++)
+      t[i] = 0.f;
+    if (inst->ev_detect_valid)
+    {
+      cudaEventSynchronize(inst->ev[EV_D4]);
+      cudaEventElapsedTime(&t[0], inst->ev[EV_D0], inst->ev[EV_D1]);
+      cudaEventElapsedTime(&t[1], inst->ev[EV_D1], inst->ev[EV_D2]);
+      cudaEventElapsedTime(&t[2], inst->ev[EV_D2], inst->ev[EV_D3]);
+      cudaEventElapsedTime(&t[3], inst->ev[EV_D3], inst->ev[EV_D4]);
+      cudaEventElapsedTime(&t[4], inst->ev[EV_D0], inst->ev[EV_D4]);
+    }
+    if (inst->ev_match_valid)
+    {
+      cudaEventSynchronize(inst->ev[EV_M2]);
+      cudaEventElapsedTime(&t[5], inst->ev[EV_M0], inst->ev[EV_M1]);
+      cudaEventElapsedTime(&t[6], inst->ev[EV_M1], inst->ev[EV_M2]);
+      cudaEventElapsedTime(&t[7], inst->ev[EV_M0], inst->ev[EV_M2]);
+    }
+  }
+
+  uint64_t vksiftx_getKernelLaunchCount(vksift_Instance inst) { return inst->launches; }
+
+  void vksiftx_getEffectiveTaps(vksift_Instance inst, uint32_t *radius, float *taps)
+  {
+    const int n = inst->cfg.nb_scales_per_octave + 3;
+    for (int s = 0; s < n; s++)
+    {
+      radius[s] = inst->scales.radius[s];
+      memcpy(taps + s * VKS_MAX_TAPS, inst->scales.taps[s], sizeof(float) * VKS_MAX_TAPS);
+    }
+  }
+
+  void vksiftx_getSectionCapacities(vksift_Instance inst, const uint32_t gpu_buffer_id, uint32_t *caps)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id))
+    {
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    const FeatureBuffer &fb = inst->buffers[gpu_buffer_id];
+    for (uint32_t o = 0; o < fb.n_oct; o++)
+      caps[o] = fb.cap[o];
+  }
+
+  void vksiftx_setMatcherImpl(vksift_Instance inst, const int32_t impl) { inst->matcher_impl = impl; }
+
+} /* extern "C" */

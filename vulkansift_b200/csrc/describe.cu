@@ -1,0 +1,478 @@
+/*
+ * describe.cu -- orientation assignment, feature assembly and 4x4x8 descriptors.
+ *
+ *   orientation_kernel  <- shaders/ComputeOrientation.comp:52-186 (one warp per keypoint)
+ *   assemble_kernel     <- the atomicAdd appends of ComputeOrientation.comp:170-183 made
+ *                          deterministic: primaries first, extra orientations after them in
+ *                          (parent, bin) order, sections clamped like
+ *                          sift_memory.c:1083-1095, output packed in octave order like
+ *                          sift_memory.c:1128-1146
+ *   descriptor_kernel   <- shaders/ComputeDescriptors.comp:84-274 (one CTA per feature)
+ *
+ * Histograms are accumulated in uint32 fixed point exactly like the shaders,
+ * so the result does not depend on the order of the shared-memory atomics.
+ */
+#include "vksift_internal.h"
+
+namespace vks
+{
+
+/* imageLoad on the Gaussian array, out of bounds -> 0 (SURVEY B-D3) */
+__device__ __forceinline__ float gauss_at(const float *__restrict__ L, int w, int h, int pitch, int x, int y)
+{
+  if (x < 0 || x >= w || y < 0 || y >= h)
+    return 0.f;
+  return __ldg(L + (size_t)y * pitch + x);
+}
+
+/* ---- orientation --------------------------------------------------------- */
+#define ORI_WARPS 4
+#define ORI_MAX_BOX 33 /* 2*floor(4.5*sigma')+1 with sigma' < 3.6 */
+
+__global__ void __launch_bounds__(ORI_WARPS * 32) orientation_kernel(const __grid_constant__ DetectParams P, const DetectCounters *__restrict__ cnt,
+                                                                      const FeatHead *__restrict__ prim, float *__restrict__ ori,
+                                                                      uint32_t *__restrict__ n_ori)
+{
+  __shared__ uint32_t s_hist[ORI_WARPS][36];
+  __shared__ uint32_t s_tmp[ORI_WARPS][36];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  uint32_t *hist = s_hist[wi], *tmp = s_tmp[wi];
+
+  uint32_t total = 0;
+  for (int o = 0; o < P.n_oct; o++)
+    total += cnt->n_prim[o];
+  const uint32_t n_warps = gridDim.x * ORI_WARPS;
+  for (uint32_t item = blockIdx.x * ORI_WARPS + wi; item < total; item += n_warps)
+  {
+    /* item -> (octave, index in section) */
+    int o = 0;
+    uint32_t idx = item;
+    while (idx >= cnt->n_prim[o])
+    {
+      idx -= cnt->n_prim[o];
+      o++;
+    }
+    const uint32_t slot = P.sec_off[o] + idx;
+    const FeatHead kp = prim[slot];
+    const OctaveView &ov = P.oct[o];
+    const float *__restrict__ L = ov.G + (size_t)kp.scale_idx * ov.layer_stride;
+
+    const float sf = vks_pow2i(kp.octave_idx);
+    const float lambda = 1.5f * (kp.sigma / sf);
+    const int r = (int)floorf(3 * lambda);
+    const float es = -1.f / (2.f * lambda * lambda);
+    const int box = 2 * r + 1;
+
+    /* ComputeOrientation.comp:75-81: M = sum_{i,j} exp(es*(i*i+j*j))*sqrt(2), accumulated in
+     * (i outer, j inner) order in fp32.  Lanes evaluate the terms of one row, then one
+     * sequential add chain per row keeps the reference summation order. */
+    float m = 0.f;
+    for (int i = -r; i <= r; i++)
+    {
+      for (int j0 = -r; j0 <= r; j0 += 32)
+      {
+        const int j = j0 + lane;
+        float term = 0.f;
+        if (j <= r)
+          term = vks_expf(es * (float)((i * i) + (j * j))) * VKS_SQRT2_F;
+        const int cntj = min(32, r - j0 + 1);
+        for (int k = 0; k < cntj; k++)
+          m += __shfl_sync(0xffffffffu, term, k);
+      }
+    }
+    const float fp = (float)(1u << (uint32_t)(30 - vks_ceil_log2(m)));
+
+    hist[lane] = 0;
+    if (lane < 4)
+      hist[32 + lane] = 0;
+    __syncwarp();
+
+    const float rsx = vks_rint(kp.scale_x), rsy = vks_rint(kp.scale_y);
+    const int cx = (int)rsx, cy = (int)rsy;
+    const float r2 = (float)(r * r);
+    for (int pix = lane; pix < box * box; pix += 32)
+    {
+      const int dy = pix / box - r, dx = pix % box - r;
+      const int gx = cx + dx, gy = cy + dy;
+      const float sdx = (rsx + (float)dx) - kp.scale_x;
+      const float sdy = (rsy + (float)dy) - kp.scale_y;
+      const float d2 = (sdx * sdx) + (sdy * sdy);
+      if ((gx < 1 || gx >= (ov.w - 1) || gy < 1 || gy >= (ov.h - 1)) && (d2 > r2))
+        continue;
+      const float gX = 0.5f * (gauss_at(L, ov.w, ov.h, ov.pitch, gx + 1, gy) - gauss_at(L, ov.w, ov.h, ov.pitch, gx - 1, gy));
+      const float gY = 0.5f * (gauss_at(L, ov.w, ov.h, ov.pitch, gx, gy + 1) - gauss_at(L, ov.w, ov.h, ov.pitch, gx, gy - 1));
+      const float mag = vks_expf(d2 * es) * vks_sqrt((gX * gX) + (gY * gY));
+      float th = vks_atan2f(gY, gX);
+      if (th < 0.f)
+        th += VKS_TWO_PI_F;
+      else if (th > VKS_TWO_PI_F)
+        th -= VKS_TWO_PI_F;
+      int bin = (int)((th * 36.f) / VKS_TWO_PI_F);
+      if (bin < 0)
+        bin += 36;
+      else if (bin >= 36)
+        bin -= 36;
+      atomicAdd(&hist[bin], (uint32_t)(mag * fp));
+    }
+    __syncwarp();
+
+    /* :130-147 three double box smoothings in uint/float mixed arithmetic */
+    for (int it = 0; it < 3; it++)
+    {
+      for (int i = lane; i < 36; i += 32)
+        tmp[i] = (uint32_t)((float)(hist[(i + 35) % 36] + hist[i] + hist[(i + 1) % 36]) / 3.f);
+      __syncwarp();
+      for (int i = lane; i < 36; i += 32)
+        hist[i] = (uint32_t)((float)(tmp[(i + 35) % 36] + tmp[i] + tmp[(i + 1) % 36]) / 3.f);
+      __syncwarp();
+    }
+    uint32_t mx = hist[lane];
+    if (lane < 4)
+      mx = max(mx, hist[32 + lane]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+
+    /* :156-183 peaks in increasing bin order */
+    uint32_t count = 0;
+    float *my_ori = ori + (size_t)slot * P.ori_stride;
+    for (int base = 0; base < 36; base += 32)
+    {
+      const int i = base + lane;
+      bool peak = false;
+      float theta = 0.f;
+      if (i < 36)
+      {
+        const uint32_t hp = hist[(i + 35) % 36], hn = hist[(i + 1) % 36], hc = hist[i];
+        if (((float)hc >= (0.8f * (float)mx)) && (hc > hp) && (hc > hn))
+        {
+          peak = true;
+          /* uint32 differences wrap before the conversion (SURVEY B-D12) */
+          const float num = (float)(uint32_t)(hp - hn);
+          const float den = (float)(uint32_t)(hp - (2u * hc) + hn);
+          const float fi = (float)i + 0.5f * (num / den);
+          theta = ((fi + 0.5f) * VKS_TWO_PI_F) / 36.f;
+        }
+      }
+      const uint32_t mask = __ballot_sync(0xffffffffu, peak);
+      if (peak)
+      {
+        const uint32_t k = count + __popc(mask & ((1u << lane) - 1u));
+        if (k < P.ori_stride)
+          my_ori[k] = theta;
+      }
+      count += __popc(mask);
+    }
+    if (lane == 0)
+    {
+      if (count == 0)
+        my_ori[0] = 0.f; /* no peak: orientation stays 0 and the keypoint is still described */
+      n_ori[slot] = count;
+    }
+    __syncwarp();
+  }
+}
+
+cudaError_t launch_orientation(const DetectParams &P, DetectCounters *cnt, const FeatHead *prim, float *ori, uint32_t *n_ori, cudaStream_t st)
+{
+  orientation_kernel<<<148 * 4, ORI_WARPS * 32, 0, st>>>(P, cnt, prim, ori, n_ori);
+  return cudaGetLastError();
+}
+
+/* ---- assembly ------------------------------------------------------------ */
+#define ASM_THREADS 1024
+__device__ __forceinline__ uint32_t extra_orientations(uint32_t n, uint32_t max_ori)
+{
+  /* peak k >= 1 is appended iff max_ori == 0 || k < max_ori (ComputeOrientation.comp:175) */
+  if (n == 0)
+    return 0;
+  const uint32_t lim = (max_ori == 0) ? n : min(n, max_ori);
+  return lim - 1;
+}
+
+__global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(const __grid_constant__ DetectParams P, DetectCounters *__restrict__ cnt,
+                                                               const uint32_t *__restrict__ n_ori, uint32_t *__restrict__ feat_src,
+                                                               uint32_t *__restrict__ host_counts)
+{
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+  uint32_t out_off = 0;
+  for (int o = 0; o < P.n_oct; o++)
+  {
+    const uint32_t np = cnt->n_prim[o];
+    const uint32_t cap = P.cap[o];
+    const uint32_t sec = P.sec_off[o];
+    if (tid == 0)
+      s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < np; base += ASM_THREADS)
+    {
+      const uint32_t i = base + tid;
+      const uint32_t e = (i < np) ? extra_orientations(n_ori[sec + i], P.max_ori) : 0u;
+      /* block exclusive scan of e */
+      uint32_t v = e;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
+      {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d)
+          v += t;
+      }
+      if (lane == 31)
+        s_warp[wi] = v;
+      __syncthreads();
+      if (wi == 0)
+      {
+        uint32_t wv = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, wv, d);
+          if (lane >= d)
+            wv += t;
+        }
+        s_warp[lane] = wv;
+      }
+      __syncthreads();
+      const uint32_t carry = s_carry;
+      const uint32_t excl = carry + (wi ? s_warp[wi - 1] : 0u) + (v - e);
+      if (i < np)
+      {
+        /* primary slot i, extras at np + excl .. */
+        if (i < cap)
+          feat_src[out_off + i] = (i << 6);
+        for (uint32_t k = 0; k < e; k++)
+        {
+          const uint32_t slot = np + excl + k;
+          if (slot < cap)
+            feat_src[out_off + slot] = (i << 6) | (k + 1);
+        }
+      }
+      __syncthreads();
+      if (tid == ASM_THREADS - 1)
+        s_carry = carry + s_warp[31];
+      __syncthreads();
+    }
+    const uint32_t found = cnt->n_cand[o] + s_carry; /* counter semantics of nb_elem */
+    const uint32_t total = np + s_carry;
+    const uint32_t kept = min(total, cap);
+    if (tid == 0)
+    {
+      cnt->n_found[o] = found;
+      cnt->n_kept[o] = kept;
+      cnt->out_off[o] = out_off;
+      host_counts[1 + o] = found;
+      host_counts[1 + VKS_MAX_OCT + o] = kept;
+    }
+    out_off += kept;
+    __syncthreads();
+  }
+  if (tid == 0)
+  {
+    cnt->n_total = out_off;
+    host_counts[0] = out_off;
+  }
+}
+
+cudaError_t launch_assemble(const DetectParams &P, DetectCounters *cnt, const uint32_t *n_ori, uint32_t *feat_src, uint32_t *host_counts,
+                            cudaStream_t st)
+{
+  assemble_kernel<<<1, ASM_THREADS, 0, st>>>(P, cnt, n_ori, feat_src, host_counts);
+  return cudaGetLastError();
+}
+
+/* ---- descriptor ---------------------------------------------------------- */
+#define DESC_THREADS 128
+
+__global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_constant__ DetectParams P, const DetectCounters *__restrict__ cnt,
+                                                                  const FeatHead *__restrict__ prim, const float *__restrict__ ori,
+                                                                  const uint32_t *__restrict__ feat_src, FeatHead *__restrict__ out_heads,
+                                                                  uint8_t *__restrict__ out_desc)
+{
+  __shared__ uint32_t s_desc[128];
+  __shared__ uint32_t s_acc;
+  __shared__ float s_terms[DESC_THREADS];
+  __shared__ float s_m;
+  const int tid = threadIdx.x;
+  const uint32_t total = cnt->n_total;
+  for (uint32_t g = blockIdx.x; g < total; g += gridDim.x)
+  {
+    int o = 0;
+    while (o + 1 < P.n_oct && g >= cnt->out_off[o + 1])
+      o++;
+    const uint32_t src = feat_src[g];
+    const uint32_t pi = P.sec_off[o] + (src >> 6), k = src & 63u;
+    FeatHead kp = prim[pi];
+    kp.orientation = ori[(size_t)pi * P.ori_stride + k];
+    const OctaveView &ov = P.oct[o];
+    const float *__restrict__ L = ov.G + (size_t)kp.scale_idx * ov.layer_stride;
+
+    s_desc[tid] = 0;
+    const float sf = vks_pow2i(kp.octave_idx);
+    const float lambda = 3.0f * (kp.sigma / sf);
+    const float radius = VKS_SQRT2_F * lambda * 5.f * 0.5f;
+    const int R = (int)floorf(radius + 0.5f);
+    float sn, cs;
+    vks_sincosf(kp.orientation, &sn, &cs);
+    const float kc = cs / lambda, ks = sn / lambda;
+    const float es = -0.125f;
+
+    /* ComputeDescriptors.comp:116-124: fixed-point scale from the sequential sum
+     *   for i<R/2 { m += e(i,i)*sqrt2; for j in (i, R/2) m += e(i,j)*sqrt2*2 }
+     * terms evaluated in parallel per row i, summed in reference order by thread 0. */
+    const int hr = R / 2;
+    float m = 0.f;
+    for (int i = 0; i < hr; i++)
+    {
+      for (int j0 = i; j0 < hr; j0 += DESC_THREADS)
+      {
+        const int j = j0 + tid;
+        if (j < hr)
+        {
+          float t = vks_expf(es * (float)((i * i) + (j * j))) * VKS_SQRT2_F;
+          if (j > i)
+            t = t * 2.f;
+          s_terms[tid] = t;
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+          const int c = min(DESC_THREADS, hr - j0);
+          for (int q = 0; q < c; q++)
+            m += s_terms[q];
+        }
+        __syncthreads();
+      }
+    }
+    if (tid == 0)
+      s_m = m;
+    __syncthreads();
+    m = s_m;
+    const float fp = (float)(1u << (uint32_t)(16 - vks_ceil_log2(m)));
+
+    const float rsx = vks_rint(kp.scale_x), rsy = vks_rint(kp.scale_y);
+    const int cx = (int)rsx, cy = (int)rsy;
+    const int box = 2 * R + 1;
+    for (int pix = tid; pix < box * box; pix += DESC_THREADS)
+    {
+      const int dy = pix / box - R, dx = pix % box - R;
+      const int ix = cx + dx, iy = cy + dy;
+      if (ix < 1 || ix >= (ov.w - 1) || iy < 1 || iy >= (ov.h - 1))
+        continue;
+      const float sdx = (rsx + (float)dx) - kp.scale_x;
+      const float sdy = (rsy + (float)dy) - kp.scale_y;
+      const float ox = kc * sdx + ks * sdy;
+      const float oy = kc * sdy - ks * sdx;
+      const float *__restrict__ c = L + (size_t)iy * ov.pitch + ix;
+      const float gX = 0.5f * (__ldg(c + 1) - __ldg(c - 1));
+      const float gY = 0.5f * (__ldg(c + ov.pitch) - __ldg(c - ov.pitch));
+      float th = vks_atan2f(gY, gX);
+      if (th < 0.f)
+        th += VKS_TWO_PI_F;
+      else if (th > VKS_TWO_PI_F)
+        th -= VKS_TWO_PI_F;
+      th = th - kp.orientation;
+      if (th < 0.f)
+        th += VKS_TWO_PI_F;
+      else if (th > VKS_TWO_PI_F)
+        th -= VKS_TWO_PI_F;
+      const float mag = vks_expf(es * ((ox * ox) + (oy * oy))) * vks_sqrt((gX * gX) + (gY * gY));
+      const float fx = ox + 2.f, fy = oy + 2.f;
+      const float fb = P.vlfeat ? ((th * 8.f) / VKS_TWO_PI_F) : ((-th * 8.f) / VKS_TWO_PI_F);
+      const int hx = (int)floorf(fx - 0.5f), hy = (int)floorf(fy - 0.5f), hb = (int)floorf(fb);
+      const float rx = fx - ((float)hx + 0.5f), ry = fy - ((float)hy + 0.5f), rb = fb - (float)hb;
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+          for (int q = 0; q < 2; q++)
+            if ((i + hx) >= 0 && (i + hx) < 4 && (j + hy) >= 0 && (j + hy) < 4)
+            {
+              const int b = (q + hb) & 7; /* non-negative modulo (SURVEY B-D7) */
+              const int idx = (j + hy) * 32 + (i + hx) * 8 + b;
+              const float val = fabsf(1.f - (float)i - rx) * fabsf(1.f - (float)j - ry) * fabsf(1.f - (float)q - rb) * mag;
+              atomicAdd(&s_desc[idx], (uint32_t)(val * fp));
+            }
+    }
+    if (tid == 0)
+      s_acc = 0;
+    __syncthreads();
+
+    /* :209-265 norm, clamp at 0.2, renorm, *512, truncate to u8 */
+    uint32_t v = s_desc[tid];
+    atomicAdd(&s_acc, v * v);
+    __syncthreads();
+    float norm = vks_sqrt((float)s_acc);
+    __syncthreads();
+    v = min(v, (uint32_t)(norm * 0.2f));
+    if (tid == 0)
+      s_acc = 0;
+    __syncthreads();
+    atomicAdd(&s_acc, v * v);
+    __syncthreads();
+    norm = vks_sqrt((float)s_acc);
+    const float d = (float)v * (512.f / norm);
+    uint32_t q8;
+    if (!(d == d))
+      q8 = 0;
+    else if (d > 255.f)
+      q8 = 255;
+    else
+      q8 = (uint32_t)d;
+    out_desc[(size_t)g * 128 + tid] = (uint8_t)q8;
+    if (tid == 0)
+      out_heads[g] = kp;
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_descriptors(const DetectParams &P, const DetectCounters *cnt, const FeatHead *prim, const float *ori, const uint32_t *feat_src,
+                               FeatHead *out_heads, uint8_t *out_desc, cudaStream_t st)
+{
+  descriptor_kernel<<<148 * 8, DESC_THREADS, 0, st>>>(P, cnt, prim, ori, feat_src, out_heads, out_desc);
+  return cudaGetLastError();
+}
+
+/* ---- AoS <-> SoA for host transfers (vksift_Feature = 36 B head + 128 B descriptor) */
+__global__ void pack_aos_kernel(const FeatHead *__restrict__ heads, const uint8_t *__restrict__ desc, uint32_t n, uint32_t *__restrict__ aos)
+{
+  /* 41 words per feature: 9 head + 32 descriptor */
+  const size_t total = (size_t)n * 41;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const uint32_t f = (uint32_t)(i / 41), wv = (uint32_t)(i % 41);
+    aos[i] = (wv < 9) ? ((const uint32_t *)heads)[(size_t)f * 9 + wv] : ((const uint32_t *)desc)[(size_t)f * 32 + (wv - 9)];
+  }
+}
+__global__ void unpack_aos_kernel(const uint32_t *__restrict__ aos, uint32_t n, FeatHead *__restrict__ heads, uint8_t *__restrict__ desc)
+{
+  const size_t total = (size_t)n * 41;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const uint32_t f = (uint32_t)(i / 41), wv = (uint32_t)(i % 41);
+    if (wv < 9)
+      ((uint32_t *)heads)[(size_t)f * 9 + wv] = aos[i];
+    else
+      ((uint32_t *)desc)[(size_t)f * 32 + (wv - 9)] = aos[i];
+  }
+}
+cudaError_t launch_pack_aos(const FeatHead *heads, const uint8_t *desc, uint32_t n, uint8_t *aos, cudaStream_t st)
+{
+  if (n == 0)
+    return cudaSuccess;
+  const int blocks = (int)min((size_t)148 * 8, ((size_t)n * 41 + 255) / 256);
+  pack_aos_kernel<<<blocks, 256, 0, st>>>(heads, desc, n, (uint32_t *)aos);
+  return cudaGetLastError();
+}
+cudaError_t launch_unpack_aos(const uint8_t *aos, uint32_t n, FeatHead *heads, uint8_t *desc, cudaStream_t st)
+{
+  if (n == 0)
+    return cudaSuccess;
+  const int blocks = (int)min((size_t)148 * 8, ((size_t)n * 41 + 255) / 256);
+  unpack_aos_kernel<<<blocks, 256, 0, st>>>((const uint32_t *)aos, n, heads, desc);
+  return cudaGetLastError();
+}
+
+} // namespace vks

@@ -1,0 +1,162 @@
+/*
+ * match.cu -- brute-force 2-nearest-neighbour search on 128-byte descriptors.
+ *
+ * Replaces shaders/Get2NearestNeighbors.comp:43-104 (dispatched by
+ * sift_matcher.c:246-279).  d(a,b)^2 = |a|^2 + |b|^2 - 2 a.b with exact integer
+ * arithmetic; the a.b term is a dense u8 x u8 -> s32 contraction.
+ *
+ * Tie rule of the shader (strict '<', b=0 and b=1 initialised specially,
+ * :69-96) == stable top-2 of B under the key (d, pos) with pos(0)=1, pos(1)=0,
+ * pos(b)=b.  Distances are compared as squared integers, which orders exactly
+ * like the shader's float sqrt while d^2 < 2^22 (|a-b| < 2048; SIFT descriptors
+ * have |a-b|^2 <= 2*512^2 < 2^20).
+ */
+#include "vksift_internal.h"
+
+#include "match_tc.cuh"
+
+namespace vks
+{
+
+struct MatchWorkspace
+{
+  uint32_t max_feats;
+  uint32_t *norm_a; /* |a|^2 per row */
+  uint32_t *norm_b;
+  unsigned long long *partial; /* [splits][na][2] packed (d2 << 32 | pos) keys */
+  uint32_t partial_splits;
+  void *tc; /* tensor-core path state (tensor maps) */
+};
+
+/* ---- |x|^2 per descriptor ------------------------------------------------ */
+__global__ void norms_kernel(const uint8_t *__restrict__ desc, uint32_t n, uint32_t *__restrict__ out)
+{
+  /* one warp per descriptor, 4 bytes per lane */
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n)
+    return;
+  const uint32_t v = __ldg((const uint32_t *)(desc + (size_t)row * 128) + lane);
+  uint32_t s = __dp4a(v, v, 0u);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, d);
+  if (lane == 0)
+    out[row] = s;
+}
+
+/* ---- SIMT cross-check kernel (verification only, vksiftx_setMatcherImpl(1)) */
+#define MS_ROWS 128
+#define MS_BTILE 64
+__device__ __forceinline__ void top2_insert(unsigned long long key, unsigned long long &k1, unsigned long long &k2)
+{
+  if (key < k1)
+  {
+    k2 = k1;
+    k1 = key;
+  }
+  else if (key < k2)
+    k2 = key;
+}
+__device__ __forceinline__ uint32_t match_pos(uint32_t b) { return b < 2u ? (b ^ 1u) : b; }
+
+__global__ void __launch_bounds__(MS_ROWS) match_simt_kernel(const uint8_t *__restrict__ da, uint32_t na, const uint32_t *__restrict__ norm_a,
+                                                             const uint8_t *__restrict__ db, uint32_t nb, const uint32_t *__restrict__ norm_b,
+                                                             vksift_Match_2NN *__restrict__ out)
+{
+  __shared__ uint32_t s_b[MS_BTILE][32];
+  __shared__ uint32_t s_nb[MS_BTILE];
+  const uint32_t row = blockIdx.x * MS_ROWS + threadIdx.x;
+  uint32_t a[32];
+  const uint32_t arow = min(row, na - 1);
+#pragma unroll
+  for (int i = 0; i < 32; i++)
+    a[i] = __ldg((const uint32_t *)(da + (size_t)arow * 128) + i);
+  const uint32_t my_na = norm_a[arow];
+  unsigned long long k1 = ~0ull, k2 = ~0ull;
+  for (uint32_t b0 = 0; b0 < nb; b0 += MS_BTILE)
+  {
+    const uint32_t cnt = min((uint32_t)MS_BTILE, nb - b0);
+    for (uint32_t i = threadIdx.x; i < cnt * 32; i += MS_ROWS)
+      s_b[i >> 5][i & 31] = __ldg((const uint32_t *)(db + (size_t)b0 * 128) + i);
+    if (threadIdx.x < cnt)
+      s_nb[threadIdx.x] = norm_b[b0 + threadIdx.x];
+    __syncthreads();
+    for (uint32_t j = 0; j < cnt; j++)
+    {
+      uint32_t dot = 0;
+#pragma unroll
+      for (int i = 0; i < 32; i++)
+        dot = __dp4a(a[i], s_b[j][i], dot);
+      const uint32_t d2 = my_na + s_nb[j] - 2u * dot;
+      top2_insert(((unsigned long long)d2 << 32) | match_pos(b0 + j), k1, k2);
+    }
+    __syncthreads();
+  }
+  if (row < na)
+  {
+    vksift_Match_2NN m;
+    m.idx_a = row;
+    m.idx_b1 = match_pos((uint32_t)k1);
+    m.idx_b2 = match_pos((uint32_t)k2);
+    m.dist_a_b1 = vks_sqrt((float)(uint32_t)(k1 >> 32));
+    m.dist_a_b2 = vks_sqrt((float)(uint32_t)(k2 >> 32));
+    out[row] = m;
+  }
+}
+
+cudaError_t match_workspace_create(MatchWorkspace **out, uint32_t max_feats)
+{
+  MatchWorkspace *ws = new MatchWorkspace();
+  ws->max_feats = max_feats;
+  ws->tc = nullptr;
+  ws->partial = nullptr;
+  ws->partial_splits = 0;
+  cudaError_t e = cudaMalloc(&ws->norm_a, sizeof(uint32_t) * (size_t)(max_feats + 256));
+  if (e == cudaSuccess)
+    e = cudaMalloc(&ws->norm_b, sizeof(uint32_t) * (size_t)(max_feats + 256));
+  if (e == cudaSuccess)
+    e = match_tc_create(&ws->tc, max_feats);
+  if (e != cudaSuccess)
+  {
+    match_workspace_destroy(ws);
+    return e;
+  }
+  *out = ws;
+  return cudaSuccess;
+}
+
+void match_workspace_destroy(MatchWorkspace *ws)
+{
+  if (!ws)
+    return;
+  match_tc_destroy(ws->tc);
+  cudaFree(ws->norm_a);
+  cudaFree(ws->norm_b);
+  cudaFree(ws->partial);
+  delete ws;
+}
+
+cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *da, uint32_t na, const uint8_t *db, uint32_t nb, vksift_Match_2NN *out,
+                         cudaStream_t st, cudaEvent_t ev_after_prepare, uint64_t *launch_count)
+{
+  if (na == 0)
+    return cudaSuccess;
+  norms_kernel<<<(na * 32 + 255) / 256, 256, 0, st>>>(da, na, ws->norm_a);
+  norms_kernel<<<(nb * 32 + 255) / 256, 256, 0, st>>>(db, nb, ws->norm_b);
+  *launch_count += 2;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return e;
+  if (ev_after_prepare)
+    cudaEventRecord(ev_after_prepare, st);
+  if (impl == 1)
+  {
+    match_simt_kernel<<<(na + MS_ROWS - 1) / MS_ROWS, MS_ROWS, 0, st>>>(da, na, ws->norm_a, db, nb, ws->norm_b, out);
+    *launch_count += 1;
+    return cudaGetLastError();
+  }
+  return match_tc_launch(ws->tc, da, na, ws->norm_a, db, nb, ws->norm_b, out, st, launch_count);
+}
+
+} // namespace vks

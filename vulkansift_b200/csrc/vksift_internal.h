@@ -1,0 +1,165 @@
+/*
+ * vksift_internal.h -- shared declarations of the B200 SIFT library.
+ *
+ * Layering (replaces reference L1-L4):
+ *   api.cu        C ABI, validation, stream/event orchestration   (vulkansift.c)
+ *   plan.cu       host tables: octaves, taps, sections            (sift_memory.c:15-87, sift_detector.c:52-145)
+ *   pyramid.cu    seed + separable blur + DoG + next-octave seed  (GaussianBlur*.comp, DifferenceOfGaussian.comp, blits)
+ *   extrema.cu    3x3x3 scan, refinement, deterministic ordering  (ExtractKeypoints.comp)
+ *   describe.cu   orientation, assembly, descriptor               (ComputeOrientation.comp, ComputeDescriptors.comp)
+ *   match.cu      2-NN brute force on tcgen05 tensor cores        (Get2NearestNeighbors.comp)
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vksift_arith.h"
+#include "vksift_b200_ext.h"
+#include "vulkansift/vulkansift.h"
+
+#define VKS_MAX_OCT 16    /* log2(65536) - 4 + 1 */
+#define VKS_MAX_LAYERS 24 /* nb_scales_per_octave + 3 <= 24 */
+#define VKS_MAX_TAPS 21   /* VKSIFT_DETECTOR_MAX_GAUSSIAN_KERNEL_SIZE (20) + centre */
+#define VKS_MAX_ORI 36    /* orientation histogram bins */
+
+namespace vks
+{
+
+/* ---- logging (vkenv/logger.c) ------------------------------------------- */
+void log_msg(int level, const char *tag, const char *fmt, ...);
+#define LOGE(tag, ...) ::vks::log_msg(VKSIFT_LOG_ERROR, tag, __VA_ARGS__)
+#define LOGW(tag, ...) ::vks::log_msg(VKSIFT_LOG_WARNING, tag, __VA_ARGS__)
+#define LOGI(tag, ...) ::vks::log_msg(VKSIFT_LOG_INFO, tag, __VA_ARGS__)
+#define LOGD(tag, ...) ::vks::log_msg(VKSIFT_LOG_DEBUG, tag, __VA_ARGS__)
+
+/* ---- device-visible plain structs --------------------------------------- */
+
+/* the 36 bytes of vksift_Feature in front of `descriptor` */
+struct FeatHead
+{
+  float x, y, scale_x, scale_y;
+  uint32_t scale_idx;
+  int32_t octave_idx;
+  float sigma, orientation, intensity;
+};
+static_assert(sizeof(FeatHead) == 36, "FeatHead layout");
+
+/* one octave of the scale space in HBM: (ns+3) Gaussian and (ns+2) DoG layers,
+ * rows padded to `pitch` floats (multiple of 32 -> 128-byte aligned rows) */
+struct OctaveView
+{
+  float *G;
+  float *D;
+  int w, h, pitch;
+  int layer_stride; /* floats between layers = pitch*h */
+};
+
+/* accepted keypoint before ordering */
+struct Candidate
+{
+  unsigned long long key; /* (s << 40) | (y << 20) | x : detection-thread order of SURVEY B-D4 */
+  FeatHead head;
+  uint32_t pad_;
+};
+static_assert(sizeof(Candidate) == 48, "Candidate layout");
+
+struct DetectParams
+{
+  OctaveView oct[VKS_MAX_OCT];
+  uint32_t cap[VKS_MAX_OCT];     /* section capacity (updateBufferInfo) */
+  uint32_t sec_off[VKS_MAX_OCT]; /* prefix sum of cap */
+  int n_oct, ns, upsample;
+  float sigma0, thr, prefilter, edge_limit;
+  uint32_t max_ori;    /* 0 = unlimited */
+  uint32_t ori_stride; /* orientation slots per primary */
+  int vlfeat;
+  uint32_t cand_cap; /* candidate list capacity per octave */
+  uint32_t max_feats;
+};
+
+/* per-buffer device counters, zeroed at the start of every detection */
+struct DetectCounters
+{
+  uint32_t n_cand[VKS_MAX_OCT];   /* accepted keypoints found (may exceed capacity) */
+  uint32_t n_prim[VKS_MAX_OCT];   /* primaries kept = min(n_cand, cap) */
+  uint32_t n_found[VKS_MAX_OCT];  /* primaries + extra orientations found */
+  uint32_t n_kept[VKS_MAX_OCT];   /* min(n_found, cap) */
+  uint32_t out_off[VKS_MAX_OCT];  /* packed output offset per octave */
+  uint32_t prim_off[VKS_MAX_OCT]; /* offset of the octave's primaries in the work list */
+  uint32_t n_prim_total;
+  uint32_t n_total; /* packed feature count */
+};
+
+/* ---- separable blur work description (pyramid.cu) ----------------------- */
+enum BlurSrcKind
+{
+  BLUR_SRC_LAYER = 0,  /* float layer of the same octave */
+  BLUR_SRC_U8_UP2 = 1, /* u8 input, 2x LINEAR blit on the fly (octave 0, upsampling) */
+  BLUR_SRC_U8 = 2      /* u8 input converted 1:1 */
+};
+
+struct BlurPass
+{
+  const void *src; /* float layer or u8 image */
+  float *dst_g;    /* Gaussian layer written */
+  float *dst_d;    /* DoG layer (dst_g - src) or NULL */
+  float *dst_next; /* next octave layer 0 (NEAREST blit of this layer) or NULL */
+  int w, h;        /* layer size */
+  int src_pitch, dst_pitch, next_pitch;
+  int src_w, src_h; /* u8 input size for the seed pass */
+  int next_w, next_h;
+  int src_kind;
+  int radius;
+  int tiles_x, tiles_y, tile_begin; /* CTA range of this pass inside the launch */
+  float taps[VKS_MAX_TAPS];
+};
+#define VKS_MAX_PASSES_PER_STEP 4
+struct BlurStep
+{
+  BlurPass pass[VKS_MAX_PASSES_PER_STEP];
+  int n_pass;
+  int n_tiles;
+};
+
+/* ---- host-side plan ------------------------------------------------------ */
+struct ScalePlan
+{
+  int ns;
+  uint32_t ksize[VKS_MAX_LAYERS];
+  uint32_t radius[VKS_MAX_LAYERS];
+  float taps[VKS_MAX_LAYERS][VKS_MAX_TAPS];
+};
+/* sift_detector.c:52-145 */
+void plan_gaussian_taps(ScalePlan *sp, const vksift_Config *cfg);
+/* sift_memory.c:655-660 */
+uint32_t plan_max_octaves(const vksift_Config *cfg, uint32_t *side_out);
+/* sift_memory.c:15-38 */
+uint32_t plan_octaves(uint32_t w, uint32_t h, bool upsample, uint32_t max_octaves, uint32_t *ow, uint32_t *oh);
+/* sift_memory.c:40-87 */
+void plan_sections(uint32_t max_feats, uint32_t n_oct, uint32_t *cap);
+
+/* ---- kernels' host launchers -------------------------------------------- */
+struct FeatureBuffer;
+struct Instance;
+
+cudaError_t launch_blur_step(const BlurStep &step, cudaStream_t st);
+cudaError_t launch_extrema(const DetectParams &P, int octave, Candidate *cand, DetectCounters *cnt, cudaStream_t st);
+cudaError_t launch_order_primaries(const DetectParams &P, const Candidate *cand, DetectCounters *cnt, FeatHead *prim, cudaStream_t st);
+cudaError_t launch_orientation(const DetectParams &P, DetectCounters *cnt, const FeatHead *prim, float *ori, uint32_t *n_ori, cudaStream_t st);
+cudaError_t launch_assemble(const DetectParams &P, DetectCounters *cnt, const uint32_t *n_ori, uint32_t *feat_src, uint32_t *host_counts,
+                            cudaStream_t st);
+cudaError_t launch_descriptors(const DetectParams &P, const DetectCounters *cnt, const FeatHead *prim, const float *ori, const uint32_t *feat_src,
+                               FeatHead *out_heads, uint8_t *out_desc, cudaStream_t st);
+/* AoS <-> SoA for host transfers */
+cudaError_t launch_pack_aos(const FeatHead *heads, const uint8_t *desc, uint32_t n, uint8_t *aos, cudaStream_t st);
+cudaError_t launch_unpack_aos(const uint8_t *aos, uint32_t n, FeatHead *heads, uint8_t *desc, cudaStream_t st);
+
+/* matcher */
+struct MatchWorkspace;
+cudaError_t match_workspace_create(MatchWorkspace **ws, uint32_t max_feats);
+void match_workspace_destroy(MatchWorkspace *ws);
+cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *desc_a, uint32_t na, const uint8_t *desc_b, uint32_t nb, vksift_Match_2NN *out,
+                         cudaStream_t st, cudaEvent_t ev_after_prepare, uint64_t *launch_count);
+
+} // namespace vks
