@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the vksift detect + 2-NN match path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric (BASELINE.json): SIFT features/s of the detection pipeline on configs[1]
+(1920x1080, upsampling, sigma0 1.6, synthetic blob field), plus 2-NN matches/s
+on configs[3] (10k x 10k x 128-D) in the "match" object.  One JSON line on rank 0.
+
+  value   : device-resident throughput (image already in HBM, CUDA events on the library stream)
+  e2e     : same metric through vksift_detectFeatures / getFeaturesNumber / downloadFeatures with HOST
+            buffers (pinned source image -> H2D, feature records D2H inside the timed region)
+  roofline: pyramid+DoG stage, algorithmic bytes / CUDA-event stage time / measured HBM peak
+  cpu_baseline: the CPU oracle (port of the reference algorithm) timed on this box's host cores
+
+N > 1 (torchrun, one rank per GPU): images shard one per GPU with no data-path collective
+(weak scaling); the all-pairs match step exchanges descriptor blocks with an NCCL all-gather.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from vulkansift_b200.synth import C2, blob_image, random_descriptors  # noqa: E402
+
+METRIC = "sift_features_per_sec"
+UNIT = "features/s"
+N_IMAGES = 4  # distinct inputs rotated through the steps
+MATCH_N = 10000
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def workload_images():
+    return [blob_image(**dict(C2, seed=C2["seed"] + i)) for i in range(N_IMAGES)]
+
+
+def algorithmic_bytes_pyramid(w, h, octaves, ns):
+    """input read once + every Gaussian and DoG layer written exactly once (fp32)."""
+    sp = sum(ow * oh for ow, oh in octaves)
+    return w * h + 4 * sp * (ns + 3) + 4 * sp * (ns + 2)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def cpu_port_baseline(images, seconds_budget=20.0, threads=0):
+    """Oracle (kind "port") on the host cores: detections of the same workload until ~budget seconds."""
+    import oracle
+    orc = oracle.Oracle(nb_threads=threads)
+    cores = threads if threads > 0 else (os.cpu_count() or 1)
+    n_feat, n_img = 0, 0
+    orc.detect(images[0])  # warm-up (page faults, allocations)
+    t0 = time.perf_counter()
+    while True:
+        f = orc.detect(images[n_img % len(images)])
+        n_feat += len(f)
+        n_img += 1
+        dt = time.perf_counter() - t0
+        if dt > seconds_budget or n_img >= 12:
+            break
+    return {"value": n_feat / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d detections of the 1920x1080 workload (%d features) in %.2f s, OpenMP oracle" % (n_img, n_feat, dt),
+            "ms_per_image": 1e3 * dt / n_img, "stage_seconds_last": orc.stage_seconds()}
+
+
+def cpu_match_baseline(threads=0, rows=1000):
+    import oracle
+    da, db = random_descriptors(MATCH_N, 1234), random_descriptors(MATCH_N, 1235)
+    t0 = time.perf_counter()
+    oracle.match_descriptors(da[:rows], db, threads)
+    dt = time.perf_counter() - t0
+    return {"value": rows / dt, "unit": "matches/s", "cores": threads if threads > 0 else (os.cpu_count() or 1), "kind": "port",
+            "sample": "%d of %d A rows against %d B rows in %.2f s" % (rows, MATCH_N, MATCH_N, dt)}
+
+
+def opencv_baseline(images, n=3):
+    """The reference's own CPU comparison path (src/perf/wrappers/opencv_wrapper.cpp:5,16), reported beside the port."""
+    try:
+        import cv2
+    except ImportError:
+        return None
+    s = cv2.SIFT_create()
+    s.detectAndCompute(images[0], None)
+    t0 = time.perf_counter()
+    nf = 0
+    for i in range(n):
+        k, _ = s.detectAndCompute(images[i % len(images)], None)
+        nf += len(k)
+    dt = time.perf_counter() - t0
+    return {"value": nf / dt, "unit": UNIT, "cores": cv2.getNumThreads(), "kind": "opencv-%s" % cv2.__version__,
+            "sample": "%d x cv2.SIFT_create().detectAndCompute on the same images" % n, "ms_per_image": 1e3 * dt / n}
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (oracle/_ref is a
+    correctness harness, not a performance build), all host threads, same config/metric/unit."""
+    if rank != 0:
+        return
+    images = workload_images()
+    import oracle
+    orc = oracle.Oracle(nb_threads=0)
+    for _ in range(max(1, min(args.warmup, 2))):
+        orc.detect(images[0])
+    steps = max(1, min(args.steps, 10))
+    n_feat = 0
+    t0 = time.perf_counter()
+    for i in range(steps):
+        n_feat += len(orc.detect(images[i % len(images)]))
+    dt = time.perf_counter() - t0
+    v = n_feat / dt
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d detections (each step = one 1920x1080 image) on %d OpenMP threads" % (steps, cores)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(world):
+    return {"workload": "configs[1]: 1920x1080 detect, upsampling ON, sigma0 1.6, nb_scales_per_octave 3 (5 DoG scales), "
+                        "octaves auto (7), synthetic blob field N=2400",
+            "images_per_step_per_gpu": 1, "distinct_images": N_IMAGES, "sharding": "one image per GPU per step" if world > 1 else "single GPU",
+            "l2": "per-step working set 489 MB (pyramid + DoG rewritten every step) > 126 MB L2; inputs rotate over %d images" % N_IMAGES}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from vulkansift_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    api.lib.vksift_setLogLevel(api.VKSIFT_LOG_WARNING)
+
+    K, W = args.steps, max(3, args.warmup)
+    images = workload_images()
+    h, w = images[0].shape
+    inst = api.Instance(gpu_device_index=local_rank, input_image_max_size=w * h)
+    stream = torch.cuda.ExternalStream(inst.stream, device=local_rank)
+    d_images = [torch.from_numpy(im).cuda() for im in images]
+    pinned = [torch.from_numpy(im).pin_memory() for im in images]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident detection (value) ----------------
+    for i in range(W):
+        inst.detect_device(d_images[i % N_IMAGES].data_ptr(), w, h, i % 2)
+    inst.wait_idle()
+    counts = {}
+    for i in range(N_IMAGES):
+        inst.detect_device(d_images[i].data_ptr(), w, h, 0)
+        counts[i] = inst.features_number(0)
+    octaves = [inst.octave_resolution(o) for o in range(inst.nb_octaves())]
+    ns = inst.config.nb_scales_per_octave
+
+    inst.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = inst.kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_acc = {}
+    n_feat = 0
+    ev0.record(stream)
+    for i in range(K):
+        inst.detect_device(d_images[i % N_IMAGES].data_ptr(), w, h, i % 2)
+        for k, v in inst.stage_times_ms().items():  # waits for this step (the next detect would wait anyway)
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+        n_feat += counts[i % N_IMAGES]
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = inst.kernel_launch_count() - launches0
+    inst.set_profiling(False)
+
+    # ---------------- end to end through the reference API (e2e) ----------------
+    for i in range(3):
+        inst.detect_raw(pinned[i % N_IMAGES].data_ptr(), w, h, 0)
+        inst.download_features(0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_feat, d2h = 0, 0
+    for i in range(K):
+        inst.detect_raw(pinned[i % N_IMAGES].data_ptr(), w, h, i % 2)
+        f = inst.download_features(i % 2)  # getFeaturesNumber + downloadFeatures
+        e2e_feat += len(f)
+        d2h += f.nbytes + 4
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # ---------------- matcher (configs[3]) ----------------
+    da, db = random_descriptors(MATCH_N, 1234), random_descriptors(MATCH_N, 1235)
+    minst = api.Instance(gpu_device_index=local_rank, max_nb_sift_per_buffer=MATCH_N, input_image_max_size=1024 * 1024)
+    mstream = torch.cuda.ExternalStream(minst.stream, device=local_rank)
+    fa = np.zeros(MATCH_N, api.FEATURE_DTYPE)
+    fb = np.zeros(MATCH_N, api.FEATURE_DTYPE)
+    fa["descriptor"], fb["descriptor"] = da, db
+    minst.upload_features(fa, 0)
+    minst.upload_features(fb, 1)
+    minst.set_profiling(True)
+    for _ in range(W):
+        minst.match(0, 1)
+    minst.wait_idle()
+    mk = max(K, 20)
+    m_acc = 0.0
+    mev0, mev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    mev0.record(mstream)
+    for _ in range(mk):
+        minst.match(0, 1)
+        m_acc += minst.stage_times_ms()["match_2nn"]
+    mev1.record(mstream)
+    barrier()
+    match_ms = mev0.elapsed_time(mev1) / mk
+    match_kernel_ms = m_acc / mk
+    # e2e matcher: upload both descriptor sets, match, download the rows
+    t0 = time.perf_counter()
+    for _ in range(5):
+        minst.upload_features(fa, 0)
+        minst.upload_features(fb, 1)
+        minst.match(0, 1)
+        minst.download_matches()
+    match_e2e_s = (time.perf_counter() - t0) / 5
+
+    # ---------------- reduce over ranks ----------------
+    vals = torch.tensor([dev_ms, e2e_s, match_ms, match_kernel_ms, stage_acc.get("pyramid_dog", 0.0) / K], dtype=torch.float64, device="cuda")
+    sums = torch.tensor([float(n_feat), float(e2e_feat)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_s, match_ms, match_kernel_ms, pyr_ms = vals.tolist()
+    n_feat_all, e2e_feat_all = sums.tolist()
+
+    if rank == 0:
+        hbm, tf_burst, tf_sust, peak_src = measured_peaks()
+        alg = algorithmic_bytes_pyramid(w, h, octaves, ns)
+        ach = alg / (pyr_ms * 1e-3) / 1e9 if pyr_ms > 0 else 0.0
+        flops = 2.0 * MATCH_N * MATCH_N * 128
+        m_ach = flops / (match_kernel_ms * 1e-3) / 1e12 if match_kernel_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": n_feat_all / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world),
+            "features_per_image": [counts[i] for i in range(N_IMAGES)],
+            "e2e": {"value": e2e_feat_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": w * h, "d2h_bytes_per_step": d2h // K,
+                    "ms_per_step": 1e3 * e2e_s / K},
+            "gpu_launches": launches,
+            "stage_ms": {k: v / K for k, v in stage_acc.items() if k.startswith(("pyramid", "extrema", "orient", "descr", "detect"))},
+            "roofline": {"bound": "hbm", "kernel": "pyramid+DoG stage (blur_step_kernel launches)", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                         "frac": ach / hbm, "traffic": None, "algorithmic_bytes": alg, "stage_ms": pyr_ms, "peak_source": peak_src},
+            "match": {"metric": "2nn_matches_per_sec", "value": world * MATCH_N / (match_ms * 1e-3), "unit": "matches/s",
+                      "workload": "configs[3]: 10000 x 10000 x 128-D u8, tcgen05 kind::i8 path", "ms_per_match_call": match_ms,
+                      "kernel_ms": match_kernel_ms, "e2e_value": MATCH_N / match_e2e_s, "e2e_ms": 1e3 * match_e2e_s,
+                      "roofline": {"bound": "tensor", "achieved": m_ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": m_ach / tf_burst,
+                                   "flops": flops, "peak_source": peak_src + " bf16 dense burst (i8 operands run at 2x this rate)"}},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world >= 1:
+            cb = cpu_port_baseline(images)
+            line["cpu_baseline"] = cb
+            line["match"]["cpu_baseline"] = cpu_match_baseline()
+            ocv = opencv_baseline(images)
+            if ocv:
+                line["opencv_baseline"] = ocv
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -263,50 +263,65 @@ void build_blur_plan(vksift_Instance inst)
   const Pyramid &p = inst->pyr;
   const int ns = inst->cfg.nb_scales_per_octave;
   inst->steps.clear();
-  for (uint32_t o = 0; o < p.n_oct; o++)
-  {
+  auto make_pass = [&](uint32_t o, int s) {
+    BlurPass bp;
+    memset(&bp, 0, sizeof(bp));
     const size_t layer = (size_t)p.pitch[o] * p.h[o];
-    for (int s = (o == 0 ? 0 : 1); s < ns + 3; s++)
+    bp.w = (int)p.w[o];
+    bp.h = (int)p.h[o];
+    bp.dst_pitch = (int)p.pitch[o];
+    bp.dst_g = p.G[o] + layer * s;
+    if (s == 0)
     {
-      BlurStep step;
-      memset(&step, 0, sizeof(step));
-      BlurPass &bp = step.pass[0];
-      bp.w = (int)p.w[o];
-      bp.h = (int)p.h[o];
-      bp.dst_pitch = (int)p.pitch[o];
-      bp.dst_g = p.G[o] + layer * s;
-      if (s == 0)
-      {
-        bp.src = inst->d_image; /* patched per call when the image already lives in HBM */
-        bp.src_kind = inst->cfg.use_input_upsampling ? BLUR_SRC_U8_UP2 : BLUR_SRC_U8;
-        bp.src_w = (int)inst->cur_w;
-        bp.src_h = (int)inst->cur_h;
-        bp.src_pitch = (int)inst->cur_w;
-        bp.dst_d = nullptr;
-      }
-      else
-      {
-        bp.src = p.G[o] + layer * (s - 1);
-        bp.src_kind = BLUR_SRC_LAYER;
-        bp.src_pitch = (int)p.pitch[o];
-        bp.dst_d = p.D[o] + layer * (s - 1);
-      }
-      if (s == ns && o + 1 < p.n_oct)
-      {
-        bp.dst_next = p.G[o + 1];
-        bp.next_pitch = (int)p.pitch[o + 1];
-        bp.next_w = (int)p.w[o + 1];
-        bp.next_h = (int)p.h[o + 1];
-      }
-      bp.radius = (int)inst->scales.radius[s];
-      memcpy(bp.taps, inst->scales.taps[s], sizeof(bp.taps));
-      bp.tiles_x = (bp.w + 63) / 64;
-      bp.tiles_y = (bp.h + 31) / 32;
-      bp.tile_begin = 0;
-      step.n_pass = 1;
-      step.n_tiles = bp.tiles_x * bp.tiles_y;
-      inst->steps.push_back(step);
+      bp.src = inst->d_image; /* patched per call when the image already lives in HBM */
+      bp.src_kind = inst->cfg.use_input_upsampling ? BLUR_SRC_U8_UP2 : BLUR_SRC_U8;
+      bp.src_w = (int)inst->cur_w;
+      bp.src_h = (int)inst->cur_h;
+      bp.src_pitch = (int)inst->cur_w;
+      bp.dst_d = nullptr;
     }
+    else
+    {
+      bp.src = p.G[o] + layer * (s - 1);
+      bp.src_kind = BLUR_SRC_LAYER;
+      bp.src_pitch = (int)p.pitch[o];
+      bp.dst_d = p.D[o] + layer * (s - 1);
+    }
+    if (s == ns && o + 1 < p.n_oct)
+    {
+      bp.dst_next = p.G[o + 1];
+      bp.next_pitch = (int)p.pitch[o + 1];
+      bp.next_w = (int)p.w[o + 1];
+      bp.next_h = (int)p.h[o + 1];
+    }
+    bp.radius = (int)inst->scales.radius[s];
+    memcpy(bp.taps, inst->scales.taps[s], sizeof(bp.taps));
+    return bp;
+  };
+  /* Wavefront schedule.  Layer s of octave o needs layer s-1 of the same octave, and layer 0 of octave
+   * o >= 1 is written by the pass that produces layer ns of octave o-1, so pass (o,s) is ready at step
+   * ns*o + s.  All passes of one step share a launch: the late scales of a large octave then run next to
+   * the early scales of the following, smaller octave instead of 36 strictly serial launches
+   * (reference order: sift_detector.c:1369-1378 records octave after octave). */
+  if (p.n_oct == 0)
+    return;
+  const int n_steps = ns * ((int)p.n_oct - 1) + ns + 3;
+  for (int t = 0; t < n_steps; t++)
+  {
+    BlurStep step;
+    memset(&step, 0, sizeof(step));
+    /* smaller octaves first: they are on the critical path, the big pass fills the remaining SMs */
+    for (int o = (int)p.n_oct - 1; o >= 0; o--)
+    {
+      const int s = t - ns * o;
+      if (s < (o == 0 ? 0 : 1) || s > ns + 2 || step.n_pass >= VKS_MAX_PASSES_PER_STEP)
+        continue;
+      step.pass[step.n_pass++] = make_pass((uint32_t)o, s);
+    }
+    if (step.n_pass == 0)
+      continue;
+    blur_step_tiles(&step);
+    inst->steps.push_back(step);
   }
 }
 
@@ -508,11 +523,8 @@ bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t bu
   }
   if (prof)
     CU_TRY(cudaEventRecord(inst->ev[EV_D1], st));
-  for (int o = 0; o < P.n_oct; o++)
-  {
-    CU_TRY(launch_extrema(P, o, inst->cand, fb.cnt, st));
-    inst->launches++;
-  }
+  CU_TRY(launch_extrema(P, inst->cand, fb.cnt, st));
+  inst->launches++;
   CU_TRY(launch_order_primaries(P, inst->cand, fb.cnt, inst->prim, st));
   inst->launches++;
   if (prof)

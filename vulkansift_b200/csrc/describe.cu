@@ -364,6 +364,11 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
       const float sdy = (rsy + (float)dy) - kp.scale_y;
       const float ox = kc * sdx + ks * sdy;
       const float oy = kc * sdy - ks * sdx;
+      /* pixels whose both spatial cells fall outside the 4x4 grid contribute to no bin (:187):
+       * skip them before the transcendental work (about half of the box after rotation) */
+      const int hx0 = (int)floorf((ox + 2.f) - 0.5f), hy0 = (int)floorf((oy + 2.f) - 0.5f);
+      if (hx0 < -1 || hx0 > 3 || hy0 < -1 || hy0 > 3)
+        continue;
       const float *__restrict__ c = L + (size_t)iy * ov.pitch + ix;
       const float gX = 0.5f * (__ldg(c + 1) - __ldg(c - 1));
       const float gY = 0.5f * (__ldg(c + ov.pitch) - __ldg(c - ov.pitch));

@@ -103,63 +103,120 @@ __device__ bool refine_keypoint(const DetectParams &P, const OctaveView &ov, int
   return true;
 }
 
-/* ExtractKeypoints.comp:44-116: one thread per (x,y,s), s in [1,ns] */
-__global__ void __launch_bounds__(256) extrema_kernel(const __grid_constant__ DetectParams P, int o, Candidate *__restrict__ cand,
+/* ExtractKeypoints.comp:44-116.  The reference runs one thread per (x,y,s) and reads 27 texels each.
+ * Here one CTA stages a 64x32 tile (+1 halo) of ALL ns+2 DoG layers of an octave in shared memory once
+ * (every DoG value is read from HBM a single time), then tests the ns inner scales from smem:
+ * prefilter |v| > 0.8*thr, strict 26-neighbour extremum, and for the few survivors the refinement
+ * (which reads global memory, it walks outside the tile).  All octaves run in one launch. */
+#define EX_TW 64
+#define EX_TH 32
+#define EX_SW 72 /* smem row: columns x0-4 .. x0+67 as 18 aligned float4 */
+#define EX_SH (EX_TH + 2)
+
+__global__ void __launch_bounds__(256) extrema_kernel(const __grid_constant__ DetectParams P, Candidate *__restrict__ cand,
                                                       DetectCounters *__restrict__ cnt)
 {
-  const OctaveView &ov = P.oct[o];
-  const int x = blockIdx.x * 32 + threadIdx.x;
-  const int y = blockIdx.y * 8 + threadIdx.y;
-  const int s = blockIdx.z + 1;
-  if (x < 1 || x >= ov.w - 1 || y < 1 || y >= ov.h - 1)
-    return;
-  const float *__restrict__ L = ov.D + (size_t)s * ov.layer_stride;
-  const float c = __ldg(L + (size_t)y * ov.pitch + x);
-  if (!(fabsf(c) > P.prefilter))
-    return;
-  bool gt = true, lt = true;
-#pragma unroll
-  for (int ds = -1; ds <= 1; ds++)
+  extern __shared__ __align__(16) float ex_smem[];
+  /* linear CTA index -> (octave, tile) */
+  int t = blockIdx.x, o = 0, tx = 0;
+  for (; o < P.n_oct; o++)
   {
-    const float *__restrict__ Ls = L + (ptrdiff_t)ds * ov.layer_stride;
-#pragma unroll
-    for (int dy = -1; dy <= 1; dy++)
+    tx = (P.oct[o].w + EX_TW - 1) / EX_TW;
+    const int n = tx * ((P.oct[o].h + EX_TH - 1) / EX_TH);
+    if (t < n)
+      break;
+    t -= n;
+  }
+  if (o >= P.n_oct)
+    return;
+  const OctaveView &ov = P.oct[o];
+  const int nl = P.ns + 2;
+  const int x0 = (t % tx) * EX_TW, y0 = (t / tx) * EX_TH;
+  const int tid = threadIdx.x;
+
+  /* stage: layer l, smem row r <-> image row y0-1+r, smem col c <-> image col x0-4+c */
+  const int n_items = nl * EX_SH * (EX_SW / 4);
+  for (int it = tid; it < n_items; it += 256)
+  {
+    const int l = it / (EX_SH * (EX_SW / 4));
+    const int rem = it - l * (EX_SH * (EX_SW / 4));
+    const int r = rem / (EX_SW / 4), c4 = rem - r * (EX_SW / 4);
+    const int gy = y0 - 1 + r, gx = x0 - 4 + c4 * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy >= 0 && gy < ov.h && gx >= 0 && gx + 3 < ov.pitch)
+      v = __ldg((const float4 *)(ov.D + (size_t)l * ov.layer_stride + (size_t)gy * ov.pitch + gx));
+    *(float4 *)(ex_smem + (l * EX_SH + r) * EX_SW + c4 * 4) = v;
+  }
+  __syncthreads();
+
+  const int lx = tid & 63, ly = (tid >> 6) * 8;
+  const int x = x0 + lx;
+  if (x < 1 || x >= ov.w - 1)
+    return;
+  for (int s = 1; s <= P.ns; s++)
+  {
+    const float *Ls = ex_smem + (s * EX_SH) * EX_SW + (lx + 4);
+#pragma unroll 1
+    for (int r = 0; r < 8; r++)
     {
-      const float *__restrict__ row = Ls + (size_t)(y + dy) * ov.pitch + x;
+      const int y = y0 + ly + r;
+      if (y < 1 || y >= ov.h - 1)
+        continue;
+      const float *pc = Ls + (ly + r + 1) * EX_SW;
+      const float c = pc[0];
+      if (!(fabsf(c) > P.prefilter))
+        continue;
+      bool gt = true, lt = true;
 #pragma unroll
-      for (int dx = -1; dx <= 1; dx++)
+      for (int ds = -1; ds <= 1; ds++)
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+          for (int dx = -1; dx <= 1; dx++)
+          {
+            if (ds == 0 && dy == 0 && dx == 0)
+              continue;
+            const float n = pc[ds * (EX_SH * EX_SW) + dy * EX_SW + dx];
+            gt = gt && (c > n);
+            lt = lt && (c < n);
+          }
+      if (!(gt || lt))
+        continue;
+      FeatHead hd;
+      if (!refine_keypoint(P, ov, o, x, y, s, &hd))
+        continue;
+      const uint32_t slot = atomicAdd(&cnt->n_cand[o], 1u);
+      if (slot < P.cand_cap)
       {
-        if (ds == 0 && dy == 0 && dx == 0)
-          continue;
-        const float n = __ldg(row + dx);
-        gt = gt && (c > n);
-        lt = lt && (c < n);
+        Candidate cd;
+        cd.key = ((unsigned long long)s << 40) | ((unsigned long long)y << 20) | (unsigned long long)x;
+        cd.head = hd;
+        cd.pad_ = 0;
+        cand[(size_t)o * P.cand_cap + slot] = cd;
       }
     }
-    if (!gt && !lt)
-      return;
-  }
-  if (!(gt || lt))
-    return;
-  FeatHead hd;
-  if (!refine_keypoint(P, ov, o, x, y, s, &hd))
-    return;
-  const uint32_t slot = atomicAdd(&cnt->n_cand[o], 1u);
-  if (slot < P.cand_cap)
-  {
-    Candidate cd;
-    cd.key = ((unsigned long long)s << 40) | ((unsigned long long)y << 20) | (unsigned long long)x;
-    cd.head = hd;
-    cd.pad_ = 0;
-    cand[(size_t)o * P.cand_cap + slot] = cd;
   }
 }
 
-cudaError_t launch_extrema(const DetectParams &P, int o, Candidate *cand, DetectCounters *cnt, cudaStream_t st)
+cudaError_t launch_extrema(const DetectParams &P, Candidate *cand, DetectCounters *cnt, cudaStream_t st)
 {
-  const OctaveView &ov = P.oct[o];
-  dim3 grid((ov.w + 31) / 32, (ov.h + 7) / 8, P.ns), block(32, 8, 1);
-  extrema_kernel<<<grid, block, 0, st>>>(P, o, cand, cnt);
+  int tiles = 0;
+  for (int o = 0; o < P.n_oct; o++)
+    tiles += ((P.oct[o].w + EX_TW - 1) / EX_TW) * ((P.oct[o].h + EX_TH - 1) / EX_TH);
+  if (tiles == 0)
+    return cudaSuccess;
+  const size_t smem = sizeof(float) * (size_t)(P.ns + 2) * EX_SH * EX_SW;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_done[dev])
+  {
+    cudaError_t e = cudaFuncSetAttribute(extrema_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (VKS_MAX_LAYERS - 1) * EX_SH * EX_SW));
+    if (e != cudaSuccess)
+      return e;
+    attr_done[dev] = true;
+  }
+  extrema_kernel<<<tiles, 256, smem, st>>>(P, cand, cnt);
   return cudaGetLastError();
 }
 

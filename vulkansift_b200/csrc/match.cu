@@ -29,13 +29,18 @@ struct MatchWorkspace
 };
 
 /* ---- |x|^2 per descriptor ------------------------------------------------ */
-__global__ void norms_kernel(const uint8_t *__restrict__ desc, uint32_t n, uint32_t *__restrict__ out)
+#define NORM_PAD_VALUE 0x40000000u /* |b|^2 of a row that does not exist: loses every comparison */
+__global__ void norms_kernel(const uint8_t *__restrict__ desc, uint32_t n, uint32_t n_padded, uint32_t *__restrict__ out)
 {
-  /* one warp per descriptor, 4 bytes per lane */
+  /* one warp per descriptor, 4 bytes per lane; rows in [n, n_padded) get the pad value */
   const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n)
+  {
+    if (row < n_padded && lane == 0)
+      out[row] = NORM_PAD_VALUE;
     return;
+  }
   const uint32_t v = __ldg((const uint32_t *)(desc + (size_t)row * 128) + lane);
   uint32_t s = __dp4a(v, v, 0u);
 #pragma unroll
@@ -142,8 +147,9 @@ cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *da, uint32
 {
   if (na == 0)
     return cudaSuccess;
-  norms_kernel<<<(na * 32 + 255) / 256, 256, 0, st>>>(da, na, ws->norm_a);
-  norms_kernel<<<(nb * 32 + 255) / 256, 256, 0, st>>>(db, nb, ws->norm_b);
+  const uint32_t nb_pad = (nb + 127u) & ~127u; /* the tensor-core path reads |b|^2 in tiles of 128 */
+  norms_kernel<<<(na * 32 + 255) / 256, 256, 0, st>>>(da, na, na, ws->norm_a);
+  norms_kernel<<<(nb_pad * 32 + 255) / 256, 256, 0, st>>>(db, nb, nb_pad, ws->norm_b);
   *launch_count += 2;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)

@@ -102,6 +102,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int32_t (&v)[32])
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ int4 lds_v4(uint32_t saddr)
+{
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 /* K-major SWIZZLE_128B operand descriptor: 8-row groups 1024 B apart (SBO), LBO unused (=1),
@@ -221,7 +227,10 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
   }
   else
   {
-    /* ===== epilogue: thread = A row, warp w reads TMEM lanes 32w..32w+31 ===== */
+    /* ===== epilogue: thread = A row, warp w reads TMEM lanes 32w..32w+31 =====
+     * Hot loop per accumulator: one IMAD (e = |b|^2 - 2 a.b) and a share of a min tree; only when the
+     * minimum of a 16-column group beats the row's current second best does the thread rescan that group
+     * with full (d^2, pos) keys.  Columns past nb carry |b|^2 = 2^30 (norms are padded), so they never win. */
     const uint32_t row = row0 + warp * 32 + lane;
     const int32_t my_na = (row < na) ? (int32_t)norm_a[row] : 0;
     unsigned long long k1 = ~0ull, k2 = ~0ull;
@@ -231,11 +240,10 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
       const uint32_t st = t % MT_STAGES, ph = (t / MT_STAGES) & 1u;
       const uint32_t buf = t & 1u, bph = (t >> 1) & 1u;
       const uint32_t b0 = (t_begin + t) * MT_N;
-      const uint32_t valid = min((uint32_t)MT_N, nb - b0);
       mbar_wait(BAR_FULL_B(st), ph); /* |b|^2 of this tile landed (same barrier as the B tile) */
       mbar_wait(BAR_TMEM_FULL(buf), bph);
       tmem_fence_after();
-      const uint32_t *nbs = s_nb + st * MT_N;
+      const uint32_t nbs = smem_u32(s_nb + st * MT_N);
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * MT_N;
 #pragma unroll 1
       for (int c0 = 0; c0 < MT_N; c0 += 32)
@@ -244,21 +252,41 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
         tmem_ld32(taddr + c0, acc);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; c++)
+        for (int g = 0; g < 2; g++)
         {
-          const int32_t e = (int32_t)nbs[c0 + c] - 2 * acc[c];
-          if (e <= thr && (uint32_t)(c0 + c) < valid)
+          int32_t e[16];
+#pragma unroll
+          for (int q = 0; q < 4; q++)
           {
-            const unsigned long long key = ((unsigned long long)(uint32_t)(e + my_na) << 32) | mt_pos(b0 + c0 + c);
-            if (key < k1)
+            const int4 n4 = lds_v4(nbs + (uint32_t)(c0 + g * 16 + q * 4) * 4u);
+            e[4 * q + 0] = n4.x - 2 * acc[g * 16 + 4 * q + 0];
+            e[4 * q + 1] = n4.y - 2 * acc[g * 16 + 4 * q + 1];
+            e[4 * q + 2] = n4.z - 2 * acc[g * 16 + 4 * q + 2];
+            e[4 * q + 3] = n4.w - 2 * acc[g * 16 + 4 * q + 3];
+          }
+          int32_t m = e[0];
+#pragma unroll
+          for (int q = 1; q < 16; q++)
+            m = min(m, e[q]);
+          if (m <= thr)
+          {
+#pragma unroll
+            for (int q = 0; q < 16; q++)
             {
-              k2 = k1;
-              k1 = key;
+              if (e[q] <= thr)
+              {
+                const unsigned long long key = ((unsigned long long)(uint32_t)(e[q] + my_na) << 32) | mt_pos(b0 + c0 + g * 16 + q);
+                if (key < k1)
+                {
+                  k2 = k1;
+                  k1 = key;
+                }
+                else if (key < k2)
+                  k2 = key;
+                if (k2 != ~0ull)
+                  thr = (int32_t)(uint32_t)(k2 >> 32) - my_na;
+              }
             }
-            else if (key < k2)
-              k2 = key;
-            if (k2 != ~0ull)
-              thr = (int32_t)(uint32_t)(k2 >> 32) - my_na;
           }
         }
       }

@@ -112,6 +112,7 @@ struct BlurPass
   int src_kind;
   int radius;
   int tiles_x, tiles_y, tile_begin; /* CTA range of this pass inside the launch */
+  int tile_h;                       /* output rows per tile chosen for this pass */
   float taps[VKS_MAX_TAPS];
 };
 #define VKS_MAX_PASSES_PER_STEP 4
@@ -143,8 +144,10 @@ void plan_sections(uint32_t max_feats, uint32_t n_oct, uint32_t *cap);
 struct FeatureBuffer;
 struct Instance;
 
+/* fills tiles_x/tiles_y/tile_begin/n_tiles of a step for the kernel that will run it */
+void blur_step_tiles(BlurStep *step);
 cudaError_t launch_blur_step(const BlurStep &step, cudaStream_t st);
-cudaError_t launch_extrema(const DetectParams &P, int octave, Candidate *cand, DetectCounters *cnt, cudaStream_t st);
+cudaError_t launch_extrema(const DetectParams &P, Candidate *cand, DetectCounters *cnt, cudaStream_t st);
 cudaError_t launch_order_primaries(const DetectParams &P, const Candidate *cand, DetectCounters *cnt, FeatHead *prim, cudaStream_t st);
 cudaError_t launch_orientation(const DetectParams &P, DetectCounters *cnt, const FeatHead *prim, float *ori, uint32_t *n_ori, cudaStream_t st);
 cudaError_t launch_assemble(const DetectParams &P, DetectCounters *cnt, const uint32_t *n_ori, uint32_t *feat_src, uint32_t *host_counts,
