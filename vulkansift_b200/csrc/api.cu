@@ -98,7 +98,11 @@ struct vksift_Instance_T
   uint32_t cur_w = 0, cur_h = 0;
   ScalePlan scales;
   Pyramid pyr;
-  std::vector<BlurStep> steps;
+  std::vector<BlurStep> steps_main; /* octaves on the fast kernel, main stream */
+  std::vector<BlurStep> steps_side; /* small octaves, compact kernel, side stream */
+  int fork_after_main = -1;         /* main step after which the side chain may start */
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   uint8_t *h_image = nullptr; /* pinned */
   uint8_t *d_image = nullptr;
@@ -262,7 +266,6 @@ void build_blur_plan(vksift_Instance inst)
 {
   const Pyramid &p = inst->pyr;
   const int ns = inst->cfg.nb_scales_per_octave;
-  inst->steps.clear();
   auto make_pass = [&](uint32_t o, int s) {
     BlurPass bp;
     memset(&bp, 0, sizeof(bp));
@@ -302,26 +305,55 @@ void build_blur_plan(vksift_Instance inst)
    * o >= 1 is written by the pass that produces layer ns of octave o-1, so pass (o,s) is ready at step
    * ns*o + s.  All passes of one step share a launch: the late scales of a large octave then run next to
    * the early scales of the following, smaller octave instead of 36 strictly serial launches
-   * (reference order: sift_detector.c:1369-1378 records octave after octave). */
+   * (reference order: sift_detector.c:1369-1378 records octave after octave).
+   * Large octaves [0,k) run on the unrolled kernel in the main stream; the small octaves [k,n) are latency
+   * bound, run on the compact kernel and form their own wavefront in a side stream that forks off after
+   * the pass producing their seed and joins before the extrema scan. */
+  inst->steps_main.clear();
+  inst->steps_side.clear();
+  inst->fork_after_main = -1;
   if (p.n_oct == 0)
     return;
-  const int n_steps = ns * ((int)p.n_oct - 1) + ns + 3;
-  for (int t = 0; t < n_steps; t++)
+  int k = 0;
+  for (; k < (int)p.n_oct; k++)
   {
-    BlurStep step;
-    memset(&step, 0, sizeof(step));
-    /* smaller octaves first: they are on the critical path, the big pass fills the remaining SMs */
-    for (int o = (int)p.n_oct - 1; o >= 0; o--)
+    bool fast = true;
+    for (int s = (k == 0 ? 0 : 1); s < ns + 3 && fast; s++)
     {
-      const int s = t - ns * o;
-      if (s < (o == 0 ? 0 : 1) || s > ns + 2 || step.n_pass >= VKS_MAX_PASSES_PER_STEP)
-        continue;
-      step.pass[step.n_pass++] = make_pass((uint32_t)o, s);
+      const BlurPass bp = make_pass((uint32_t)k, s);
+      fast = blur_pass_is_fast(bp);
     }
-    if (step.n_pass == 0)
-      continue;
-    blur_step_tiles(&step);
-    inst->steps.push_back(step);
+    if (!fast)
+      break;
+  }
+  auto wavefront = [&](int o_begin, int o_end, std::vector<BlurStep> &out) {
+    if (o_end <= o_begin)
+      return;
+    const int n_steps = ns * (o_end - o_begin - 1) + ns + 3;
+    for (int t = 0; t < n_steps; t++)
+    {
+      BlurStep step;
+      memset(&step, 0, sizeof(step));
+      /* smaller octaves first: they are on the critical path, the big pass fills the remaining SMs */
+      for (int o = o_end - 1; o >= o_begin; o--)
+      {
+        const int s = t - ns * (o - o_begin);
+        if (s < (o == 0 ? 0 : 1) || s > ns + 2 || step.n_pass >= VKS_MAX_PASSES_PER_STEP)
+          continue;
+        step.pass[step.n_pass++] = make_pass((uint32_t)o, s);
+      }
+      if (step.n_pass == 0)
+        continue;
+      blur_step_tiles(&step);
+      out.push_back(step);
+    }
+  };
+  wavefront(0, k, inst->steps_main);
+  wavefront(k, (int)p.n_oct, inst->steps_side);
+  if (k > 0 && k < (int)p.n_oct)
+  {
+    /* the seed of octave k is written by pass (k-1, ns) = main step ns*(k-1)+ns (octave 0 starts at s=0) */
+    inst->fork_after_main = ns * (k - 1) + ns;
   }
 }
 
@@ -445,6 +477,12 @@ void destroy_instance(vksift_Instance inst)
     cudaEventDestroy(inst->ev_detect_done);
   if (inst->ev_match_done)
     cudaEventDestroy(inst->ev_match_done);
+  if (inst->ev_fork)
+    cudaEventDestroy(inst->ev_fork);
+  if (inst->ev_join)
+    cudaEventDestroy(inst->ev_join);
+  if (inst->side_stream)
+    cudaStreamDestroy(inst->side_stream);
   if (inst->stream)
     cudaStreamDestroy(inst->stream);
   delete inst;
@@ -454,6 +492,9 @@ bool create_resources(vksift_Instance inst)
 {
   const vksift_Config &c = inst->cfg;
   CU_TRY(cudaStreamCreateWithFlags(&inst->stream, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&inst->side_stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreateWithFlags(&inst->ev_fork, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&inst->ev_join, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&inst->ev_detect_done, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&inst->ev_match_done, cudaEventDisableTiming));
   for (int i = 0; i < EV_COUNT; i++)
@@ -513,13 +554,40 @@ bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t bu
   if (prof)
     CU_TRY(cudaEventRecord(inst->ev[EV_D0], st));
   CU_TRY(cudaMemsetAsync(fb.cnt, 0, sizeof(DetectCounters), st));
-  for (BlurStep &step : inst->steps)
-  {
+  auto run_step = [&](BlurStep &step, cudaStream_t s) -> bool {
     for (int i = 0; i < step.n_pass; i++)
       if (step.pass[i].src_kind != BLUR_SRC_LAYER)
         step.pass[i].src = d_image;
-    CU_TRY(launch_blur_step(step, st));
+    CU_TRY(launch_blur_step(step, s));
     inst->launches++;
+    return true;
+  };
+  if (inst->steps_main.empty())
+  {
+    for (BlurStep &step : inst->steps_side)
+      if (!run_step(step, st))
+        return false;
+  }
+  else
+  {
+    bool forked = false;
+    for (size_t i = 0; i < inst->steps_main.size(); i++)
+    {
+      if (!run_step(inst->steps_main[i], st))
+        return false;
+      if ((int)i == inst->fork_after_main && !inst->steps_side.empty())
+      {
+        CU_TRY(cudaEventRecord(inst->ev_fork, st));
+        CU_TRY(cudaStreamWaitEvent(inst->side_stream, inst->ev_fork, 0));
+        for (BlurStep &step : inst->steps_side)
+          if (!run_step(step, inst->side_stream))
+            return false;
+        CU_TRY(cudaEventRecord(inst->ev_join, inst->side_stream));
+        forked = true;
+      }
+    }
+    if (forked)
+      CU_TRY(cudaStreamWaitEvent(st, inst->ev_join, 0));
   }
   if (prof)
     CU_TRY(cudaEventRecord(inst->ev[EV_D1], st));

@@ -69,12 +69,20 @@ __global__ void __launch_bounds__(ORI_WARPS * 32) orientation_kernel(const __gri
     float m = 0.f;
     for (int i = -r; i <= r; i++)
     {
-      for (int j0 = -r; j0 <= r; j0 += 32)
+      /* first 32 terms of the row: fixed-length unrolled chain so the shuffles pipeline; lanes past the
+       * row end contribute +0.0f, which leaves the positive partial sum bit-identical */
+      {
+        const int j = -r + lane;
+        const float term = (j <= r) ? vks_expf(es * (float)((i * i) + (j * j))) * VKS_SQRT2_F : 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; k++)
+          m += __shfl_sync(0xffffffffu, term, k);
+      }
+      /* remaining terms (box side 33 at most for sigma' < 3.7, generic otherwise) */
+      for (int j0 = -r + 32; j0 <= r; j0 += 32)
       {
         const int j = j0 + lane;
-        float term = 0.f;
-        if (j <= r)
-          term = vks_expf(es * (float)((i * i) + (j * j))) * VKS_SQRT2_F;
+        const float term = (j <= r) ? vks_expf(es * (float)((i * i) + (j * j))) * VKS_SQRT2_F : 0.f;
         const int cntj = min(32, r - j0 + 1);
         for (int k = 0; k < cntj; k++)
           m += __shfl_sync(0xffffffffu, term, k);

@@ -134,18 +134,34 @@ __global__ void __launch_bounds__(256) extrema_kernel(const __grid_constant__ De
   const int x0 = (t % tx) * EX_TW, y0 = (t / tx) * EX_TH;
   const int tid = threadIdx.x;
 
-  /* stage: layer l, smem row r <-> image row y0-1+r, smem col c <-> image col x0-4+c */
+  /* stage: layer l, smem row r <-> image row y0-1+r, smem col c <-> image col x0-4+c.
+   * Loads are issued in batches of 6 per thread before any store so their latencies overlap. */
   const int n_items = nl * EX_SH * (EX_SW / 4);
-  for (int it = tid; it < n_items; it += 256)
+  for (int it0 = tid; it0 < n_items; it0 += 6 * 256)
   {
-    const int l = it / (EX_SH * (EX_SW / 4));
-    const int rem = it - l * (EX_SH * (EX_SW / 4));
-    const int r = rem / (EX_SW / 4), c4 = rem - r * (EX_SW / 4);
-    const int gy = y0 - 1 + r, gx = x0 - 4 + c4 * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gy >= 0 && gy < ov.h && gx >= 0 && gx + 3 < ov.pitch)
-      v = __ldg((const float4 *)(ov.D + (size_t)l * ov.layer_stride + (size_t)gy * ov.pitch + gx));
-    *(float4 *)(ex_smem + (l * EX_SH + r) * EX_SW + c4 * 4) = v;
+    float4 v[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+    {
+      const int it = it0 + k * 256;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (it < n_items)
+      {
+        const int l = it / (EX_SH * (EX_SW / 4));
+        const int rem = it - l * (EX_SH * (EX_SW / 4));
+        const int r = rem / (EX_SW / 4), c4 = rem - r * (EX_SW / 4);
+        const int gy = y0 - 1 + r, gx = x0 - 4 + c4 * 4;
+        if (gy >= 0 && gy < ov.h && gx >= 0 && gx + 3 < ov.pitch)
+          v[k] = __ldg((const float4 *)(ov.D + (size_t)l * ov.layer_stride + (size_t)gy * ov.pitch + gx));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+    {
+      const int it = it0 + k * 256;
+      if (it < n_items)
+        *(float4 *)(ex_smem + it * 4) = v[k]; /* item order == smem order: (l, r, c4) row-major */
+    }
   }
   __syncthreads();
 

@@ -77,21 +77,28 @@ __device__ __forceinline__ float fetch_src(const BlurPass &p, int x, int y)
   return vks_unorm8(((const uint8_t *)p.src)[(size_t)y * p.src_w + x]);
 }
 
-/* ---- baseline tile kernel ------------------------------------------------
- * 64x32 output tile per CTA, 256 threads.  Stage 1 loads the tile plus a halo
- * of `radius` on every side, stage 2 blurs rows (for tile rows plus the
- * vertical halo), stage 3 blurs columns and writes G, DoG and the decimated
- * seed of the next octave. */
-#define BT_W 64
-#define BT_H 32
-#define BT_RMAX 19
-#define BT_IN_W (BT_W + 2 * BT_RMAX + 2) /* 104, even row length */
-#define BT_IN_H (BT_H + 2 * BT_RMAX)     /* 70 */
+/* ---- compact tile kernel ----------------------------------------------------
+ * Any radius (<= 20), 32x16 output tile, 256 threads, rolled tap loops: a few hundred bytes of
+ * code.  It runs the small octaves, where a launch is latency bound and the unrolled fast kernel
+ * below loses more time fetching its straight-line code than computing, and every pass whose
+ * radius the fast kernel does not cover.  Same per-pixel operation sequence as everywhere. */
+#define SB_W 32
+#define SB_H 16
+#define SB_RMAX 20
+#define SB_IN_W (SB_W + 2 * SB_RMAX)
+#define SB_IN_H (SB_H + 2 * SB_RMAX)
 
-__global__ void __launch_bounds__(256) blur_step_kernel(const __grid_constant__ BlurStep S)
+/* reflect once on either side: valid for -n <= i < 2n */
+__device__ __forceinline__ int mirror_once(int i, int n)
 {
-  __shared__ float s_in[BT_IN_H][BT_IN_W];
-  __shared__ float s_mid[BT_IN_H][BT_W];
+  i = i < 0 ? -1 - i : i;
+  return i >= n ? 2 * n - 1 - i : i;
+}
+
+__global__ void __launch_bounds__(256) blur_step_small_kernel(const __grid_constant__ BlurStep S)
+{
+  __shared__ float s_in[SB_IN_H * SB_IN_W];
+  __shared__ float s_mid[SB_IN_H * SB_W];
 
   int pi = 0;
 #pragma unroll
@@ -100,42 +107,76 @@ __global__ void __launch_bounds__(256) blur_step_kernel(const __grid_constant__ 
       pi = i;
   const BlurPass &p = S.pass[pi];
   const int t = (int)blockIdx.x - p.tile_begin;
-  const int x0 = (t % p.tiles_x) * BT_W;
-  const int y0 = (t / p.tiles_x) * BT_H;
+  const int x0 = (t % p.tiles_x) * SB_W;
+  const int y0 = (t / p.tiles_x) * SB_H;
   const int R = p.radius;
-  const int in_w = BT_W + 2 * R, in_h = BT_H + 2 * R;
+  const int in_w = SB_W + 2 * R;
+  const int rows_valid = min(SB_H, p.h - y0);
+  const int in_h = rows_valid + 2 * R;
   const int tid = threadIdx.x;
+  const int n_el = in_w * in_h;
 
-  for (int i = tid; i < in_w * in_h; i += 256)
+  if (p.src_kind == BLUR_SRC_LAYER)
   {
-    const int yy = i / in_w, xx = i - yy * in_w;
-    s_in[yy][xx] = fetch_src(p, x0 - R + xx, y0 - R + yy);
+    const bool once = (x0 - R >= -p.w) && (x0 + SB_W + R <= 2 * p.w) && (y0 - R >= -p.h) && (y0 + SB_H + R <= 2 * p.h);
+    const float *__restrict__ src = (const float *)p.src;
+    for (int i0 = tid; i0 < n_el; i0 += 8 * 256)
+    {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+      {
+        const int i = i0 + k * 256;
+        v[k] = 0.f;
+        if (i < n_el)
+        {
+          const int m = i / in_w, c = i - m * in_w;
+          int gx = x0 - R + c, gy = y0 - R + m;
+          gx = once ? mirror_once(gx, p.w) : vks_mirror(gx, p.w);
+          gy = once ? mirror_once(gy, p.h) : vks_mirror(gy, p.h);
+          v[k] = __ldg(src + (size_t)gy * p.src_pitch + gx);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (i0 + k * 256 < n_el)
+          s_in[i0 + k * 256] = v[k];
+    }
+  }
+  else
+  {
+    for (int i = tid; i < n_el; i += 256)
+    {
+      const int m = i / in_w, c = i - m * in_w;
+      s_in[i] = fetch_src(p, x0 - R + c, y0 - R + m);
+    }
   }
   __syncthreads();
 
-  for (int i = tid; i < in_h * BT_W; i += 256)
+  for (int i = tid; i < in_h * SB_W; i += 256)
   {
-    const int yy = i / BT_W, xx = i - yy * BT_W;
-    const float *row = &s_in[yy][xx + R];
+    const int yy = i / SB_W, xx = i - yy * SB_W;
+    const float *row = s_in + yy * in_w + xx + R;
     float acc = vks_mul(row[0], p.taps[0]);
     for (int k = 1; k <= R; k++)
       acc = vks_blur_tap(acc, row[k], row[-k], p.taps[k]);
-    s_mid[yy][xx] = acc;
+    s_mid[i] = acc;
   }
   __syncthreads();
 
-  for (int i = tid; i < BT_H * BT_W; i += 256)
+  for (int i = tid; i < rows_valid * SB_W; i += 256)
   {
-    const int yy = i / BT_W, xx = i - yy * BT_W;
+    const int yy = i / SB_W, xx = i - yy * SB_W;
     const int x = x0 + xx, y = y0 + yy;
-    if (x >= p.w || y >= p.h)
+    if (x >= p.w)
       continue;
-    float acc = vks_mul(s_mid[yy + R][xx], p.taps[0]);
+    const float *col = s_mid + (yy + R) * SB_W + xx;
+    float acc = vks_mul(col[0], p.taps[0]);
     for (int k = 1; k <= R; k++)
-      acc = vks_blur_tap(acc, s_mid[yy + R + k][xx], s_mid[yy + R - k][xx], p.taps[k]);
+      acc = vks_blur_tap(acc, col[k * SB_W], col[-k * SB_W], p.taps[k]);
     p.dst_g[(size_t)y * p.dst_pitch + x] = acc;
     if (p.dst_d)
-      p.dst_d[(size_t)y * p.dst_pitch + x] = vks_sub(acc, s_in[yy + R][xx + R]);
+      p.dst_d[(size_t)y * p.dst_pitch + x] = vks_sub(acc, s_in[(yy + R) * in_w + xx + R]);
     if (p.dst_next && (x & 1) && (y & 1))
     {
       const int nx = x >> 1, ny = y >> 1;
@@ -144,7 +185,6 @@ __global__ void __launch_bounds__(256) blur_step_kernel(const __grid_constant__ 
     }
   }
 }
-
 
 /* ==========================================================================
  * Fast tile kernel: even radius <= 12 (every scale of the default configuration).
@@ -192,19 +232,13 @@ __device__ __forceinline__ float pk_hi(pk2 a) { return __uint_as_float((uint32_t
 __device__ __forceinline__ pk2 pk_make(float lo, float hi) { return (pk2)__float_as_uint(lo) | ((pk2)__float_as_uint(hi) << 32); }
 
 #define FT_W 64
+#define FT_H 128
 #define FT_THREADS 256
 #define FT_MS (FT_W + 2) /* row stride of the horizontal-pass result, floats */
 
 __host__ __device__ constexpr int ft_rx(int R) { return (R + 3) & ~3; }                              /* x halo rounded to float4 */
 __host__ __device__ constexpr int ft_ss(int R) { return (((FT_W + 2 * ft_rx(R)) * 2 / 4) | 1) * 4; } /* floats per row pair, stride/4 odd */
 __host__ __device__ constexpr int ft_smem_floats(int R, int TH) { return ((TH + 2 * R) / 2) * ft_ss(R) + (TH + 2 * R) * FT_MS; }
-
-/* reflect once on either side: valid for -n <= i < 2n */
-__device__ __forceinline__ int mirror_once(int i, int n)
-{
-  i = i < 0 ? -1 - i : i;
-  return i >= n ? 2 * n - 1 - i : i;
-}
 
 template <int R, int TH>
 __device__ __forceinline__ void blur_tile_fast(const BlurPass &p, const pk2 *__restrict__ taps2, float *smem, int x0, int y0)
@@ -460,36 +494,30 @@ __global__ void __launch_bounds__(FT_THREADS, 2) blur_step_fast_kernel(const __g
   const pk2 *taps2 = reinterpret_cast<const pk2 *>(S.taps2[pi]);
   const int t = (int)blockIdx.x - p.tile_begin;
   const int x0 = (t % p.tiles_x) * FT_W;
-  const int y0 = (t / p.tiles_x) * p.tile_h;
-  if (p.tile_h == 128)
-    blur_tile_dispatch<128>(p, taps2, ft_smem, x0, y0);
-  else
-    blur_tile_dispatch<32>(p, taps2, ft_smem, x0, y0);
+  const int y0 = (t / p.tiles_x) * FT_H;
+  blur_tile_dispatch<FT_H>(p, taps2, ft_smem, x0, y0);
 }
 
-bool blur_step_is_fast(const BlurStep &step)
+/* A pass goes to the fast kernel when its radius is covered and the layer is large enough for
+ * throughput to matter (more 64x128 tiles than SMs); everything else runs on the compact kernel. */
+bool blur_pass_is_fast(const BlurPass &bp)
 {
-  for (int i = 0; i < step.n_pass; i++)
-    if (step.pass[i].radius > 12 || step.pass[i].radius < 1)
-      return false;
-  return step.n_pass > 0;
+  if (bp.radius < 1 || bp.radius > 12)
+    return false;
+  return ((bp.w + FT_W - 1) / FT_W) * ((bp.h + FT_H - 1) / FT_H) >= 148;
 }
+
+bool blur_step_is_fast(const BlurStep &step) { return step.n_pass > 0 && blur_pass_is_fast(step.pass[0]); }
 
 void blur_step_tiles(BlurStep *step)
 {
-  /* tile geometry depends on the kernel that will run the step */
+  /* tile geometry depends on the kernel that will run the step; a step never mixes the two kinds */
   const bool fast = blur_step_is_fast(*step);
+  const int tw = fast ? FT_W : SB_W, th = fast ? FT_H : SB_H;
   int begin = 0;
   for (int i = 0; i < step->n_pass; i++)
   {
     BlurPass &bp = step->pass[i];
-    int tw = BT_W, th = BT_H;
-    if (fast)
-    {
-      /* tall tiles amortise the vertical halo; small layers take short tiles so that every SM gets work */
-      tw = FT_W;
-      th = (((bp.w + FT_W - 1) / FT_W) * ((bp.h + 127) / 128) > 148) ? 128 : 32;
-    }
     bp.tile_h = th;
     bp.tiles_x = (bp.w + tw - 1) / tw;
     bp.tiles_y = (bp.h + th - 1) / th;
@@ -507,7 +535,7 @@ static cudaError_t launch_blur_step_fast(const BlurStep &step, cudaStream_t st)
   if (dev < 64 && !attr_done[dev])
   {
     cudaError_t e =
-        cudaFuncSetAttribute(blur_step_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(float) * ft_smem_floats(12, 128));
+        cudaFuncSetAttribute(blur_step_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(float) * ft_smem_floats(12, FT_H));
     if (e != cudaSuccess)
       return e;
     attr_done[dev] = true;
@@ -518,7 +546,7 @@ static cudaError_t launch_blur_step_fast(const BlurStep &step, cudaStream_t st)
   for (int i = 0; i < step.n_pass; i++)
   {
     const int re = (step.pass[i].radius + 1) & ~1;
-    const size_t need = sizeof(float) * (size_t)ft_smem_floats(re < 2 ? 2 : re, step.pass[i].tile_h);
+    const size_t need = sizeof(float) * (size_t)ft_smem_floats(re < 2 ? 2 : re, FT_H);
     smem = need > smem ? need : smem;
     for (int k = 0; k < 14; k++)
     {
@@ -536,7 +564,7 @@ cudaError_t launch_blur_step(const BlurStep &step, cudaStream_t st)
     return cudaSuccess;
   if (blur_step_is_fast(step))
     return launch_blur_step_fast(step, st);
-  blur_step_kernel<<<step.n_tiles, 256, 0, st>>>(step);
+  blur_step_small_kernel<<<step.n_tiles, 256, 0, st>>>(step);
   return cudaGetLastError();
 }
 

@@ -146,6 +146,8 @@ struct Instance;
 
 /* fills tiles_x/tiles_y/tile_begin/n_tiles of a step for the kernel that will run it */
 void blur_step_tiles(BlurStep *step);
+/* true when the pass runs on the unrolled packed-fp32 kernel, false for the compact kernel */
+bool blur_pass_is_fast(const BlurPass &bp);
 cudaError_t launch_blur_step(const BlurStep &step, cudaStream_t st);
 cudaError_t launch_extrema(const DetectParams &P, Candidate *cand, DetectCounters *cnt, cudaStream_t st);
 cudaError_t launch_order_primaries(const DetectParams &P, const Candidate *cand, DetectCounters *cnt, FeatHead *prim, cudaStream_t st);
