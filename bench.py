@@ -311,6 +311,36 @@ def main():
         minst.download_matches()
     match_e2e_s = (time.perf_counter() - t0) / 5
 
+    # ---------------- all-pairs cross-image matching (configs[4] pattern), N > 1 only ----------------
+    allpairs = None
+    if world > 1:
+        from vulkansift_b200 import dist as vdist
+        own = blob_image(**dict(C2, seed=C2["seed"] + 100 + rank))
+        inst.detect(own, 0)
+        n_own = inst.features_number(0)
+        reps = 5
+        ap_t, gather_t = [], []
+        for rep in range(reps + 1):
+            barrier()
+            t0 = time.perf_counter()
+            counts_g, blocks_g = vdist.gather_instance_descriptors(inst, 0)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            vdist.match_against_peers(inst, 0, 1, counts_g, blocks_g, rank, world, download=True)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            if rep > 0:  # first repetition warms NCCL up
+                gather_t.append(t1 - t0)
+                ap_t.append(t2 - t0)
+        ap = torch.tensor([sum(ap_t) / reps, sum(gather_t) / reps], dtype=torch.float64, device="cuda")
+        rows = torch.tensor([float(n_own * (world - 1))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ap, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rows, op=dist.ReduceOp.SUM)
+        allpairs = {"workload": "one 1920x1080 image per GPU, NCCL all-gather of descriptor blocks, every GPU matches its features "
+                                "against each of the %d other blocks (ordered pairs: %d)" % (world - 1, world * (world - 1)),
+                    "value": rows.item() / ap[0].item(), "unit": "matches/s", "ms_total": 1e3 * ap[0].item(),
+                    "ms_gather": 1e3 * ap[1].item(), "matched_rows": rows.item()}
+
     # ---------------- reduce over ranks ----------------
     vals = torch.tensor([dev_ms, e2e_s, match_ms, match_kernel_ms, stage_acc.get("pyramid_dog", 0.0) / K], dtype=torch.float64, device="cuda")
     sums = torch.tensor([float(n_feat), float(e2e_feat)], dtype=torch.float64, device="cuda")
@@ -344,6 +374,8 @@ def main():
                                    "flops": flops, "peak_source": peak_src + " bf16 dense burst (i8 operands run at 2x this rate)"}},
             "clocks": clocks,
         }
+        if allpairs:
+            line["allpairs"] = allpairs
         if not args.no_cpu_baseline and world >= 1:
             cb = cpu_port_baseline(images)
             line["cpu_baseline"] = cb

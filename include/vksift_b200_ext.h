@@ -49,6 +49,11 @@ extern "C"
   VKSIFT_EXPORT void vksiftx_uploadDescriptorsDevice(vksift_Instance instance, const void *d_descriptors, const uint32_t nb_feats,
                                                      const uint32_t gpu_buffer_id);
 
+  /* Copy the packed descriptors of a feature buffer into caller-owned device memory ([capacity][128] u8,
+   * e.g. the send slot of an NCCL all-gather); rows past the feature count are zero-filled up to
+   * `capacity`.  Returns the feature count.  Blocking like the other transfer functions. */
+  VKSIFT_EXPORT uint32_t vksiftx_copyDescriptorsToDevice(vksift_Instance instance, const uint32_t gpu_buffer_id, void *d_dst, const uint32_t capacity);
+
   /* Device pointer of the last match result: vksift_getMatchesNumber() rows of vksift_Match_2NN. */
   VKSIFT_EXPORT void *vksiftx_getMatchesDevice(vksift_Instance instance);
 

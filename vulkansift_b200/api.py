@@ -95,6 +95,7 @@ def _load_library():
         "vksiftx_waitIdle": (None, [I]),
         "vksiftx_getBufferDeviceView": (None, [I, u32, P(u32), P(C.c_void_p), P(C.c_void_p)]),
         "vksiftx_uploadDescriptorsDevice": (None, [I, C.c_void_p, u32, u32]),
+        "vksiftx_copyDescriptorsToDevice": (u32, [I, u32, C.c_void_p, u32]),
         "vksiftx_getMatchesDevice": (C.c_void_p, [I]),
         "vksiftx_setProfiling": (None, [I, C.c_bool]),
         "vksiftx_getStageTimesMs": (None, [I, P(C.c_float)]),
@@ -283,6 +284,11 @@ class Instance:
     def upload_descriptors_device(self, dev_ptr, n, buffer_id=0):
         lib.vksiftx_uploadDescriptorsDevice(self._h, dev_ptr, n, buffer_id)
         self._check("vksiftx_uploadDescriptorsDevice")
+
+    def copy_descriptors_to_device(self, buffer_id, dev_ptr, capacity):
+        n = lib.vksiftx_copyDescriptorsToDevice(self._h, buffer_id, dev_ptr, capacity)
+        self._check("vksiftx_copyDescriptorsToDevice")
+        return n
 
     def matches_device(self):
         return lib.vksiftx_getMatchesDevice(self._h)

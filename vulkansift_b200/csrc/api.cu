@@ -1174,6 +1174,51 @@ extern "C"
       *d_heads = inst->buffers[gpu_buffer_id].heads;
   }
 
+  uint32_t vksiftx_copyDescriptorsToDevice(vksift_Instance inst, const uint32_t gpu_buffer_id, void *d_dst, const uint32_t capacity)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id) || d_dst == NULL)
+    {
+      LOGE(TAG, "vksiftx_copyDescriptorsToDevice() error: invalid input.");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return 0;
+    }
+    bool ok = true, too_small = false;
+    uint32_t n = 0;
+    {
+      DeviceGuard g(inst->device);
+      if (!vksift_isBufferAvailable(inst, gpu_buffer_id))
+        wait_pipelines(inst, true, true);
+      n = buffer_count(inst, gpu_buffer_id, false);
+      if (n > capacity)
+        too_small = true;
+      else
+      {
+        auto run = [&]() -> bool {
+          if (n > 0)
+            CU_TRY(cudaMemcpyAsync(d_dst, inst->buffers[gpu_buffer_id].desc, 128 * (size_t)n, cudaMemcpyDeviceToDevice, inst->stream));
+          if (capacity > n)
+            CU_TRY(cudaMemsetAsync((uint8_t *)d_dst + 128 * (size_t)n, 0, 128 * (size_t)(capacity - n), inst->stream));
+          CU_TRY(cudaStreamSynchronize(inst->stream));
+          return true;
+        };
+        ok = run();
+      }
+    }
+    if (too_small)
+    {
+      LOGE(TAG, "vksiftx_copyDescriptorsToDevice() error: destination holds %u descriptors, the buffer has %u.", capacity, n);
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return 0;
+    }
+    if (!ok)
+    {
+      LOGE(TAG, "vksiftx_copyDescriptorsToDevice() error when copying descriptors.");
+      inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
+      return 0;
+    }
+    return n;
+  }
+
   void *vksiftx_getMatchesDevice(vksift_Instance inst) { return inst->d_matches; }
 
   void vksiftx_setProfiling(vksift_Instance inst, const bool enabled) { inst->profiling = enabled; }

@@ -29,10 +29,14 @@ struct MatchWorkspace
 };
 
 /* ---- |x|^2 per descriptor ------------------------------------------------ */
-#define NORM_PAD_VALUE 0x40000000u /* |b|^2 of a row that does not exist: loses every comparison */
-__global__ void norms_kernel(const uint8_t *__restrict__ desc, uint32_t n, uint32_t n_padded, uint32_t *__restrict__ out)
+__device__ __forceinline__ uint32_t match_pos_host_device(uint32_t b) { return b < 2u ? (b ^ 1u) : b; }
+/* |x|^2 per descriptor.  packed == 0: plain norms (A side).  packed == 1 (B side): nbk = |b|^2 * 256 + (pos(b) & 255),
+ * the per-column constant of the tensor-core epilogue's 32-bit keys; |b|^2 <= 128*255^2 < 2^23 so nbk fits int32.
+ * Rows in [n, n_padded) do not exist and get the largest nbk: they lose every comparison. */
+#define NORM_PAD_VALUE 0x7fffffffu
+__global__ void norms_kernel(const uint8_t *__restrict__ desc, uint32_t n, uint32_t n_padded, uint32_t *__restrict__ out, int packed)
 {
-  /* one warp per descriptor, 4 bytes per lane; rows in [n, n_padded) get the pad value */
+  /* one warp per descriptor, 4 bytes per lane */
   const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n)
@@ -47,7 +51,7 @@ __global__ void norms_kernel(const uint8_t *__restrict__ desc, uint32_t n, uint3
   for (int d = 16; d > 0; d >>= 1)
     s += __shfl_xor_sync(0xffffffffu, s, d);
   if (lane == 0)
-    out[row] = s;
+    out[row] = packed ? (s * 256u + (match_pos_host_device(row) & 255u)) : s;
 }
 
 /* ---- SIMT cross-check kernel (verification only, vksiftx_setMatcherImpl(1)) */
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(MS_ROWS) match_simt_kernel(const uint8_t *__re
     for (uint32_t i = threadIdx.x; i < cnt * 32; i += MS_ROWS)
       s_b[i >> 5][i & 31] = __ldg((const uint32_t *)(db + (size_t)b0 * 128) + i);
     if (threadIdx.x < cnt)
-      s_nb[threadIdx.x] = norm_b[b0 + threadIdx.x];
+      s_nb[threadIdx.x] = norm_b[b0 + threadIdx.x] >> 8; /* norm_b holds the packed nbk */
     __syncthreads();
     for (uint32_t j = 0; j < cnt; j++)
     {
@@ -148,8 +152,8 @@ cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *da, uint32
   if (na == 0)
     return cudaSuccess;
   const uint32_t nb_pad = (nb + 127u) & ~127u; /* the tensor-core path reads |b|^2 in tiles of 128 */
-  norms_kernel<<<(na * 32 + 255) / 256, 256, 0, st>>>(da, na, na, ws->norm_a);
-  norms_kernel<<<(nb_pad * 32 + 255) / 256, 256, 0, st>>>(db, nb, nb_pad, ws->norm_b);
+  norms_kernel<<<(na * 32 + 255) / 256, 256, 0, st>>>(da, na, na, ws->norm_a, 0);
+  norms_kernel<<<(nb_pad * 32 + 255) / 256, 256, 0, st>>>(db, nb, nb_pad, ws->norm_b, 1);
   *launch_count += 2;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)

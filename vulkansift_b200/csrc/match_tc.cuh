@@ -5,9 +5,10 @@
  * K = 128 (one 128-byte row = one SWIZZLE_128B atom row, four K=32 MMAs):
  *
  *   TMA (cp.async.bulk.tensor.2d, 128B swizzle)  ->  smem A tile 128x128 B (once per CTA)
- *                                                ->  smem B tiles 128x128 B + 512 B of |b|^2, 4-stage ring
- *   tcgen05.mma.cta_group::1.kind::i8  M=128 N=128 K=32 x4 -> TMEM accumulator (2 x 128 columns, double buffered)
- *   4 epilogue warps: tcgen05.ld 32x32b.x32 -> e = |b|^2 - 2*dot, running top-2 per A row in registers
+ *                                                ->  smem B tiles 128x128 B + 512 B of packed |b|^2, 4-stage ring
+ *   tcgen05.mma.cta_group::1.kind::i8  M=128 N=128 K=32 x4 -> TMEM accumulators (2 x 128 columns, one per epilogue warpgroup)
+ *   2 x 4 epilogue warps (one warpgroup per TMEM buffer): tcgen05.ld 32x32b.x32 -> packed key
+ *     256*(|b|^2 - 2 a.b) + (pos & 255) with one IMAD, branch-free running top-2 of the keys (min/max only)
  *
  * One CTA owns 128 rows of A and a contiguous range of B tiles ("split");
  * partial top-2 keys ((d^2 << 32) | pos) go to HBM and a small merge kernel
@@ -29,12 +30,15 @@ namespace vks
 {
 
 #define MT_M 128        /* A rows per CTA = TMEM lanes */
-#define MT_N 128        /* B rows per MMA tile = TMEM columns per buffer */
+#define MT_N 128         /* B rows per MMA tile = TMEM columns per accumulator buffer */
 #define MT_STAGES 4     /* B smem ring */
+#define MT_BUFS 2       /* TMEM accumulator buffers, one per epilogue warpgroup (N=64 x 4 buffers measured 10% slower) */
 #define MT_TILE_BYTES (MT_N * 128)
-#define MT_THREADS 192  /* warps 0-3 epilogue, warp 4 TMA, warp 5 MMA + TMEM alloc */
+#define MT_THREADS 320  /* warps 0-3 and 4-7: two epilogue warpgroups (one per TMEM buffer), warp 8 TMA, warp 9 MMA + TMEM alloc */
+#define MT_WARP_TMA 8
+#define MT_WARP_MMA 9
 #define MT_TMEM_COLS 256
-#define MT_SMEM_BYTES (1024 + MT_M * 128 + MT_STAGES * (MT_TILE_BYTES + MT_N * 4) + 256)
+#define MT_SMEM_BYTES (1024 + MT_M * 128 + MT_STAGES * (MT_TILE_BYTES + MT_N * 4) + 512)
 
 /* ---- PTX wrappers --------------------------------------------------------- */
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -109,6 +113,18 @@ __device__ __forceinline__ int4 lds_v4(uint32_t saddr)
   return v;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+/* wait::ld that also names the destination registers of the load it completes, so the compiler cannot move
+ * any use of them above the wait (tcgen05.ld fills its registers asynchronously) */
+__device__ __forceinline__ void tmem_ld_wait_for(int32_t (&v)[32])
+{
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]),
+                 "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]),
+                 "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]),
+                 "+r"(v[31])
+               :
+               : "memory");
+}
 
 /* K-major SWIZZLE_128B operand descriptor: 8-row groups 1024 B apart (SBO), LBO unused (=1),
  * descriptor version 1, layout type 2.  (cute/arch/mma_sm100_desc.hpp SmemDescriptor) */
@@ -122,16 +138,20 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr)
   d |= (uint64_t)2 << 61;            /* SWIZZLE_128B */
   return d;
 }
-/* kind::i8 instruction descriptor: D=s32, A=B=u8, K-major both, N=128, M=128 */
+/* kind::i8 instruction descriptor: D=s32, A=B=u8, K-major both, N=MT_N, M=128 */
 #define MT_IDESC ((2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(MT_N >> 3) << 17) | ((uint32_t)(MT_M >> 4) << 24))
 
 __device__ __forceinline__ uint32_t mt_pos(uint32_t b) { return b < 2u ? (b ^ 1u) : b; }
 
-/* ---- main kernel ---------------------------------------------------------- */
+/* ---- main kernel ----------------------------------------------------------
+ * Work unit = (row block of 128 A rows, B tile of 128 rows); units are numbered row-block major and cut into
+ * equal contiguous ranges, one per CTA, so that 2 CTAs per SM all carry the same load whatever nA/128 is.
+ * A range may cross into the next row block: the CTA then starts a new "segment" (reloads A, flushes and
+ * resets the running top-2).  Segment j of row block rb lands in partial slot (rb, j). */
 __global__ void __launch_bounds__(MT_THREADS, 2)
     match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const uint32_t *__restrict__ norm_a,
-                    const uint32_t *__restrict__ norm_b, uint32_t na, uint32_t nb, uint32_t tiles_per_split, uint32_t n_tiles,
-                    unsigned long long *__restrict__ partial, uint32_t na_pad)
+                    const uint32_t *__restrict__ norm_b, uint32_t na, uint32_t n_tiles, uint32_t units_per_cta, uint32_t total_units,
+                    uint32_t max_segs, unsigned long long *__restrict__ partial, int32_t key_scale)
 {
   extern __shared__ uint8_t smem_raw[];
   /* 1024-byte alignment required by SWIZZLE_128B */
@@ -140,39 +160,39 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
   uint8_t *s_b = smem + MT_M * 128;
   uint32_t *s_nb = (uint32_t *)(s_b + MT_STAGES * MT_TILE_BYTES);
   uint64_t *s_bar = (uint64_t *)(s_nb + MT_STAGES * MT_N);
-  /* barriers: [0..S) full_b, [S..2S) empty_b, 2S full_a, 2S+1..2S+2 tmem_full, 2S+3..2S+4 tmem_empty */
-  uint32_t *s_tmem = (uint32_t *)(s_bar + 2 * MT_STAGES + 5);
+  /* barriers: [0..S) full_b, [S..2S) empty_b, 2S full_a, 2S+1 empty_a, then MT_BUFS tmem_full, MT_BUFS tmem_empty */
+  uint32_t *s_tmem = (uint32_t *)(s_bar + 2 * MT_STAGES + 2 + 2 * MT_BUFS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t row0 = blockIdx.x * MT_M;
-  const uint32_t split = blockIdx.y;
-  const uint32_t t_begin = split * tiles_per_split;
-  const uint32_t t_end = min(n_tiles, t_begin + tiles_per_split);
-  const uint32_t my_tiles = (t_end > t_begin) ? (t_end - t_begin) : 0u;
+  const uint32_t u0 = blockIdx.x * units_per_cta;
+  const uint32_t u1 = min(total_units, u0 + units_per_cta);
+  const uint32_t my_tiles = (u1 > u0) ? (u1 - u0) : 0u;
 
   const uint32_t bar0 = smem_u32(s_bar);
 #define BAR_FULL_B(i) (bar0 + 8u * (uint32_t)(i))
 #define BAR_EMPTY_B(i) (bar0 + 8u * (uint32_t)(MT_STAGES + (i)))
 #define BAR_FULL_A (bar0 + 8u * (uint32_t)(2 * MT_STAGES))
-#define BAR_TMEM_FULL(i) (bar0 + 8u * (uint32_t)(2 * MT_STAGES + 1 + (i)))
-#define BAR_TMEM_EMPTY(i) (bar0 + 8u * (uint32_t)(2 * MT_STAGES + 3 + (i)))
+#define BAR_EMPTY_A (bar0 + 8u * (uint32_t)(2 * MT_STAGES + 1))
+#define BAR_TMEM_FULL(i) (bar0 + 8u * (uint32_t)(2 * MT_STAGES + 2 + (i)))
+#define BAR_TMEM_EMPTY(i) (bar0 + 8u * (uint32_t)(2 * MT_STAGES + 2 + MT_BUFS + (i)))
 
   if (threadIdx.x == 0)
   {
     for (int i = 0; i < MT_STAGES; i++)
     {
       mbar_init(BAR_FULL_B(i), 1);
-      mbar_init(BAR_EMPTY_B(i), 1 + 4); /* MMA commit + 4 epilogue warps (they read the stage's |b|^2) */
+      mbar_init(BAR_EMPTY_B(i), 1 + 4); /* MMA commit + the 4 epilogue warps that read the stage's nbk */
     }
     mbar_init(BAR_FULL_A, 1);
-    for (int i = 0; i < 2; i++)
+    mbar_init(BAR_EMPTY_A, 1);
+    for (int i = 0; i < MT_BUFS; i++)
     {
       mbar_init(BAR_TMEM_FULL(i), 1);
       mbar_init(BAR_TMEM_EMPTY(i), 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5)
+  if (warp == MT_WARP_MMA)
   {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(MT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -181,38 +201,47 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
   __syncthreads();
   tmem_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  const uint32_t rb_first = u0 / n_tiles;
 
-  if (warp == 4)
+  if (warp == MT_WARP_TMA)
   {
     /* ===== TMA producer ===== */
     if (lane == 0)
     {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-      mbar_expect_tx(BAR_FULL_A, MT_M * 128);
-      tma_load_2d(smem_u32(s_a), &map_a, 0, (int)row0, BAR_FULL_A);
       for (uint32_t t = 0; t < my_tiles; t++)
       {
+        const uint32_t u = u0 + t, rb = u / n_tiles, tile = u - rb * n_tiles;
+        if (t == 0 || tile == 0)
+        {
+          const uint32_t seg = rb - rb_first;
+          mbar_wait(BAR_EMPTY_A, (seg & 1u) ^ 1u); /* previous segment's MMAs are done with the A tile */
+          mbar_expect_tx(BAR_FULL_A, MT_M * 128);
+          tma_load_2d(smem_u32(s_a), &map_a, 0, (int)(rb * MT_M), BAR_FULL_A);
+        }
         const uint32_t st = t % MT_STAGES, ph = (t / MT_STAGES) & 1u;
         mbar_wait(BAR_EMPTY_B(st), ph ^ 1u);
-        const uint32_t b0 = (t_begin + t) * MT_N;
+        const uint32_t b0 = tile * MT_N;
         mbar_expect_tx(BAR_FULL_B(st), MT_TILE_BYTES + MT_N * 4);
         tma_load_2d(smem_u32(s_b + st * MT_TILE_BYTES), &map_b, 0, (int)b0, BAR_FULL_B(st));
         bulk_load_1d(smem_u32(s_nb + st * MT_N), norm_b + b0, MT_N * 4, BAR_FULL_B(st));
       }
     }
   }
-  else if (warp == 5)
+  else if (warp == MT_WARP_MMA)
   {
     /* ===== MMA issuer (one thread) ===== */
     if (lane == 0)
     {
-      mbar_wait(BAR_FULL_A, 0);
       const uint64_t adesc = umma_smem_desc(smem_u32(s_a));
       for (uint32_t t = 0; t < my_tiles; t++)
       {
+        const uint32_t u = u0 + t, rb = u / n_tiles, tile = u - rb * n_tiles;
+        if (t == 0 || tile == 0)
+          mbar_wait(BAR_FULL_A, (rb - rb_first) & 1u);
         const uint32_t st = t % MT_STAGES, ph = (t / MT_STAGES) & 1u;
-        const uint32_t buf = t & 1u, bph = (t >> 1) & 1u;
+        const uint32_t buf = t % MT_BUFS, bph = (t / MT_BUFS) & 1u;
         mbar_wait(BAR_TMEM_EMPTY(buf), bph ^ 1u);
         mbar_wait(BAR_FULL_B(st), ph);
         tmem_fence_after();
@@ -222,72 +251,99 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
           umma_i8(tmem_base + buf * MT_N, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), MT_IDESC, k > 0 ? 1u : 0u);
         umma_commit(BAR_EMPTY_B(st));     /* smem stage consumed by the tensor core */
         umma_commit(BAR_TMEM_FULL(buf)); /* accumulator ready */
+        if (tile == n_tiles - 1 || t == my_tiles - 1)
+          umma_commit(BAR_EMPTY_A); /* last MMA of the segment: the A tile may be replaced */
       }
     }
   }
   else
   {
-    /* ===== epilogue: thread = A row, warp w reads TMEM lanes 32w..32w+31 =====
-     * Hot loop per accumulator: one IMAD (e = |b|^2 - 2 a.b) and a share of a min tree; only when the
-     * minimum of a 16-column group beats the row's current second best does the thread rescan that group
-     * with full (d^2, pos) keys.  Columns past nb carry |b|^2 = 2^30 (norms are padded), so they never win. */
-    const uint32_t row = row0 + warp * 32 + lane;
-    const int32_t my_na = (row < na) ? (int32_t)norm_a[row] : 0;
+    /* ===== epilogue: thread = A row; warpgroup g (warps 4g..4g+3) drains the tiles with (t & 1) == g, i.e.
+     * TMEM buffer g; warp w of a group reads TMEM lanes 32*(w%4).. =====
+     * Per accumulator: key = nbk[c] - 512*acc = 256*(|b|^2 - 2 a.b) + (pos & 255)  (one IMAD; nbk comes from the
+     * norms kernel), then a branch-free top-2 of the 32-bit keys with min/max.  Keys are unique inside a tile
+     * (distinct low bytes) and order exactly like (d^2, pos).  After each tile the two survivors are widened to
+     * 64-bit (d^2 << 32 | pos) keys and merged into the row's running top-2.  Columns past nb carry the largest
+     * possible nbk, so they only win when a segment holds fewer than two real columns (the merge drops them). */
+    const int wg = warp >> 2;
+    const uint32_t lrow = (uint32_t)(warp & 3) * 32 + lane;
     unsigned long long k1 = ~0ull, k2 = ~0ull;
-    int32_t thr = 0x7fffffff; /* e-threshold: second-best d^2 - |a|^2 */
-    for (uint32_t t = 0; t < my_tiles; t++)
+    int32_t my_na = 0;
+    uint32_t cur_rb = 0xffffffffu;
+    /* every (row block, segment, warpgroup) slot of this CTA is published, also when the warpgroup gets no
+     * tile of a short segment: start from "nothing found" and overwrite with the real result below */
+    if (my_tiles > 0)
+      for (uint32_t rb = rb_first; rb <= (u1 - 1) / n_tiles; rb++)
+      {
+        const uint32_t seg_slot = blockIdx.x - (rb * n_tiles) / units_per_cta;
+        const size_t slot = (((size_t)rb * max_segs + seg_slot) * 2 + wg) * MT_M + lrow;
+        partial[slot * 2 + 0] = ~0ull;
+        partial[slot * 2 + 1] = ~0ull;
+      }
+    for (uint32_t t = (uint32_t)wg; t < my_tiles; t += 2)
     {
+      const uint32_t u = u0 + t, rb = u / n_tiles, tile = u - rb * n_tiles;
+      if (rb != cur_rb)
+      {
+        if (cur_rb != 0xffffffffu)
+        {
+          /* flush the finished segment */
+          const uint32_t seg_slot = blockIdx.x - (cur_rb * n_tiles) / units_per_cta;
+          const size_t slot = (((size_t)cur_rb * max_segs + seg_slot) * 2 + wg) * MT_M + lrow;
+          partial[slot * 2 + 0] = k1;
+          partial[slot * 2 + 1] = k2;
+          k1 = k2 = ~0ull;
+        }
+        cur_rb = rb;
+        const uint32_t row = rb * MT_M + lrow;
+        my_na = (row < na) ? (int32_t)norm_a[row] : 0;
+      }
       const uint32_t st = t % MT_STAGES, ph = (t / MT_STAGES) & 1u;
-      const uint32_t buf = t & 1u, bph = (t >> 1) & 1u;
-      const uint32_t b0 = (t_begin + t) * MT_N;
-      mbar_wait(BAR_FULL_B(st), ph); /* |b|^2 of this tile landed (same barrier as the B tile) */
+      const uint32_t buf = t % MT_BUFS, bph = (t / MT_BUFS) & 1u;
+      const uint32_t b0 = tile * MT_N;
+      mbar_wait(BAR_FULL_B(st), ph); /* nbk of this tile landed (same barrier as the B tile) */
       mbar_wait(BAR_TMEM_FULL(buf), bph);
       tmem_fence_after();
       const uint32_t nbs = smem_u32(s_nb + st * MT_N);
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * MT_N;
-#pragma unroll 1
-      for (int c0 = 0; c0 < MT_N; c0 += 32)
-      {
-        int32_t acc[32];
-        tmem_ld32(taddr + c0, acc);
-        tmem_ld_wait();
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + buf * MT_N;
+      int32_t c1 = 0x7fffffff, c2 = 0x7fffffff;
+      /* 32 columns at a time; the load of the next 32 is in flight while the current 32 are reduced */
+      auto reduce32 = [&](const int32_t(&a)[32], int c0) {
 #pragma unroll
-        for (int g = 0; g < 2; g++)
+        for (int q = 0; q < 8; q++)
         {
-          int32_t e[16];
-#pragma unroll
-          for (int q = 0; q < 4; q++)
+          const int4 n4 = lds_v4(nbs + (uint32_t)(c0 + q * 4) * 4u);
+          /* key_scale = -512 arrives as a kernel argument so that this stays one IMAD on the FMA pipe; a literal
+           * power of two is strength-reduced to shift+add on the ALU pipe, which the min/max ops already load */
+          const int32_t e0 = a[q * 4 + 0] * key_scale + n4.x, e1 = a[q * 4 + 1] * key_scale + n4.y;
+          const int32_t e2 = a[q * 4 + 2] * key_scale + n4.z, e3 = a[q * 4 + 3] * key_scale + n4.w;
           {
-            const int4 n4 = lds_v4(nbs + (uint32_t)(c0 + g * 16 + q * 4) * 4u);
-            e[4 * q + 0] = n4.x - 2 * acc[g * 16 + 4 * q + 0];
-            e[4 * q + 1] = n4.y - 2 * acc[g * 16 + 4 * q + 1];
-            e[4 * q + 2] = n4.z - 2 * acc[g * 16 + 4 * q + 2];
-            e[4 * q + 3] = n4.w - 2 * acc[g * 16 + 4 * q + 3];
+            const int32_t lo = min(e0, e1), hi = max(e0, e1), tt = max(c1, lo);
+            c1 = min(c1, lo);
+            c2 = min(min(c2, tt), hi);
           }
-          int32_t m = e[0];
-#pragma unroll
-          for (int q = 1; q < 16; q++)
-            m = min(m, e[q]);
-          if (m <= thr)
           {
-#pragma unroll
-            for (int q = 0; q < 16; q++)
-            {
-              if (e[q] <= thr)
-              {
-                const unsigned long long key = ((unsigned long long)(uint32_t)(e[q] + my_na) << 32) | mt_pos(b0 + c0 + g * 16 + q);
-                if (key < k1)
-                {
-                  k2 = k1;
-                  k1 = key;
-                }
-                else if (key < k2)
-                  k2 = key;
-                if (k2 != ~0ull)
-                  thr = (int32_t)(uint32_t)(k2 >> 32) - my_na;
-              }
-            }
+            const int32_t lo = min(e2, e3), hi = max(e2, e3), tt = max(c1, lo);
+            c1 = min(c1, lo);
+            c2 = min(min(c2, tt), hi);
           }
+        }
+      };
+      {
+        int32_t acc0[32], acc1[32];
+        tmem_ld32(taddr, acc0);
+        tmem_ld_wait_for(acc0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < MT_N; c0 += 64)
+        {
+          tmem_ld32(taddr + c0 + 32, acc1);
+          reduce32(acc0, c0);
+          tmem_ld_wait_for(acc1);
+          if (c0 + 64 < MT_N)
+            tmem_ld32(taddr + c0 + 64, acc0);
+          reduce32(acc1, c0 + 32);
+          if (c0 + 64 < MT_N)
+            tmem_ld_wait_for(acc0);
         }
       }
       tmem_fence_before();
@@ -297,37 +353,59 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
         mbar_arrive(BAR_TMEM_EMPTY(buf));
         mbar_arrive(BAR_EMPTY_B(st));
       }
+      /* widen the tile's two survivors and merge */
+#pragma unroll
+      for (int q = 0; q < 2; q++)
+      {
+        const int32_t ck = q ? c2 : c1;
+        const uint32_t d2 = (uint32_t)((ck >> 8) + my_na);
+        const uint32_t pos = (b0 & ~255u) | ((uint32_t)ck & 255u);
+        const unsigned long long key = ((unsigned long long)d2 << 32) | pos;
+        if (key < k1)
+        {
+          k2 = k1;
+          k1 = key;
+        }
+        else if (key < k2)
+          k2 = key;
+      }
     }
-    if (row < na_pad)
+    if (cur_rb != 0xffffffffu)
     {
-      partial[((size_t)split * na_pad + row) * 2 + 0] = k1;
-      partial[((size_t)split * na_pad + row) * 2 + 1] = k2;
+      const uint32_t seg_slot = blockIdx.x - (cur_rb * n_tiles) / units_per_cta;
+      const size_t slot = (((size_t)cur_rb * max_segs + seg_slot) * 2 + wg) * MT_M + lrow;
+      partial[slot * 2 + 0] = k1;
+      partial[slot * 2 + 1] = k2;
     }
   }
 
   tmem_fence_before();
   __syncthreads();
-  if (warp == 5)
+  if (warp == MT_WARP_MMA)
   {
     tmem_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(MT_TMEM_COLS) : "memory");
   }
 }
 
-/* fold the splits, undo the pos permutation, sqrt (Get2NearestNeighbors.comp:98-102) */
-__global__ void match_merge_kernel(const unsigned long long *__restrict__ partial, uint32_t splits, uint32_t na, uint32_t na_pad,
-                                   vksift_Match_2NN *__restrict__ out)
+/* fold the segments of each row block, undo the pos permutation, sqrt (Get2NearestNeighbors.comp:98-102) */
+__global__ void match_merge_kernel(const unsigned long long *__restrict__ partial, uint32_t n_tiles, uint32_t units_per_cta, uint32_t max_segs,
+                                   uint32_t na, vksift_Match_2NN *__restrict__ out)
 {
   const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= na)
     return;
+  const uint32_t rb = row / MT_M, lrow = row - rb * MT_M;
+  const uint32_t first_cta = (rb * n_tiles) / units_per_cta, last_cta = ((rb + 1) * n_tiles - 1) / units_per_cta;
+  const uint32_t n_seg = last_cta - first_cta + 1;
   unsigned long long k1 = ~0ull, k2 = ~0ull;
-  for (uint32_t s = 0; s < splits; s++)
+  for (uint32_t s = 0; s < n_seg * 2; s++)
   {
+    const size_t slot = (((size_t)rb * max_segs) * 2 + s) * MT_M + lrow;
 #pragma unroll
     for (int q = 0; q < 2; q++)
     {
-      const unsigned long long key = partial[((size_t)s * na_pad + row) * 2 + q];
+      const unsigned long long key = partial[slot * 2 + q];
       if (key < k1)
       {
         k2 = k1;
@@ -396,11 +474,11 @@ static void match_tc_destroy(void *p)
   delete tc;
 }
 
-static bool mt_make_map(MatchTc *tc, CUtensorMap *map, const uint8_t *base, uint32_t rows)
+static bool mt_make_map(MatchTc *tc, CUtensorMap *map, const uint8_t *base, uint32_t rows, uint32_t box_rows)
 {
   const cuuint64_t gdim[2] = {128, rows};
   const cuuint64_t gstride[1] = {128};
-  const cuuint32_t box[2] = {128, MT_N};
+  const cuuint32_t box[2] = {128, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = tc->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -413,16 +491,15 @@ static cudaError_t match_tc_launch(void *p, const uint8_t *da, uint32_t na, cons
   MatchTc *tc = (MatchTc *)p;
   const uint32_t row_blocks = (na + MT_M - 1) / MT_M;
   const uint32_t n_tiles = (nb + MT_N - 1) / MT_N;
-  /* two CTAs are resident per SM: aim at one full wave of 2*SMs CTAs */
-  uint32_t splits = (2u * (uint32_t)tc->sm_count) / row_blocks;
-  if (splits < 1)
-    splits = 1;
-  if (splits > n_tiles)
-    splits = n_tiles;
-  const uint32_t tiles_per_split = (n_tiles + splits - 1) / splits;
-  splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
-  const uint32_t na_pad = row_blocks * MT_M;
-  const size_t need = (size_t)splits * na_pad * 2;
+  /* two CTAs are resident per SM: one full wave of equally loaded CTAs */
+  const uint32_t total_units = row_blocks * n_tiles;
+  uint32_t n_cta = 2u * (uint32_t)tc->sm_count;
+  if (n_cta > total_units)
+    n_cta = total_units;
+  const uint32_t units_per_cta = (total_units + n_cta - 1) / n_cta;
+  n_cta = (total_units + units_per_cta - 1) / units_per_cta;
+  const uint32_t max_segs = (n_tiles + units_per_cta - 1) / units_per_cta + 1;
+  const size_t need = (size_t)row_blocks * max_segs * 2 * MT_M * 2;
   if (need > tc->partial_elems)
   {
     /* grows only when a larger problem shows up; stream-ordered with respect to earlier matches */
@@ -436,14 +513,13 @@ static cudaError_t match_tc_launch(void *p, const uint8_t *da, uint32_t na, cons
     tc->partial_elems = need;
   }
   CUtensorMap map_a, map_b;
-  if (!mt_make_map(tc, &map_a, da, na) || !mt_make_map(tc, &map_b, db, nb))
+  if (!mt_make_map(tc, &map_a, da, na, MT_M) || !mt_make_map(tc, &map_b, db, nb, MT_N))
     return cudaErrorInvalidValue;
-  dim3 grid(row_blocks, splits, 1);
-  match_tc_kernel<<<grid, MT_THREADS, MT_SMEM_BYTES, st>>>(map_a, map_b, norm_a, norm_b, na, nb, tiles_per_split, n_tiles, tc->partial, na_pad);
+  match_tc_kernel<<<n_cta, MT_THREADS, MT_SMEM_BYTES, st>>>(map_a, map_b, norm_a, norm_b, na, n_tiles, units_per_cta, total_units, max_segs, tc->partial, -512);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
-  match_merge_kernel<<<(na + 255) / 256, 256, 0, st>>>(tc->partial, splits, na, na_pad, out);
+  match_merge_kernel<<<(na + 255) / 256, 256, 0, st>>>(tc->partial, n_tiles, units_per_cta, max_segs, na, out);
   *launch_count += 2;
   return cudaGetLastError();
 }

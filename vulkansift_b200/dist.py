@@ -1,0 +1,72 @@
+"""Multi-GPU host logic: image sharding and the descriptor exchange of cross-image matching.
+
+One process per GPU (torchrun).  Detection shards by image with no data-path collective
+(SURVEY 8e); all-pairs matching has exactly one exchange step: every rank contributes its
+descriptor block and receives everyone else's (all-gather, NCCL over NVLink on the GPU box).
+The functions below only move tensors, so the same code runs on CPU tensors with the gloo
+backend in the tests; the CUDA-specific glue is `gather_instance_descriptors`.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous, balanced [begin, end) of n_items for `rank` (first n_items % world ranks get one more)."""
+    base, extra = divmod(n_items, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def exchange_descriptor_blocks(local_desc, group=None):
+    """All-gather of per-rank descriptor blocks of different lengths.
+
+    local_desc: (n_local, 128) uint8 tensor on the backend's device.
+    Returns (counts, blocks): counts[j] = rows contributed by rank j; blocks is (world, max_n, 128),
+    rank j's descriptors are blocks[j, :counts[j]] and the padding rows are zero.
+    Two collectives: 4-byte counts, then blocks padded to the largest count (0.4 MB/rank at ~3k features).
+    """
+    world = dist.get_world_size(group)
+    dev = local_desc.device
+    assert local_desc.dtype == torch.uint8 and local_desc.dim() == 2 and local_desc.shape[1] == 128
+    n_local = torch.tensor([local_desc.shape[0]], dtype=torch.int64, device=dev)
+    counts_t = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts_t, n_local, group=group)
+    counts = [int(c) for c in counts_t.tolist()]
+    max_n = max(max(counts), 1)
+    send = torch.zeros((max_n, 128), dtype=torch.uint8, device=dev)
+    send[:local_desc.shape[0]] = local_desc
+    blocks = torch.empty((world, max_n, 128), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(blocks.view(world * max_n, 128), send, group=group)
+    return counts, blocks
+
+
+def all_pairs_schedule(rank, world):
+    """Peers whose block this rank matches its own features against: every j != rank, starting after
+    the own rank so that the ranks do not all read the same block at the same time."""
+    return [(rank + d) % world for d in range(1, world)]
+
+
+def gather_instance_descriptors(inst, buffer_id, group=None):
+    """CUDA glue: all-gather the descriptors of one feature buffer of a vulkansift_b200.api.Instance.
+
+    The local block is copied device-to-device into a torch tensor (the NCCL send buffer) by
+    vksiftx_copyDescriptorsToDevice; nothing touches the host except the 8-byte counts.
+    """
+    n = inst.features_number(buffer_id)
+    dev = torch.device("cuda", inst.device_index)
+    local = torch.empty((max(n, 1), 128), dtype=torch.uint8, device=dev)
+    inst.copy_descriptors_to_device(buffer_id, local.data_ptr(), max(n, 1))
+    return exchange_descriptor_blocks(local[:n], group)
+
+
+def match_against_peers(inst, buffer_a, scratch_buffer, counts, blocks, rank, world, download=True):
+    """Match the local features (buffer_a) against every peer block.  Returns {peer: matches or None}."""
+    out = {}
+    for j in all_pairs_schedule(rank, world):
+        if counts[j] < 2:
+            out[j] = None
+            continue
+        inst.upload_descriptors_device(blocks[j].data_ptr(), counts[j], scratch_buffer)
+        inst.match(buffer_a, scratch_buffer)
+        out[j] = inst.download_matches() if download else None
+    return out
