@@ -98,6 +98,7 @@ struct vksift_Instance_T
   uint32_t cur_w = 0, cur_h = 0;
   ScalePlan scales;
   Pyramid pyr;
+  ExtremaPlan *extrema_plan = nullptr;
   std::vector<BlurStep> steps_main; /* octaves on the fast kernel, main stream */
   std::vector<BlurStep> steps_side; /* small octaves, compact kernel, side stream */
   int fork_after_main = -1;         /* main step after which the side chain may start */
@@ -109,6 +110,7 @@ struct vksift_Instance_T
 
   std::vector<FeatureBuffer> buffers;
   Candidate *cand = nullptr;
+  unsigned long long *raw = nullptr; /* queued extrema (s,y,x) per octave */
   uint32_t cand_cap = 0;
   FeatHead *prim = nullptr;
   float *ori = nullptr;
@@ -357,6 +359,8 @@ void build_blur_plan(vksift_Instance inst)
   }
 }
 
+void fill_detect_params(vksift_Instance inst, const FeatureBuffer &fb, DetectParams *P);
+
 bool set_resolution(vksift_Instance inst, uint32_t w, uint32_t h)
 {
   inst->cur_w = w;
@@ -366,6 +370,13 @@ bool set_resolution(vksift_Instance inst, uint32_t w, uint32_t h)
   if (!alloc_pyramid(inst))
     return false;
   build_blur_plan(inst);
+  {
+    /* tensor maps of the extrema scan only depend on the pyramid geometry */
+    DetectParams P;
+    FeatureBuffer dummy;
+    fill_detect_params(inst, dummy, &P);
+    CU_TRY(extrema_plan_build(P, &inst->extrema_plan));
+  }
   return true;
 }
 
@@ -463,6 +474,7 @@ void destroy_instance(vksift_Instance inst)
     cudaFreeHost(inst->h_image);
   cudaFree(inst->d_image);
   cudaFree(inst->cand);
+  cudaFree(inst->raw);
   cudaFree(inst->prim);
   cudaFree(inst->ori);
   cudaFree(inst->n_ori);
@@ -470,6 +482,7 @@ void destroy_instance(vksift_Instance inst)
   cudaFree(inst->d_aos);
   cudaFree(inst->d_matches);
   match_workspace_destroy(inst->match_ws);
+  extrema_plan_destroy(inst->extrema_plan);
   for (int i = 0; i < EV_COUNT; i++)
     if (inst->ev[i])
       cudaEventDestroy(inst->ev[i]);
@@ -513,6 +526,7 @@ bool create_resources(vksift_Instance inst)
                                                                                                                    : c.max_nb_orientation_per_keypoint;
   inst->cand_cap = c.max_nb_sift_per_buffer;
   CU_TRY(cudaMalloc(&inst->cand, sizeof(Candidate) * (size_t)inst->cand_cap * (inst->max_octaves ? inst->max_octaves : 1)));
+  CU_TRY(cudaMalloc(&inst->raw, sizeof(unsigned long long) * (size_t)inst->cand_cap * (inst->max_octaves ? inst->max_octaves : 1)));
   CU_TRY(cudaMalloc(&inst->prim, sizeof(FeatHead) * (maxf + 1)));
   CU_TRY(cudaMalloc(&inst->ori, sizeof(float) * (maxf + 1) * inst->ori_stride));
   CU_TRY(cudaMalloc(&inst->n_ori, sizeof(uint32_t) * (maxf + 1)));
@@ -591,8 +605,8 @@ bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t bu
   }
   if (prof)
     CU_TRY(cudaEventRecord(inst->ev[EV_D1], st));
-  CU_TRY(launch_extrema(P, inst->cand, fb.cnt, st));
-  inst->launches++;
+  CU_TRY(launch_extrema(P, inst->extrema_plan, inst->raw, inst->cand, fb.cnt, st));
+  inst->launches += 2;
   CU_TRY(launch_order_primaries(P, inst->cand, fb.cnt, inst->prim, st));
   inst->launches++;
   if (prof)

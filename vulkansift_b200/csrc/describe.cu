@@ -26,23 +26,27 @@ __device__ __forceinline__ float gauss_at(const float *__restrict__ L, int w, in
 }
 
 /* ---- orientation --------------------------------------------------------- */
-#define ORI_WARPS 4
-#define ORI_MAX_BOX 33 /* 2*floor(4.5*sigma')+1 with sigma' < 3.6 */
+#define ORI_THREADS 128
+#define ORI_TERMS 2048 /* terms of the fixed-point scale staged per chunk */
 
-__global__ void __launch_bounds__(ORI_WARPS * 32) orientation_kernel(const __grid_constant__ DetectParams P, const DetectCounters *__restrict__ cnt,
-                                                                      const FeatHead *__restrict__ prim, float *__restrict__ ori,
-                                                                      uint32_t *__restrict__ n_ori)
+/* One CTA per keypoint.  The reference runs one 32-thread work group per keypoint in which EVERY thread
+ * recomputes the (2r+1)^2-term fixed-point scale (:75-81); here 128 threads evaluate the terms once into
+ * shared memory, one thread adds them in the reference's (i outer, j inner) fp32 order, and all four warps
+ * share the pixel loop. */
+__global__ void __launch_bounds__(ORI_THREADS) orientation_kernel(const __grid_constant__ DetectParams P, const DetectCounters *__restrict__ cnt,
+                                                                  const FeatHead *__restrict__ prim, float *__restrict__ ori,
+                                                                  uint32_t *__restrict__ n_ori)
 {
-  __shared__ uint32_t s_hist[ORI_WARPS][36];
-  __shared__ uint32_t s_tmp[ORI_WARPS][36];
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  uint32_t *hist = s_hist[wi], *tmp = s_tmp[wi];
+  __shared__ uint32_t hist[36];
+  __shared__ uint32_t tmp[36];
+  __shared__ float s_terms[ORI_TERMS];
+  __shared__ float s_m;
+  const int tid = threadIdx.x, lane = tid & 31;
 
   uint32_t total = 0;
   for (int o = 0; o < P.n_oct; o++)
     total += cnt->n_prim[o];
-  const uint32_t n_warps = gridDim.x * ORI_WARPS;
-  for (uint32_t item = blockIdx.x * ORI_WARPS + wi; item < total; item += n_warps)
+  for (uint32_t item = blockIdx.x; item < total; item += gridDim.x)
   {
     /* item -> (octave, index in section) */
     int o = 0;
@@ -62,43 +66,38 @@ __global__ void __launch_bounds__(ORI_WARPS * 32) orientation_kernel(const __gri
     const int r = (int)floorf(3 * lambda);
     const float es = -1.f / (2.f * lambda * lambda);
     const int box = 2 * r + 1;
+    const int n_terms = box * box;
 
-    /* ComputeOrientation.comp:75-81: M = sum_{i,j} exp(es*(i*i+j*j))*sqrt(2), accumulated in
-     * (i outer, j inner) order in fp32.  Lanes evaluate the terms of one row, then one
-     * sequential add chain per row keeps the reference summation order. */
+    /* ComputeOrientation.comp:75-81: M = sum_{i,j} exp(es*(i*i+j*j))*sqrt(2) in (i outer, j inner) fp32 order */
     float m = 0.f;
-    for (int i = -r; i <= r; i++)
+    for (int t0 = 0; t0 < n_terms; t0 += ORI_TERMS)
     {
-      /* first 32 terms of the row: fixed-length unrolled chain so the shuffles pipeline; lanes past the
-       * row end contribute +0.0f, which leaves the positive partial sum bit-identical */
+      const int nt = min(ORI_TERMS, n_terms - t0);
+      for (int t = tid; t < nt; t += ORI_THREADS)
       {
-        const int j = -r + lane;
-        const float term = (j <= r) ? vks_expf(es * (float)((i * i) + (j * j))) * VKS_SQRT2_F : 0.f;
-#pragma unroll
-        for (int k = 0; k < 32; k++)
-          m += __shfl_sync(0xffffffffu, term, k);
+        const int q = t0 + t;
+        const int i = q / box - r, j = q % box - r;
+        s_terms[t] = vks_expf(es * (float)((i * i) + (j * j))) * VKS_SQRT2_F;
       }
-      /* remaining terms (box side 33 at most for sigma' < 3.7, generic otherwise) */
-      for (int j0 = -r + 32; j0 <= r; j0 += 32)
+      if (t0 == 0 && tid < 36)
+        hist[tid] = 0;
+      __syncthreads();
+      if (tid == 0)
       {
-        const int j = j0 + lane;
-        const float term = (j <= r) ? vks_expf(es * (float)((i * i) + (j * j))) * VKS_SQRT2_F : 0.f;
-        const int cntj = min(32, r - j0 + 1);
-        for (int k = 0; k < cntj; k++)
-          m += __shfl_sync(0xffffffffu, term, k);
+#pragma unroll 8
+        for (int t = 0; t < nt; t++)
+          m += s_terms[t];
+        s_m = m;
       }
+      __syncthreads();
     }
+    m = s_m;
     const float fp = (float)(1u << (uint32_t)(30 - vks_ceil_log2(m)));
-
-    hist[lane] = 0;
-    if (lane < 4)
-      hist[32 + lane] = 0;
-    __syncwarp();
 
     const float rsx = vks_rint(kp.scale_x), rsy = vks_rint(kp.scale_y);
     const int cx = (int)rsx, cy = (int)rsy;
     const float r2 = (float)(r * r);
-    for (int pix = lane; pix < box * box; pix += 32)
+    for (int pix = tid; pix < n_terms; pix += ORI_THREADS)
     {
       const int dy = pix / box - r, dx = pix % box - r;
       const int gx = cx + dx, gy = cy + dy;
@@ -122,68 +121,71 @@ __global__ void __launch_bounds__(ORI_WARPS * 32) orientation_kernel(const __gri
         bin -= 36;
       atomicAdd(&hist[bin], (uint32_t)(mag * fp));
     }
-    __syncwarp();
+    __syncthreads();
 
-    /* :130-147 three double box smoothings in uint/float mixed arithmetic */
-    for (int it = 0; it < 3; it++)
+    if (tid < 32)
     {
-      for (int i = lane; i < 36; i += 32)
-        tmp[i] = (uint32_t)((float)(hist[(i + 35) % 36] + hist[i] + hist[(i + 1) % 36]) / 3.f);
-      __syncwarp();
-      for (int i = lane; i < 36; i += 32)
-        hist[i] = (uint32_t)((float)(tmp[(i + 35) % 36] + tmp[i] + tmp[(i + 1) % 36]) / 3.f);
-      __syncwarp();
-    }
-    uint32_t mx = hist[lane];
-    if (lane < 4)
-      mx = max(mx, hist[32 + lane]);
+      /* :130-147 three double box smoothings in uint/float mixed arithmetic */
+      for (int it = 0; it < 3; it++)
+      {
+        for (int i = lane; i < 36; i += 32)
+          tmp[i] = (uint32_t)((float)(hist[(i + 35) % 36] + hist[i] + hist[(i + 1) % 36]) / 3.f);
+        __syncwarp();
+        for (int i = lane; i < 36; i += 32)
+          hist[i] = (uint32_t)((float)(tmp[(i + 35) % 36] + tmp[i] + tmp[(i + 1) % 36]) / 3.f);
+        __syncwarp();
+      }
+      uint32_t mx = hist[lane];
+      if (lane < 4)
+        mx = max(mx, hist[32 + lane]);
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1)
-      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      for (int d = 16; d > 0; d >>= 1)
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
 
-    /* :156-183 peaks in increasing bin order */
-    uint32_t count = 0;
-    float *my_ori = ori + (size_t)slot * P.ori_stride;
-    for (int base = 0; base < 36; base += 32)
-    {
-      const int i = base + lane;
-      bool peak = false;
-      float theta = 0.f;
-      if (i < 36)
+      /* :156-183 peaks in increasing bin order */
+      uint32_t count = 0;
+      float *my_ori = ori + (size_t)slot * P.ori_stride;
+      for (int base = 0; base < 36; base += 32)
       {
-        const uint32_t hp = hist[(i + 35) % 36], hn = hist[(i + 1) % 36], hc = hist[i];
-        if (((float)hc >= (0.8f * (float)mx)) && (hc > hp) && (hc > hn))
+        const int i = base + lane;
+        bool peak = false;
+        float theta = 0.f;
+        if (i < 36)
         {
-          peak = true;
-          /* uint32 differences wrap before the conversion (SURVEY B-D12) */
-          const float num = (float)(uint32_t)(hp - hn);
-          const float den = (float)(uint32_t)(hp - (2u * hc) + hn);
-          const float fi = (float)i + 0.5f * (num / den);
-          theta = ((fi + 0.5f) * VKS_TWO_PI_F) / 36.f;
+          const uint32_t hp = hist[(i + 35) % 36], hn = hist[(i + 1) % 36], hc = hist[i];
+          if (((float)hc >= (0.8f * (float)mx)) && (hc > hp) && (hc > hn))
+          {
+            peak = true;
+            /* uint32 differences wrap before the conversion (SURVEY B-D12) */
+            const float num = (float)(uint32_t)(hp - hn);
+            const float den = (float)(uint32_t)(hp - (2u * hc) + hn);
+            const float fi = (float)i + 0.5f * (num / den);
+            theta = ((fi + 0.5f) * VKS_TWO_PI_F) / 36.f;
+          }
         }
+        const uint32_t mask = __ballot_sync(0xffffffffu, peak);
+        if (peak)
+        {
+          const uint32_t k = count + __popc(mask & ((1u << lane) - 1u));
+          if (k < P.ori_stride)
+            my_ori[k] = theta;
+        }
+        count += __popc(mask);
       }
-      const uint32_t mask = __ballot_sync(0xffffffffu, peak);
-      if (peak)
+      if (lane == 0)
       {
-        const uint32_t k = count + __popc(mask & ((1u << lane) - 1u));
-        if (k < P.ori_stride)
-          my_ori[k] = theta;
+        if (count == 0)
+          my_ori[0] = 0.f; /* no peak: orientation stays 0 and the keypoint is still described */
+        n_ori[slot] = count;
       }
-      count += __popc(mask);
     }
-    if (lane == 0)
-    {
-      if (count == 0)
-        my_ori[0] = 0.f; /* no peak: orientation stays 0 and the keypoint is still described */
-      n_ori[slot] = count;
-    }
-    __syncwarp();
+    __syncthreads();
   }
 }
 
 cudaError_t launch_orientation(const DetectParams &P, DetectCounters *cnt, const FeatHead *prim, float *ori, uint32_t *n_ori, cudaStream_t st)
 {
-  orientation_kernel<<<148 * 4, ORI_WARPS * 32, 0, st>>>(P, cnt, prim, ori, n_ori);
+  orientation_kernel<<<148 * 8, ORI_THREADS, 0, st>>>(P, cnt, prim, ori, n_ori);
   return cudaGetLastError();
 }
 

@@ -14,6 +14,8 @@
  */
 #include "vksift_internal.h"
 
+#include "tma_util.cuh"
+
 namespace vks
 {
 
@@ -104,135 +106,240 @@ __device__ bool refine_keypoint(const DetectParams &P, const OctaveView &ov, int
 }
 
 /* ExtractKeypoints.comp:44-116.  The reference runs one thread per (x,y,s) and reads 27 texels each.
- * Here one CTA stages a 64x32 tile (+1 halo) of ALL ns+2 DoG layers of an octave in shared memory once
- * (every DoG value is read from HBM a single time), then tests the ns inner scales from smem:
- * prefilter |v| > 0.8*thr, strict 26-neighbour extremum, and for the few survivors the refinement
- * (which reads global memory, it walks outside the tile).  All octaves run in one launch. */
-#define EX_TW 64
-#define EX_TH 32
-#define EX_SW 72 /* smem row: columns x0-4 .. x0+67 as 18 aligned float4 */
+ * Here a persistent CTA walks 240x8 tiles; for each tile ONE TMA request (cp.async.bulk.tensor.3d, box
+ * 256 x 10 x (ns+2), zero fill outside the image) brings the tile plus a 1-pixel halo of ALL DoG layers of the
+ * octave into shared memory, double buffered so that the next tile lands while the current one is tested:
+ * every DoG value is read from HBM once and no thread spends instructions on the staging.  The ns inner
+ * scales are tested from smem: prefilter |v| > 0.8*thr, strict 26-neighbour extremum, and for the few
+ * survivors the refinement (global reads, it walks outside the tile).  All octaves run in one launch. */
+#define EX_TW 240
+#define EX_TH 8
+#define EX_SW 256 /* smem row: columns x0-4 .. x0+251.  TMA moves a box row by row at a fixed cost per row, so rows
+                     are made as long as a box allows (256 elements = 1 KB): 72-float rows measured 6 B/clk/SM */
 #define EX_SH (EX_TH + 2)
 
-__global__ void __launch_bounds__(256) extrema_kernel(const __grid_constant__ DetectParams P, Candidate *__restrict__ cand,
-                                                      DetectCounters *__restrict__ cnt)
+struct ExtremaMaps
 {
-  extern __shared__ __align__(16) float ex_smem[];
-  /* linear CTA index -> (octave, tile) */
-  int t = blockIdx.x, o = 0, tx = 0;
-  for (; o < P.n_oct; o++)
+  CUtensorMap m[VKS_MAX_OCT]; /* 3-D fp32 maps over D[o]: (x, y, layer) */
+};
+
+__device__ __forceinline__ bool extrema_tile_coords(const DetectParams &P, int t, int *o_out, int *x0, int *y0)
+{
+  for (int o = 0; o < P.n_oct; o++)
   {
-    tx = (P.oct[o].w + EX_TW - 1) / EX_TW;
+    const int tx = (P.oct[o].w + EX_TW - 1) / EX_TW;
     const int n = tx * ((P.oct[o].h + EX_TH - 1) / EX_TH);
     if (t < n)
-      break;
+    {
+      *o_out = o;
+      *x0 = (t % tx) * EX_TW;
+      *y0 = (t / tx) * EX_TH;
+      return true;
+    }
     t -= n;
   }
-  if (o >= P.n_oct)
-    return;
-  const OctaveView &ov = P.oct[o];
-  const int nl = P.ns + 2;
-  const int x0 = (t % tx) * EX_TW, y0 = (t / tx) * EX_TH;
-  const int tid = threadIdx.x;
+  return false;
+}
 
-  /* stage: layer l, smem row r <-> image row y0-1+r, smem col c <-> image col x0-4+c.
-   * Loads are issued in batches of 6 per thread before any store so their latencies overlap. */
-  const int n_items = nl * EX_SH * (EX_SW / 4);
-  for (int it0 = tid; it0 < n_items; it0 += 6 * 256)
+__global__ void __launch_bounds__(256) extrema_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ ExtremaMaps maps, int n_tiles,
+                                                      unsigned long long *__restrict__ raw, DetectCounters *__restrict__ cnt)
+{
+  extern __shared__ __align__(128) float ex_smem[];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  const int ns = P.ns, nl = P.ns + 2;
+  const float prefilter = P.prefilter;
+  const uint32_t tile_bytes = (uint32_t)(nl * EX_SH * EX_SW) * 4u;
+  const int buf_floats = (nl * EX_SH * EX_SW + 31) & ~31; /* TMA destinations must be 128-byte aligned */
+  const int tid = threadIdx.x;
+  const uint32_t bar0 = tma_smem_u32(&s_bar[0]);
+
+  if (tid == 0)
   {
-    float4 v[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++)
+    tma_mbar_init(bar0, 1);
+    tma_mbar_init(bar0 + 8, 1);
+    tma_mbar_fence_init();
+    int o, x0, y0;
+    if (extrema_tile_coords(P, (int)blockIdx.x, &o, &x0, &y0))
     {
-      const int it = it0 + k * 256;
-      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (it < n_items)
-      {
-        const int l = it / (EX_SH * (EX_SW / 4));
-        const int rem = it - l * (EX_SH * (EX_SW / 4));
-        const int r = rem / (EX_SW / 4), c4 = rem - r * (EX_SW / 4);
-        const int gy = y0 - 1 + r, gx = x0 - 4 + c4 * 4;
-        if (gy >= 0 && gy < ov.h && gx >= 0 && gx + 3 < ov.pitch)
-          v[k] = __ldg((const float4 *)(ov.D + (size_t)l * ov.layer_stride + (size_t)gy * ov.pitch + gx));
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 6; k++)
-    {
-      const int it = it0 + k * 256;
-      if (it < n_items)
-        *(float4 *)(ex_smem + it * 4) = v[k]; /* item order == smem order: (l, r, c4) row-major */
+      tma_mbar_expect_tx(bar0, tile_bytes);
+      tma_load_3d(tma_smem_u32(ex_smem), &maps.m[o], x0 - 4, y0 - 1, 0, bar0);
     }
   }
   __syncthreads();
 
-  const int lx = tid & 63, ly = (tid >> 6) * 8;
-  const int x = x0 + lx;
-  if (x < 1 || x >= ov.w - 1)
-    return;
-  for (int s = 1; s <= P.ns; s++)
+  int it = 0;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it++)
   {
-    const float *Ls = ex_smem + (s * EX_SH) * EX_SW + (lx + 4);
-#pragma unroll 1
-    for (int r = 0; r < 8; r++)
+    const int cur = it & 1;
+    int o, x0, y0;
+    extrema_tile_coords(P, t, &o, &x0, &y0);
+    if (tid == 0)
     {
-      const int y = y0 + ly + r;
-      if (y < 1 || y >= ov.h - 1)
-        continue;
-      const float *pc = Ls + (ly + r + 1) * EX_SW;
-      const float c = pc[0];
-      if (!(fabsf(c) > P.prefilter))
-        continue;
-      bool gt = true, lt = true;
-#pragma unroll
-      for (int ds = -1; ds <= 1; ds++)
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-          for (int dx = -1; dx <= 1; dx++)
-          {
-            if (ds == 0 && dy == 0 && dx == 0)
-              continue;
-            const float n = pc[ds * (EX_SH * EX_SW) + dy * EX_SW + dx];
-            gt = gt && (c > n);
-            lt = lt && (c < n);
-          }
-      if (!(gt || lt))
-        continue;
-      FeatHead hd;
-      if (!refine_keypoint(P, ov, o, x, y, s, &hd))
-        continue;
-      const uint32_t slot = atomicAdd(&cnt->n_cand[o], 1u);
-      if (slot < P.cand_cap)
+      /* prefetch the next tile into the other buffer (its previous readers passed the barrier below) */
+      int on, xn, yn;
+      if (t + (int)gridDim.x < n_tiles && extrema_tile_coords(P, t + (int)gridDim.x, &on, &xn, &yn))
       {
-        Candidate cd;
-        cd.key = ((unsigned long long)s << 40) | ((unsigned long long)y << 20) | (unsigned long long)x;
-        cd.head = hd;
-        cd.pad_ = 0;
-        cand[(size_t)o * P.cand_cap + slot] = cd;
+        tma_fence_proxy_async();
+        tma_mbar_expect_tx(bar0 + 8 * (cur ^ 1), tile_bytes);
+        tma_load_3d(tma_smem_u32(ex_smem + (cur ^ 1) * buf_floats), &maps.m[on], xn - 4, yn - 1, 0, bar0 + 8 * (cur ^ 1));
       }
+    }
+    tma_mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
+
+    const OctaveView &ov = P.oct[o];
+    const float *tile = ex_smem + cur * buf_floats;
+    const int lx = tid, ly = 0; /* one column of 8 rows per thread */
+    const int x = x0 + lx;
+    const int ow = ov.w, oh = ov.h;
+    if (lx < EX_TW && x >= 1 && x < ow - 1)
+    {
+      /* rows of this thread that are inside [1, h-2] */
+      const int r_lo = max(0, 1 - (y0 + ly)), r_hi = min(8, (oh - 1) - (y0 + ly));
+      for (int s = 1; s <= ns; s++)
+      {
+        const float *col = tile + (s * EX_SH + ly + 1) * EX_SW + (lx + 4);
+        /* prefilter all 8 centre values first (independent loads), then visit only the survivors */
+        float cv[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+          cv[r] = col[r * EX_SW];
+        uint32_t mask = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+          mask |= (fabsf(cv[r]) > prefilter && r >= r_lo && r < r_hi) ? (1u << r) : 0u;
+        while (mask)
+        {
+          const int r = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float *pc = col + r * EX_SW;
+          const float c = pc[0];
+          /* strict 26-neighbour test (:59-116), staged so that the many non-extrema leave after 4 compares */
+          bool gt = true, lt = true;
+#define EX_CMP(off)                                                                                                                                  \
+  {                                                                                                                                                  \
+    const float n = pc[off];                                                                                                                         \
+    gt = gt && (c > n);                                                                                                                              \
+    lt = lt && (c < n);                                                                                                                              \
+  }
+          EX_CMP(-1) EX_CMP(1) EX_CMP(-EX_SW) EX_CMP(EX_SW)
+          if (!(gt || lt))
+            continue;
+          EX_CMP(-EX_SW - 1) EX_CMP(-EX_SW + 1) EX_CMP(EX_SW - 1) EX_CMP(EX_SW + 1)
+          if (!(gt || lt))
+            continue;
+#pragma unroll
+          for (int ds = -1; ds <= 1; ds += 2)
+          {
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+              for (int dx = -1; dx <= 1; dx++)
+                EX_CMP(ds * (EX_SH * EX_SW) + dy * EX_SW + dx)
+            if (!(gt || lt))
+              break;
+          }
+#undef EX_CMP
+          if (!(gt || lt))
+            continue;
+          /* a strict extremum: queue it.  The sub-pixel refinement (a long serial chain of dependent global
+           * loads and divisions for one lane) runs in its own kernel with one thread per queued candidate,
+           * instead of stalling this tile's whole CTA at the next barrier. */
+          const int y = y0 + ly + r;
+          const uint32_t slot = atomicAdd(&cnt->n_raw[o], 1u);
+          if (slot < P.cand_cap)
+            raw[(size_t)o * P.cand_cap + slot] = ((unsigned long long)s << 40) | ((unsigned long long)y << 20) | (unsigned long long)x;
+        }
+      }
+    }
+    __syncthreads(); /* everyone is done with buffer `cur` before it is refilled two iterations later */
+  }
+}
+
+/* ExtractKeypoints.comp:118-224 for the queued extrema: one thread per candidate, all octaves in one launch */
+__global__ void __launch_bounds__(128) refine_kernel(const __grid_constant__ DetectParams P, const unsigned long long *__restrict__ raw,
+                                                     Candidate *__restrict__ cand, DetectCounters *__restrict__ cnt)
+{
+  const int o = blockIdx.y;
+  const uint32_t n = min(cnt->n_raw[o], P.cand_cap);
+  const OctaveView &ov = P.oct[o];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  {
+    const unsigned long long key = raw[(size_t)o * P.cand_cap + i];
+    const int s = (int)(key >> 40), y = (int)((key >> 20) & 0xfffffu), x = (int)(key & 0xfffffu);
+    FeatHead hd;
+    if (!refine_keypoint(P, ov, o, x, y, s, &hd))
+      continue;
+    const uint32_t slot = atomicAdd(&cnt->n_cand[o], 1u);
+    if (slot < P.cand_cap)
+    {
+      Candidate cd;
+      cd.key = key;
+      cd.head = hd;
+      cd.pad_ = 0;
+      cand[(size_t)o * P.cand_cap + slot] = cd;
     }
   }
 }
 
-cudaError_t launch_extrema(const DetectParams &P, Candidate *cand, DetectCounters *cnt, cudaStream_t st)
+struct ExtremaPlan
 {
-  int tiles = 0;
+  ExtremaMaps maps;
+  int n_tiles;
+  bool valid;
+};
+
+/* (re)build the tensor maps for the current pyramid; called when the resolution changes */
+cudaError_t extrema_plan_build(const DetectParams &P, ExtremaPlan **plan_io)
+{
+  if (*plan_io == nullptr)
+    *plan_io = new ExtremaPlan();
+  ExtremaPlan *pl = *plan_io;
+  pl->valid = false;
+  pl->n_tiles = 0;
   for (int o = 0; o < P.n_oct; o++)
-    tiles += ((P.oct[o].w + EX_TW - 1) / EX_TW) * ((P.oct[o].h + EX_TH - 1) / EX_TH);
-  if (tiles == 0)
+  {
+    const OctaveView &ov = P.oct[o];
+    const uint64_t dims[3] = {(uint64_t)ov.w, (uint64_t)ov.h, (uint64_t)(P.ns + 2)};
+    const uint64_t strides[2] = {(uint64_t)ov.pitch * 4, (uint64_t)ov.layer_stride * 4};
+    const uint32_t box[3] = {EX_SW, EX_SH, (uint32_t)(P.ns + 2)};
+    if (!tma_make_map_f32(&pl->maps.m[o], ov.D, 3, dims, strides, box))
+      return cudaErrorInvalidValue;
+    pl->n_tiles += ((ov.w + EX_TW - 1) / EX_TW) * ((ov.h + EX_TH - 1) / EX_TH);
+  }
+  pl->valid = true;
+  return cudaSuccess;
+}
+
+void extrema_plan_destroy(ExtremaPlan *pl) { delete pl; }
+
+cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, unsigned long long *raw, Candidate *cand, DetectCounters *cnt,
+                           cudaStream_t st)
+{
+  if (!pl || !pl->valid || pl->n_tiles == 0)
     return cudaSuccess;
-  const size_t smem = sizeof(float) * (size_t)(P.ns + 2) * EX_SH * EX_SW;
+  const size_t smem = 2 * sizeof(float) * (size_t)((((P.ns + 2) * EX_SH * EX_SW) + 31) & ~31);
+  if (smem > 220 * 1024)
+    return cudaErrorInvalidConfiguration; /* nb_scales_per_octave too large for the double-buffered tile */
   static bool attr_done[64] = {false};
-  int dev = 0;
+  int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_done[dev])
   {
-    cudaError_t e = cudaFuncSetAttribute(extrema_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (VKS_MAX_LAYERS - 1) * EX_SH * EX_SW));
+    cudaError_t e = cudaFuncSetAttribute(extrema_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess)
       return e;
     attr_done[dev] = true;
   }
-  extrema_kernel<<<tiles, 256, smem, st>>>(P, cand, cnt);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int per_sm = (int)((220 * 1024) / smem) < 1 ? 1 : (int)((220 * 1024) / smem);
+  int grid = sms * (per_sm > 2 ? 2 : per_sm);
+  if (grid > pl->n_tiles)
+    grid = pl->n_tiles;
+  extrema_kernel<<<grid, 256, smem, st>>>(P, pl->maps, pl->n_tiles, raw, cnt);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return e;
+  refine_kernel<<<dim3(32, P.n_oct, 1), 128, 0, st>>>(P, raw, cand, cnt);
   return cudaGetLastError();
 }
 

@@ -81,6 +81,7 @@ struct DetectParams
 /* per-buffer device counters, zeroed at the start of every detection */
 struct DetectCounters
 {
+  uint32_t n_raw[VKS_MAX_OCT];    /* strict extrema queued for refinement */
   uint32_t n_cand[VKS_MAX_OCT];   /* accepted keypoints found (may exceed capacity) */
   uint32_t n_prim[VKS_MAX_OCT];   /* primaries kept = min(n_cand, cap) */
   uint32_t n_found[VKS_MAX_OCT];  /* primaries + extra orientations found */
@@ -149,7 +150,11 @@ void blur_step_tiles(BlurStep *step);
 /* true when the pass runs on the unrolled packed-fp32 kernel, false for the compact kernel */
 bool blur_pass_is_fast(const BlurPass &bp);
 cudaError_t launch_blur_step(const BlurStep &step, cudaStream_t st);
-cudaError_t launch_extrema(const DetectParams &P, Candidate *cand, DetectCounters *cnt, cudaStream_t st);
+struct ExtremaPlan; /* TMA tensor maps over the DoG layers of the current pyramid */
+cudaError_t extrema_plan_build(const DetectParams &P, ExtremaPlan **plan_io);
+void extrema_plan_destroy(ExtremaPlan *pl);
+cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, unsigned long long *raw, Candidate *cand, DetectCounters *cnt,
+                           cudaStream_t st);
 cudaError_t launch_order_primaries(const DetectParams &P, const Candidate *cand, DetectCounters *cnt, FeatHead *prim, cudaStream_t st);
 cudaError_t launch_orientation(const DetectParams &P, DetectCounters *cnt, const FeatHead *prim, float *ori, uint32_t *n_ori, cudaStream_t st);
 cudaError_t launch_assemble(const DetectParams &P, DetectCounters *cnt, const uint32_t *n_ori, uint32_t *feat_src, uint32_t *host_counts,
