@@ -213,6 +213,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL print a banner on stdout; stdout must carry the JSON line only
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     api.lib.vksift_setLogLevel(api.VKSIFT_LOG_WARNING)
 

@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(256) extrema_kernel(const __grid_constant__ De
     if (extrema_tile_coords(P, (int)blockIdx.x, &o, &x0, &y0))
     {
       tma_mbar_expect_tx(bar0, tile_bytes);
-      tma_load_3d(tma_smem_u32(ex_smem), &maps.m[o], x0 - 4, y0 - 1, 0, bar0);
+      for (int l = 0; l < nl; l++) /* one request per layer: the TMA unit pipelines independent requests */
+        tma_load_3d(tma_smem_u32(ex_smem + l * EX_SH * EX_SW), &maps.m[o], x0 - 4, y0 - 1, l, bar0);
     }
   }
   __syncthreads();
@@ -181,7 +182,8 @@ __global__ void __launch_bounds__(256) extrema_kernel(const __grid_constant__ De
       {
         tma_fence_proxy_async();
         tma_mbar_expect_tx(bar0 + 8 * (cur ^ 1), tile_bytes);
-        tma_load_3d(tma_smem_u32(ex_smem + (cur ^ 1) * buf_floats), &maps.m[on], xn - 4, yn - 1, 0, bar0 + 8 * (cur ^ 1));
+        for (int l = 0; l < nl; l++)
+          tma_load_3d(tma_smem_u32(ex_smem + (cur ^ 1) * buf_floats + l * EX_SH * EX_SW), &maps.m[on], xn - 4, yn - 1, l, bar0 + 8 * (cur ^ 1));
       }
     }
     tma_mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
@@ -301,7 +303,7 @@ cudaError_t extrema_plan_build(const DetectParams &P, ExtremaPlan **plan_io)
     const OctaveView &ov = P.oct[o];
     const uint64_t dims[3] = {(uint64_t)ov.w, (uint64_t)ov.h, (uint64_t)(P.ns + 2)};
     const uint64_t strides[2] = {(uint64_t)ov.pitch * 4, (uint64_t)ov.layer_stride * 4};
-    const uint32_t box[3] = {EX_SW, EX_SH, (uint32_t)(P.ns + 2)};
+    const uint32_t box[3] = {EX_SW, EX_SH, 1}; /* one layer per request */
     if (!tma_make_map_f32(&pl->maps.m[o], ov.D, 3, dims, strides, box))
       return cudaErrorInvalidValue;
     pl->n_tiles += ((ov.w + EX_TW - 1) / EX_TW) * ((ov.h + EX_TH - 1) / EX_TH);
