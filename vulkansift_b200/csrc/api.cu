@@ -99,11 +99,23 @@ struct vksift_Instance_T
   ScalePlan scales;
   Pyramid pyr;
   ExtremaPlan *extrema_plan = nullptr;
-  std::vector<BlurStep> steps_main; /* octaves on the fast kernel, main stream */
-  std::vector<BlurStep> steps_side; /* small octaves, compact kernel, side stream */
-  int fork_after_main = -1;         /* main step after which the side chain may start */
-  cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<std::vector<BlurPass>> fast_oct; /* octaves [0,k) on the fast kernel: one stream per octave, one launch per layer */
+  std::vector<BlurStep> steps_side;            /* small octaves [k,n) that cannot be fused: compact kernel, wavefront steps on the side stream */
+  struct FusedOct
+  {
+    BlurStep seed_step;              /* octave 0 only: the u8 -> layer 0 pass (compact kernel) */
+    bool has_seed_step = false;
+    std::vector<FusedLaunch> chain;  /* launches up to the one that seeds the next octave: the critical path */
+    std::vector<FusedLaunch> rest;   /* remaining layers, second side stream */
+  };
+  std::vector<FusedOct> fused_oct;             /* small octaves [k,n): fused kernel, one or two launches per octave */
+  cudaStream_t side_stream = nullptr, side2_stream = nullptr;
+  cudaEvent_t ev_chain[VKS_MAX_OCT] = {nullptr}; /* chain launches of octave o enqueued on the side stream */
+  cudaEvent_t ev_join2 = nullptr;
+  cudaStream_t oct_stream[VKS_MAX_OCT] = {nullptr}; /* [0] unused: octave 0 runs on the main stream */
+  cudaEvent_t ev_seed[VKS_MAX_OCT] = {nullptr};     /* layer 0 of octave o written (by the pass producing layer ns of octave o-1) */
+  cudaEvent_t ev_oct_done[VKS_MAX_OCT] = {nullptr};
+  cudaEvent_t ev_join = nullptr;
 
   uint8_t *h_image = nullptr; /* pinned */
   uint8_t *d_image = nullptr;
@@ -125,6 +137,15 @@ struct vksift_Instance_T
   int matcher_impl = 0;
 
   bool profiling = false;
+  /* VKSIFT_TRACE=1: an event pair around every launch of the scale-space stage, printed as a timeline (debug aid) */
+  struct TraceMark
+  {
+    char name[32];
+    cudaEvent_t e0, e1;
+  };
+  bool trace = false;
+  std::vector<TraceMark> trace_marks;
+  size_t trace_used = 0;
   cudaEvent_t ev[EV_COUNT] = {nullptr};
   bool ev_detect_valid = false, ev_match_valid = false;
   uint64_t launches = 0;
@@ -264,7 +285,7 @@ bool alloc_pyramid(vksift_Instance inst)
 
 /* Launch plan of the scale space for the current resolution: the CUDA twin of
  * recScaleSpaceConstructionCmds + recDifferenceOfGaussianCmds (sift_detector.c:893-1079). */
-void build_blur_plan(vksift_Instance inst)
+bool build_blur_plan(vksift_Instance inst)
 {
   const Pyramid &p = inst->pyr;
   const int ns = inst->cfg.nb_scales_per_octave;
@@ -303,19 +324,19 @@ void build_blur_plan(vksift_Instance inst)
     memcpy(bp.taps, inst->scales.taps[s], sizeof(bp.taps));
     return bp;
   };
-  /* Wavefront schedule.  Layer s of octave o needs layer s-1 of the same octave, and layer 0 of octave
-   * o >= 1 is written by the pass that produces layer ns of octave o-1, so pass (o,s) is ready at step
-   * ns*o + s.  All passes of one step share a launch: the late scales of a large octave then run next to
-   * the early scales of the following, smaller octave instead of 36 strictly serial launches
-   * (reference order: sift_detector.c:1369-1378 records octave after octave).
-   * Large octaves [0,k) run on the unrolled kernel in the main stream; the small octaves [k,n) are latency
-   * bound, run on the compact kernel and form their own wavefront in a side stream that forks off after
-   * the pass producing their seed and joins before the extrema scan. */
-  inst->steps_main.clear();
+  /* Schedule.  Layer s of octave o needs layer s-1 of the same octave, and layer 0 of octave o >= 1 is
+   * written by the pass that produces layer ns of octave o-1 (reference order: sift_detector.c:1369-1378
+   * records octave after octave, 72 serial dispatches).
+   * Octaves [0,k) that are at least one tile wide run on the fast kernel, one launch per layer, each octave
+   * in its own stream that starts once its seed exists: the late scales of an octave run next to the early
+   * scales of the following ones and the block scheduler fills the tail of one launch with the head of another.
+   * The remaining small octaves [k,n) are latency bound; they run on the compact kernel as one wavefront
+   * (all passes that are ready share a launch) in a side stream and join before the extrema scan. */
+  inst->fast_oct.clear();
   inst->steps_side.clear();
-  inst->fork_after_main = -1;
   if (p.n_oct == 0)
-    return;
+    return true;
+  bool ok = true;
   int k = 0;
   for (; k < (int)p.n_oct; k++)
   {
@@ -328,6 +349,21 @@ void build_blur_plan(vksift_Instance inst)
     if (!fast)
       break;
   }
+  for (int o = 0; o < k; o++)
+  {
+    std::vector<BlurPass> passes;
+    for (int s = (o == 0 ? 0 : 1); s < ns + 3; s++)
+    {
+      BlurPass bp = make_pass((uint32_t)o, s);
+      if (!blur_pass_prepare_fast(&bp))
+      {
+        LOGE(TAG, "cuTensorMapEncodeTiled failed for a scale-space layer (%dx%d)", bp.w, bp.h);
+        ok = false;
+      }
+      passes.push_back(bp);
+    }
+    inst->fast_oct.push_back(passes);
+  }
   auto wavefront = [&](int o_begin, int o_end, std::vector<BlurStep> &out) {
     if (o_end <= o_begin)
       return;
@@ -336,7 +372,6 @@ void build_blur_plan(vksift_Instance inst)
     {
       BlurStep step;
       memset(&step, 0, sizeof(step));
-      /* smaller octaves first: they are on the critical path, the big pass fills the remaining SMs */
       for (int o = o_end - 1; o >= o_begin; o--)
       {
         const int s = t - ns * (o - o_begin);
@@ -350,13 +385,43 @@ void build_blur_plan(vksift_Instance inst)
       out.push_back(step);
     }
   };
-  wavefront(0, k, inst->steps_main);
-  wavefront(k, (int)p.n_oct, inst->steps_side);
-  if (k > 0 && k < (int)p.n_oct)
+  /* small octaves: fused launches (chain = up to the layer seeding the next octave, rest = the others) */
+  inst->fused_oct.clear();
+  bool fused_ok = true;
+  for (int o = k; o < (int)p.n_oct && fused_ok; o++)
   {
-    /* the seed of octave k is written by pass (k-1, ns) = main step ns*(k-1)+ns (octave 0 starts at s=0) */
-    inst->fork_after_main = ns * (k - 1) + ns;
+    vksift_Instance_T::FusedOct fo;
+    std::vector<BlurPass> passes;
+    for (int s = 1; s < ns + 3; s++)
+      passes.push_back(make_pass((uint32_t)o, s));
+    if (o == 0)
+    {
+      memset(&fo.seed_step, 0, sizeof(fo.seed_step));
+      fo.seed_step.pass[0] = make_pass(0, 0);
+      fo.seed_step.n_pass = 1;
+      blur_step_tiles(&fo.seed_step);
+      fo.has_seed_step = true;
+    }
+    std::vector<FusedLaunch> all;
+    fused_ok = fused_plan_octave(passes.data(), (int)passes.size(), &all);
+    bool seen_next = (o + 1 >= (int)p.n_oct); /* the last octave seeds nothing: everything is off the critical path */
+    for (const FusedLaunch &F : all)
+    {
+      if (seen_next && o + 1 < (int)p.n_oct)
+        fo.rest.push_back(F);
+      else
+        fo.chain.push_back(F);
+      if (F.next_k >= 0)
+        seen_next = true;
+    }
+    inst->fused_oct.push_back(fo);
   }
+  if (!fused_ok)
+  {
+    inst->fused_oct.clear();
+    wavefront(k, (int)p.n_oct, inst->steps_side);
+  }
+  return ok;
 }
 
 void fill_detect_params(vksift_Instance inst, const FeatureBuffer &fb, DetectParams *P);
@@ -369,7 +434,8 @@ bool set_resolution(vksift_Instance inst, uint32_t w, uint32_t h)
   p.n_oct = plan_octaves(w, h, inst->cfg.use_input_upsampling, inst->max_octaves, p.w, p.h);
   if (!alloc_pyramid(inst))
     return false;
-  build_blur_plan(inst);
+  if (!build_blur_plan(inst))
+    return false;
   {
     /* tensor maps of the extrema scan only depend on the pyramid geometry */
     DetectParams P;
@@ -490,10 +556,24 @@ void destroy_instance(vksift_Instance inst)
     cudaEventDestroy(inst->ev_detect_done);
   if (inst->ev_match_done)
     cudaEventDestroy(inst->ev_match_done);
-  if (inst->ev_fork)
-    cudaEventDestroy(inst->ev_fork);
   if (inst->ev_join)
     cudaEventDestroy(inst->ev_join);
+  if (inst->ev_join2)
+    cudaEventDestroy(inst->ev_join2);
+  for (int o = 0; o < VKS_MAX_OCT; o++)
+    if (inst->ev_chain[o])
+      cudaEventDestroy(inst->ev_chain[o]);
+  if (inst->side2_stream)
+    cudaStreamDestroy(inst->side2_stream);
+  for (int o = 0; o < VKS_MAX_OCT; o++)
+  {
+    if (inst->ev_seed[o])
+      cudaEventDestroy(inst->ev_seed[o]);
+    if (inst->ev_oct_done[o])
+      cudaEventDestroy(inst->ev_oct_done[o]);
+    if (inst->oct_stream[o])
+      cudaStreamDestroy(inst->oct_stream[o]);
+  }
   if (inst->side_stream)
     cudaStreamDestroy(inst->side_stream);
   if (inst->stream)
@@ -505,9 +585,24 @@ bool create_resources(vksift_Instance inst)
 {
   const vksift_Config &c = inst->cfg;
   CU_TRY(cudaStreamCreateWithFlags(&inst->stream, cudaStreamNonBlocking));
-  CU_TRY(cudaStreamCreateWithFlags(&inst->side_stream, cudaStreamNonBlocking));
-  CU_TRY(cudaEventCreateWithFlags(&inst->ev_fork, cudaEventDisableTiming));
+  /* The dependency chain of the pyramid runs octave 0 -> 1 -> ... (each needs layer ns of the previous one), so the
+   * smaller an octave, the later it starts and the more the pipeline waits for it: smaller octaves get the higher
+   * stream priority and their CTAs are placed before the queued CTAs of the big, throughput-bound launches. */
+  int prio_lo = 0, prio_hi = 0;
+  CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi)); /* numerically lower = more urgent */
+  auto prio = [&](int level) { return prio_lo - level < prio_hi ? prio_hi : prio_lo - level; };
+  CU_TRY(cudaStreamCreateWithPriority(&inst->side_stream, cudaStreamNonBlocking, prio(3)));
+  CU_TRY(cudaStreamCreateWithPriority(&inst->side2_stream, cudaStreamNonBlocking, prio(1)));
+  CU_TRY(cudaEventCreateWithFlags(&inst->ev_join2, cudaEventDisableTiming));
+  for (int o = 0; o < VKS_MAX_OCT; o++)
+    CU_TRY(cudaEventCreateWithFlags(&inst->ev_chain[o], cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&inst->ev_join, cudaEventDisableTiming));
+  for (int o = 1; o < VKS_MAX_OCT; o++)
+  {
+    CU_TRY(cudaStreamCreateWithPriority(&inst->oct_stream[o], cudaStreamNonBlocking, prio(o >= 2 ? 2 : 1)));
+    CU_TRY(cudaEventCreateWithFlags(&inst->ev_seed[o], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&inst->ev_oct_done[o], cudaEventDisableTiming));
+  }
   CU_TRY(cudaEventCreateWithFlags(&inst->ev_detect_done, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&inst->ev_match_done, cudaEventDisableTiming));
   for (int i = 0; i < EV_COUNT; i++)
@@ -556,6 +651,51 @@ bool create_resources(vksift_Instance inst)
   return true;
 }
 
+struct TraceScope
+{
+  vksift_Instance inst;
+  cudaStream_t st;
+  size_t idx = (size_t)-1;
+  TraceScope(vksift_Instance i, cudaStream_t s, const char *fmt, int a, int b) : inst(i), st(s)
+  {
+    if (!inst->trace)
+      return;
+    if (inst->trace_used == inst->trace_marks.size())
+    {
+      vksift_Instance_T::TraceMark m;
+      cudaEventCreate(&m.e0);
+      cudaEventCreate(&m.e1);
+      inst->trace_marks.push_back(m);
+    }
+    idx = inst->trace_used++;
+    snprintf(inst->trace_marks[idx].name, sizeof(inst->trace_marks[idx].name), fmt, a, b);
+    cudaEventRecord(inst->trace_marks[idx].e0, st);
+  }
+  ~TraceScope()
+  {
+    if (idx != (size_t)-1)
+      cudaEventRecord(inst->trace_marks[idx].e1, st);
+  }
+};
+
+void trace_dump(vksift_Instance inst)
+{
+  if (!inst->trace || inst->trace_used == 0 || !inst->profiling)
+    return;
+  cudaEventSynchronize(inst->ev[EV_D4]);
+  fprintf(stderr, "[trace] %-24s %9s %9s %9s\n", "launch", "start_us", "end_us", "dur_us");
+  for (size_t i = 0; i < inst->trace_used; i++)
+  {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, inst->ev[EV_D0], inst->trace_marks[i].e0);
+    cudaEventElapsedTime(&b, inst->ev[EV_D0], inst->trace_marks[i].e1);
+    fprintf(stderr, "[trace] %-24s %9.1f %9.1f %9.1f\n", inst->trace_marks[i].name, a * 1e3f, b * 1e3f, (b - a) * 1e3f);
+  }
+  float d1 = 0.f;
+  cudaEventElapsedTime(&d1, inst->ev[EV_D0], inst->ev[EV_D1]);
+  fprintf(stderr, "[trace] scale space done at %.1f us\n", d1 * 1e3f);
+}
+
 /* enqueue the whole detection pipeline (sift_detector.c:1369-1393) */
 bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t buf)
 {
@@ -565,44 +705,99 @@ bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t bu
   fill_detect_params(inst, fb, &P);
   const bool prof = inst->profiling;
 
+  inst->trace_used = 0;
   if (prof)
     CU_TRY(cudaEventRecord(inst->ev[EV_D0], st));
   CU_TRY(cudaMemsetAsync(fb.cnt, 0, sizeof(DetectCounters), st));
-  auto run_step = [&](BlurStep &step, cudaStream_t s) -> bool {
-    for (int i = 0; i < step.n_pass; i++)
-      if (step.pass[i].src_kind != BLUR_SRC_LAYER)
-        step.pass[i].src = d_image;
-    CU_TRY(launch_blur_step(step, s));
-    inst->launches++;
-    return true;
-  };
-  if (inst->steps_main.empty())
+  const int ns = inst->cfg.nb_scales_per_octave;
+  const int n_fast = (int)inst->fast_oct.size();
+  for (int o = 0; o < n_fast; o++)
   {
-    for (BlurStep &step : inst->steps_side)
-      if (!run_step(step, st))
-        return false;
-  }
-  else
-  {
-    bool forked = false;
-    for (size_t i = 0; i < inst->steps_main.size(); i++)
+    cudaStream_t so = (o == 0) ? st : inst->oct_stream[o];
+    if (o > 0)
+      CU_TRY(cudaStreamWaitEvent(so, inst->ev_seed[o], 0));
+    for (BlurPass &bp : inst->fast_oct[o])
     {
-      if (!run_step(inst->steps_main[i], st))
-        return false;
-      if ((int)i == inst->fork_after_main && !inst->steps_side.empty())
+      if (bp.src_kind != BLUR_SRC_LAYER)
+        bp.src = d_image;
       {
-        CU_TRY(cudaEventRecord(inst->ev_fork, st));
-        CU_TRY(cudaStreamWaitEvent(inst->side_stream, inst->ev_fork, 0));
-        for (BlurStep &step : inst->steps_side)
-          if (!run_step(step, inst->side_stream))
-            return false;
-        CU_TRY(cudaEventRecord(inst->ev_join, inst->side_stream));
-        forked = true;
+        TraceScope ts(inst, so, "fast o%d r%d", o, bp.radius);
+        CU_TRY(launch_blur_pass_fast(bp, so));
+      }
+      inst->launches++;
+      if (bp.dst_next && o + 1 < VKS_MAX_OCT)
+        CU_TRY(cudaEventRecord(inst->ev_seed[o + 1], so)); /* written by the pass producing layer ns */
+    }
+    if (o > 0)
+      CU_TRY(cudaEventRecord(inst->ev_oct_done[o], so));
+  }
+  (void)ns;
+  if (!inst->fused_oct.empty())
+  {
+    cudaStream_t ss = (n_fast == 0) ? st : inst->side_stream;
+    if (n_fast > 0)
+      CU_TRY(cudaStreamWaitEvent(ss, inst->ev_seed[n_fast], 0));
+    bool used2 = false;
+    for (size_t j = 0; j < inst->fused_oct.size(); j++)
+    {
+      auto &fo = inst->fused_oct[j];
+      if (fo.has_seed_step)
+      {
+        fo.seed_step.pass[0].src = d_image;
+        CU_TRY(launch_blur_step(fo.seed_step, ss));
+        inst->launches++;
+      }
+      for (const FusedLaunch &F : fo.chain)
+      {
+        TraceScope ts(inst, ss, "fused chain o%d n%d", n_fast + (int)j, F.n_layers);
+        CU_TRY(launch_fused(F, ss));
+        inst->launches++;
+      }
+      if (!fo.rest.empty())
+      {
+        CU_TRY(cudaEventRecord(inst->ev_chain[j], ss));
+        CU_TRY(cudaStreamWaitEvent(inst->side2_stream, inst->ev_chain[j], 0));
+        for (const FusedLaunch &F : fo.rest)
+        {
+          TraceScope ts(inst, inst->side2_stream, "fused rest o%d n%d", n_fast + (int)j, F.n_layers);
+          CU_TRY(launch_fused(F, inst->side2_stream));
+          inst->launches++;
+        }
+        used2 = true;
       }
     }
-    if (forked)
+    if (n_fast > 0)
+    {
+      CU_TRY(cudaEventRecord(inst->ev_join, ss));
       CU_TRY(cudaStreamWaitEvent(st, inst->ev_join, 0));
+    }
+    if (used2)
+    {
+      CU_TRY(cudaEventRecord(inst->ev_join2, inst->side2_stream));
+      CU_TRY(cudaStreamWaitEvent(st, inst->ev_join2, 0));
+    }
   }
+  if (!inst->steps_side.empty())
+  {
+    cudaStream_t ss = (n_fast == 0) ? st : inst->side_stream;
+    if (n_fast > 0)
+      CU_TRY(cudaStreamWaitEvent(ss, inst->ev_seed[n_fast], 0));
+    for (BlurStep &step : inst->steps_side)
+    {
+      for (int i = 0; i < step.n_pass; i++)
+        if (step.pass[i].src_kind != BLUR_SRC_LAYER)
+          step.pass[i].src = d_image;
+      CU_TRY(launch_blur_step(step, ss));
+      inst->launches++;
+    }
+    if (n_fast > 0)
+    {
+      CU_TRY(cudaEventRecord(inst->ev_join, ss));
+      CU_TRY(cudaStreamWaitEvent(st, inst->ev_join, 0));
+    }
+  }
+  for (int o = 1; o < n_fast; o++)
+    CU_TRY(cudaStreamWaitEvent(st, inst->ev_oct_done[o], 0));
   if (prof)
     CU_TRY(cudaEventRecord(inst->ev[EV_D1], st));
   CU_TRY(launch_extrema(P, inst->extrema_plan, inst->raw, inst->cand, fb.cnt, st));
@@ -1235,7 +1430,12 @@ extern "C"
 
   void *vksiftx_getMatchesDevice(vksift_Instance inst) { return inst->d_matches; }
 
-  void vksiftx_setProfiling(vksift_Instance inst, const bool enabled) { inst->profiling = enabled; }
+  void vksiftx_setProfiling(vksift_Instance inst, const bool enabled)
+  {
+    inst->profiling = enabled;
+    const char *t = getenv("VKSIFT_TRACE");
+    inst->trace = enabled && t && t[0] == '1';
+  }
 
   void vksiftx_getStageTimesMs(vksift_Instance inst, float *t)
   {
@@ -1246,6 +1446,7 @@ extern "C"
     if (inst->ev_detect_valid)
     {
       cudaEventSynchronize(inst->ev[EV_D4]);
+      trace_dump(inst);
       cudaEventElapsedTime(&t[0], inst->ev[EV_D0], inst->ev[EV_D1]);
       cudaEventElapsedTime(&t[1], inst->ev[EV_D1], inst->ev[EV_D2]);
       cudaEventElapsedTime(&t[2], inst->ev[EV_D2], inst->ev[EV_D3]);

@@ -18,6 +18,10 @@
  * results do not depend on the tiling.
  */
 #include "vksift_internal.h"
+#include "tma_util.cuh"
+
+#include <cstring>
+#include <vector>
 
 namespace vks
 {
@@ -187,20 +191,24 @@ __global__ void __launch_bounds__(256) blur_step_small_kernel(const __grid_const
 }
 
 /* ==========================================================================
- * Fast tile kernel: even radius <= 12 (every scale of the default configuration).
+ * Fast tile kernel: radius <= 12 (every scale of the default configuration).
  *
- * FP32 issue rate, not HBM, is what limits this stage on B200 (about 2R+1 fp32
- * operations per pixel and pass), so the arithmetic runs on the packed
- * FADD2/FFMA2/FMUL2 pipe (add/fma/mul.rn.f32x2, two IEEE results per
- * instruction, bit-identical to the scalar sequence of vksift_arith.h):
- *   - 64x128 output tile, 256 threads, two CTAs per SM
- *   - input tile + halo in smem with ROW PAIRS interleaved ([y/2][x][y&1]) so the
- *     horizontal pass packs (row y, row y+1) and reads aligned pairs for every tap
- *   - horizontal pass: one thread = 2 rows x 8 columns, sliding window of 8+2R
- *     packed values in registers; result row-major in smem
- *   - vertical pass: one thread = 2 columns x 8 rows, packs (x, x+1); writes G with
- *     64-bit stores, DoG = G - centre from the input tile, and the decimated seed
- *   - taps live in uniform registers as (k,k) pairs straight from the kernel parameters
+ * Measured on B200 (tools/ubench/fp32_rate.cu): FFMA2/FADD2 retire the same number of fp32 results per
+ * cycle as FFMA/FADD (128 per SM), they only halve the issue slots.  A blur pass needs 2(2R+1) fp32
+ * operations per pixel, which puts the fp32 pipe of the late scales at the same cost as the HBM writes of
+ * the layer; everything that is not a blur operation therefore has to fit into the issue slots the packed
+ * instructions leave free:
+ *   - 64x128 output tile, 256 threads, two CTAs per SM (one loads/stores while the other computes)
+ *   - the source tile + halo arrives by TMA (cp.async.bulk.tensor.2d, zero thread instructions) in four
+ *     row bands with one mbarrier each, so the horizontal pass starts when the first band has landed;
+ *     tiles on the image border get their MIRRORED_REPEAT halo patched in shared memory
+ *   - horizontal pass: one thread = 1 row x 16 columns, window in registers straight from LDS.128.
+ *     Output pairs (x, x+1): even taps use the aligned register pairs of the window (FADD2), odd taps add
+ *     the two scalars into a fresh pair (2 FADD), both feed one FFMA2 -- no register shuffles
+ *   - vertical pass: one thread = 2 columns x 16 rows, pairs (x, x+1), sliding window of LDS.64;
+ *     writes G, DoG = G - centre (from the source tile) and the decimated seed with 64-bit stores
+ *   - one launch = one layer, one kernel per (radius, kind): every parameter and tap is a constant operand
+ * Per-pixel operation sequence is the one of vksift_arith.h; add/fma.rn.f32x2 are two IEEE operations.
  * ========================================================================== */
 typedef unsigned long long pk2; /* two packed fp32 */
 __device__ __forceinline__ pk2 pk_fma(pk2 a, pk2 b, pk2 c)
@@ -229,277 +237,687 @@ __device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b)
 }
 __device__ __forceinline__ float pk_lo(pk2 a) { return __uint_as_float((uint32_t)a); }
 __device__ __forceinline__ float pk_hi(pk2 a) { return __uint_as_float((uint32_t)(a >> 32)); }
-__device__ __forceinline__ pk2 pk_make(float lo, float hi) { return (pk2)__float_as_uint(lo) | ((pk2)__float_as_uint(hi) << 32); }
+__device__ __forceinline__ pk2 pk_make(float lo, float hi)
+{
+  pk2 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
 
 #define FT_W 64
 #define FT_H 128
 #define FT_THREADS 256
-#define FT_MS (FT_W + 2) /* row stride of the horizontal-pass result, floats */
+#define FT_MS (FT_W + 4) /* row stride of the horizontal-pass result, floats (stride/4 odd) */
+#define FT_VR 16         /* output rows per thread in the vertical pass = FT_H / warps */
+#define FT_NB 4          /* TMA row bands per tile */
 
-__host__ __device__ constexpr int ft_rx(int R) { return (R + 3) & ~3; }                              /* x halo rounded to float4 */
-__host__ __device__ constexpr int ft_ss(int R) { return (((FT_W + 2 * ft_rx(R)) * 2 / 4) | 1) * 4; } /* floats per row pair, stride/4 odd */
-__host__ __device__ constexpr int ft_smem_floats(int R, int TH) { return ((TH + 2 * R) / 2) * ft_ss(R) + (TH + 2 * R) * FT_MS; }
-
-template <int R, int TH>
-__device__ __forceinline__ void blur_tile_fast(const BlurPass &p, const pk2 *__restrict__ taps2, float *smem, int x0, int y0)
+enum
 {
+  FT_KIND_SEED = 0, /* u8 source (octave 0, layer 0): no DoG */
+  FT_KIND_LAYER = 1, /* float source, G + DoG */
+  FT_KIND_NEXT = 2   /* float source, G + DoG + decimated seed of the next octave (layer ns) */
+};
+
+__host__ __device__ constexpr int ft_rx(int R) { return (R + 3) & ~3; } /* x halo rounded to float4 */
+/* source tile row stride (= TMA box width), floats: covers 64 + 2 halos, stride/4 odd -> LDS.128 down a column is conflict free */
+__host__ __device__ constexpr int ft_s(int R) { return (((FT_W + 2 * ft_rx(R)) / 4) | 1) * 4; }
+__host__ __device__ constexpr int ft_in_h(int R) { return FT_H + 2 * R; }
+#define FT_BOX_H 8 /* rows per TMA request: 8 rows of a stride that is a multiple of 4 floats keep every destination 128-byte aligned */
+__host__ __device__ constexpr int ft_n_box(int R) { return (ft_in_h(R) + FT_BOX_H - 1) / FT_BOX_H; }
+__host__ __device__ constexpr int ft_in_ha(int R) { return ft_n_box(R) * FT_BOX_H; } /* rows allocated for the source tile */
+/* source tile, horizontal-pass result, TMA barriers, UNORM table of the seed pass */
+__host__ __device__ constexpr int ft_smem_bytes(int R) { return 4 * (ft_in_ha(R) * ft_s(R) + ft_in_h(R) * FT_MS) + 8 * FT_NB + 1024; }
+__host__ __device__ constexpr int ft_even(int r) { return r < 2 ? 2 : ((r + 1) & ~1); }
+
+struct BlurPassFast
+{
+  BlurPass p;
+  float2 taps2[14]; /* (k,k) pairs, zero padded to the even radius */
+};
+
+#define FT_TAP(i) (*reinterpret_cast<const pk2 *>(&P.taps2[i]))
+
+template <int R, int KIND>
+__global__ void __launch_bounds__(FT_THREADS, 2) blur_pass_fast_kernel(const __grid_constant__ BlurPassFast P)
+{
+  extern __shared__ __align__(128) float ft_smem[];
   constexpr int RX = ft_rx(R);
-  constexpr int SS = ft_ss(R);
-  constexpr int IN_W = FT_W + 2 * RX; /* columns loaded */
-  constexpr int IN_H = TH + 2 * R;    /* rows loaded */
-  constexpr int NRP = IN_H / 2;
-  float *s_in = smem;
-  float *s_mid = smem + NRP * SS;
+  constexpr int S = ft_s(R);
+  constexpr int IN_H = ft_in_h(R);
+  constexpr int IN_HA = ft_in_ha(R);
+  constexpr int NBOX = ft_n_box(R); /* TMA requests per tile; request j signals barrier j*FT_NB/NBOX */
+  const BlurPass &p = P.p;
+  float *s_in = ft_smem;
+  float *s_mid = ft_smem + IN_HA * S;
+  const uint32_t bar0 = tma_smem_u32(ft_smem + IN_HA * S + IN_H * FT_MS);
   const int tid = threadIdx.x;
+  const int wi = tid >> 5, lane = tid & 31;
+  const int t = (int)blockIdx.x;
+  const int x0 = (t % p.tiles_x) * FT_W;
+  const int y0 = (t / p.tiles_x) * FT_H;
 
-  /* rows / columns of this tile that can influence a pixel inside the image */
-  const int rows_valid = min(TH, p.h - y0);                 /* output rows */
-  const int nrp = min(NRP, (rows_valid + 2 * R + 1) / 2);   /* row pairs the vertical pass will read */
-  const int ncg = min(FT_W / 8, (p.w - x0 + 7) / 8);        /* 8-column groups with at least one pixel */
+  /* rows of this tile that can influence a pixel inside the image */
+  const int rows_valid = min(FT_H, p.h - y0); /* output rows */
+  const int rows_in = rows_valid + 2 * R;     /* source rows the vertical pass will read */
+  int bands_seen = FT_NB;                      /* TMA bands this thread has already waited for */
 
-  /* ---- stage 1: source -> smem, row pairs interleaved ---- */
-  const bool interior = (p.src_kind == BLUR_SRC_LAYER) && (x0 - RX >= 0) && (x0 + FT_W + RX <= p.w) && (y0 - R >= 0) && (y0 + TH + R <= p.h);
-  if (interior)
+  /* ---- stage 1: source tile -> smem ---- */
+  if (KIND != FT_KIND_SEED)
   {
-    const float *__restrict__ src = (const float *)p.src + (size_t)(y0 - R) * p.src_pitch + (x0 - RX);
-    constexpr int C4 = IN_W / 4;
-    constexpr int ITEMS = NRP * C4;
-#pragma unroll 4
-    for (int it = tid; it < ITEMS; it += FT_THREADS)
+    if (tid == 0)
     {
-      const int rp = it / C4, c4 = it - rp * C4;
-      const float4 a = __ldg((const float4 *)(src + (size_t)(2 * rp) * p.src_pitch) + c4);
-      const float4 b = __ldg((const float4 *)(src + (size_t)(2 * rp + 1) * p.src_pitch) + c4);
-      float4 *d = (float4 *)(s_in + rp * SS + c4 * 8);
-      d[0] = make_float4(a.x, b.x, a.y, b.y);
-      d[1] = make_float4(a.z, b.z, a.w, b.w);
+#pragma unroll
+      for (int b = 0; b < FT_NB; b++)
+        tma_mbar_init(bar0 + 8 * b, 1);
+      tma_mbar_fence_init();
+#pragma unroll
+      for (int b = 0; b < FT_NB; b++)
+      {
+        constexpr int per = FT_BOX_H * S * 4;
+        const int n_req = ((b + 1) * NBOX + FT_NB - 1) / FT_NB - (b * NBOX + FT_NB - 1) / FT_NB; /* requests j with j*FT_NB/NBOX == b */
+        tma_mbar_expect_tx(bar0 + 8 * b, (uint32_t)(n_req * per));
+      }
+#pragma unroll
+      for (int j = 0; j < NBOX; j++)
+        tma_load_2d_f32(tma_smem_u32(s_in + j * FT_BOX_H * S), &p.tmap, x0 - RX, y0 - R + j * FT_BOX_H, bar0 + 8 * (j * FT_NB / NBOX));
+    }
+    __syncthreads(); /* barriers initialised before anybody polls them */
+    bands_seen = 0;
+    const bool border = (x0 - RX < 0) || (x0 - RX + S > p.w) || (y0 - R < 0) || (y0 - R + IN_H > p.h);
+    if (border)
+    {
+      /* MIRRORED_REPEAT: cells outside the image (zero filled by TMA) take the value of their mirror
+       * cell, which lies inside the image and inside this tile for every cell an in-image output reads.
+       * Columns first (rows that exist in the image), then whole rows. */
+#pragma unroll
+      for (int b = 0; b < FT_NB; b++)
+        tma_mbar_wait(bar0 + 8 * b, 0);
+      bands_seen = FT_NB;
+      const int cx = x0 - RX, cy = y0 - R;          /* image coordinates of cell (0,0) */
+      const int nl = max(0, -cx);                   /* columns left of the image */
+      const int cr = min(S, max(0, p.w - cx));      /* first column right of the image */
+      const int ncol = nl + (S - cr);
+      const int r_lo = max(0, -cy), r_hi = min(rows_in, p.h - cy); /* rows inside the image */
+      if (ncol > 0)
+      {
+        for (int i = tid; i < (r_hi - r_lo) * ncol; i += FT_THREADS)
+        {
+          const int rr = i / ncol, k = i - rr * ncol;
+          const int r = r_lo + rr;
+          const int c = k < nl ? k : cr + (k - nl);
+          const int mx = min(max(mirror_once(cx + c, p.w) - cx, 0), S - 1);
+          s_in[r * S + c] = s_in[r * S + mx];
+        }
+        __syncthreads();
+      }
+      const int nrow = r_lo + (rows_in - r_hi);
+      if (nrow > 0)
+      {
+        for (int i = tid; i < nrow * (S / 4); i += FT_THREADS)
+        {
+          const int k = i / (S / 4), c4 = i - k * (S / 4);
+          const int r = k < r_lo ? k : r_hi + (k - r_lo);
+          const int my = min(max(mirror_once(cy + r, p.h) - cy, 0), IN_H - 1);
+          ((float4 *)(s_in + r * S))[c4] = ((const float4 *)(s_in + my * S))[c4];
+        }
+      }
+      __syncthreads();
     }
   }
   else
   {
-    const bool once = (x0 - RX >= -p.w) && (x0 + FT_W + RX <= 2 * p.w) && (y0 - R >= -p.h) && (y0 + TH + R <= 2 * p.h);
-    const int n_el = IN_W * 2 * nrp;
-    if (p.src_kind == BLUR_SRC_LAYER)
+    /* octave 0 seed.  s_mid serves as scratch: the u8 source window as float (one UNORM division per
+     * source pixel, MIRRORED_REPEAT / clamp-to-edge resolved here), then the LINEAR 2x blit (or the 1:1
+     * copy) out of shared memory.  Destination cell (m, c) <-> image pixel (x0-RX+c, y0-R+m). */
+    const bool up = (p.src_kind == BLUR_SRC_U8_UP2);
+    const bool once = (x0 - RX >= -p.w) && (x0 - RX + S <= 2 * p.w) && (y0 - R >= -p.h) && (y0 + FT_H + R <= 2 * p.h);
+    const uint8_t *__restrict__ img = (const uint8_t *)p.src;
+    const int n_el = S * rows_in;
+    /* mirrored destination coordinates stay inside [lo, hi] of the image */
+    const int dx_lo = max(0, min(x0 - RX, p.w - 1)), dx_hi = min(p.w - 1, max(0, x0 - RX + S - 1));
+    const int dy_lo = max(0, min(y0 - R, p.h - 1)), dy_hi = min(p.h - 1, max(0, y0 + rows_in - R - 1));
+    const bool full = !once; /* tiny images reflect more than once: stage the whole source */
+    const int sx_lo = full ? 0 : (up ? max(0, (dx_lo >> 1) - 1) : dx_lo);
+    const int sx_hi = full ? p.src_w - 1 : (up ? min(p.src_w - 1, (dx_hi >> 1) + 1) : dx_hi);
+    const int sy_lo = full ? 0 : (up ? max(0, (dy_lo >> 1) - 1) : dy_lo);
+    const int sy_hi = full ? p.src_h - 1 : (up ? min(p.src_h - 1, (dy_hi >> 1) + 1) : dy_hi);
+    const int sw = sx_hi - sx_lo + 1, sh = sy_hi - sy_lo + 1;
+    if (sw * sh <= IN_H * FT_MS && once)
     {
-      const float *__restrict__ src = (const float *)p.src;
-#pragma unroll 8
-      for (int i = tid; i < n_el; i += FT_THREADS)
+      /* UNORM conversion through a 256-entry table (one IEEE division per CTA thread instead of one per pixel) */
+      float *lut = ft_smem + IN_HA * S + IN_H * FT_MS + 2 * FT_NB;
+      lut[tid] = vks_unorm8((uint8_t)tid);
+      __syncthreads();
+      for (int i = tid; i < sw * sh; i += FT_THREADS)
       {
-        const int m = i / IN_W, c = i - m * IN_W;
-        int gx = x0 - RX + c, gy = y0 - R + m;
-        gx = once ? mirror_once(gx, p.w) : vks_mirror(gx, p.w);
-        gy = once ? mirror_once(gy, p.h) : vks_mirror(gy, p.h);
-        s_in[(m >> 1) * SS + c * 2 + (m & 1)] = __ldg(src + (size_t)gy * p.src_pitch + gx);
+        const int yy = i / sw, xx = i - yy * sw;
+        s_mid[i] = lut[__ldg(img + (size_t)(sy_lo + yy) * p.src_w + sx_lo + xx)];
       }
-    }
-    else
-    {
-      /* octave 0 seed: stage the u8 source window as float (one UNORM division per source pixel),
-       * then apply the LINEAR 2x blit (or the 1:1 copy) from shared memory */
-      const bool up = (p.src_kind == BLUR_SRC_U8_UP2);
-      const uint8_t *__restrict__ img = (const uint8_t *)p.src;
-      /* mirrored destination coordinates stay inside [lo, hi] of the image */
-      const int dx_lo = max(0, min(x0 - RX, p.w - 1)), dx_hi = min(p.w - 1, max(0, x0 + FT_W + RX - 1));
-      const int dy_lo = max(0, min(y0 - R, p.h - 1)), dy_hi = min(p.h - 1, max(0, y0 + 2 * nrp - R - 1));
-      const bool full = !once; /* tiny images reflect more than once: stage the whole source */
-      const int sx_lo = full ? 0 : (up ? max(0, (dx_lo >> 1) - 1) : dx_lo);
-      const int sx_hi = full ? p.src_w - 1 : (up ? min(p.src_w - 1, (dx_hi >> 1) + 1) : dx_hi);
-      const int sy_lo = full ? 0 : (up ? max(0, (dy_lo >> 1) - 1) : dy_lo);
-      const int sy_hi = full ? p.src_h - 1 : (up ? min(p.src_h - 1, (dy_hi >> 1) + 1) : dy_hi);
-      const int sw = sx_hi - sx_lo + 1, sh = sy_hi - sy_lo + 1;
-      const bool staged = (sw * sh <= IN_H * FT_MS);
-      if (staged)
+      __syncthreads();
+      const int cx = x0 - RX, cy = y0 - R; /* both even */
+      const bool inner = up && cx >= 2 && cx + S <= p.w - 2 && cy >= 2 && cy + rows_in <= p.h - 2 && (rows_in & 1) == 0;
+      if (inner)
       {
-#pragma unroll 4
-        for (int i = tid; i < sw * sh; i += FT_THREADS)
+        /* Tile away from the image border: no mirroring, no clamping, sx_lo = cx/2 - 1, sy_lo = cy/2 - 1.
+         * With H[t][c] = the horizontal lerp of staged row t at destination column c, destination row
+         * 2j = lerp(H[j], H[j+1], .75) and row 2j+1 = lerp(H[j+1], H[j+2], .25).  One thread owns a column
+         * pair (even c: staged columns (c/2, c/2+1), f=.75; odd c+1: (c/2+1, c/2+2), f=.25) and walks down. */
+        constexpr int NCP = S / 2;
+        constexpr int NG = FT_THREADS / NCP;
+        const int cp = tid % NCP, grp = tid / NCP;
+        const int n_rp = rows_in >> 1;
+        const int per = (n_rp + NG - 1) / NG;
+        const int j0 = grp * per, j1 = min(n_rp, j0 + per);
+        if (grp < NG && j0 < j1)
         {
-          const int yy = i / sw, xx = i - yy * sw;
-          s_mid[i] = vks_unorm8(__ldg(img + (size_t)(sy_lo + yy) * p.src_w + sx_lo + xx));
-        }
-        __syncthreads();
-        for (int i = tid; i < n_el; i += FT_THREADS)
-        {
-          const int m = i / IN_W, c = i - m * IN_W;
-          int gx = x0 - RX + c, gy = y0 - R + m;
-          gx = once ? mirror_once(gx, p.w) : vks_mirror(gx, p.w);
-          gy = once ? mirror_once(gy, p.h) : vks_mirror(gy, p.h);
-          float v;
-          if (up)
+          const float *sp = s_mid + j0 * sw + cp;
+          float a0 = sp[0], a1 = sp[1], a2 = sp[2];
+          float he0 = vks_lerp(a0, a1, 0.75f), ho0 = vks_lerp(a1, a2, 0.25f);
+          sp += sw;
+          a0 = sp[0], a1 = sp[1], a2 = sp[2];
+          float he1 = vks_lerp(a0, a1, 0.75f), ho1 = vks_lerp(a1, a2, 0.25f);
+          float *dp = s_in + (2 * j0) * S + 2 * cp;
+          for (int j = j0; j < j1; j++)
           {
-            const int kx = gx >> 1, ky = gy >> 1;
+            sp += sw;
+            a0 = sp[0], a1 = sp[1], a2 = sp[2];
+            const float he2 = vks_lerp(a0, a1, 0.75f), ho2 = vks_lerp(a1, a2, 0.25f);
+            *(float2 *)dp = make_float2(vks_lerp(he0, he1, 0.75f), vks_lerp(ho0, ho1, 0.75f));
+            *(float2 *)(dp + S) = make_float2(vks_lerp(he1, he2, 0.25f), vks_lerp(ho1, ho2, 0.25f));
+            dp += 2 * S;
+            he0 = he1, ho0 = ho1, he1 = he2, ho1 = ho2;
+          }
+        }
+      }
+      else
+      if (up)
+      {
+        /* one thread = one destination column pair (even x, odd x): their source columns are
+         * (k-1, k) with f=.75 and (k, k+1) with f=.25; walk down the rows */
+        for (int i = tid; i < (S / 2) * rows_in; i += FT_THREADS)
+        {
+          const int m = i / (S / 2), cp = i - m * (S / 2);
+          const int gy = mirror_once(y0 - R + m, p.h);
+          const int ky = gy >> 1;
+          const int ay = min(max(max(((gy & 1) ? ky : ky - 1), 0) - sy_lo, 0), sh - 1);
+          const int by = min(max(min(((gy & 1) ? ky + 1 : ky), p.src_h - 1) - sy_lo, 0), sh - 1);
+          const float fy = (gy & 1) ? 0.25f : 0.75f;
+          float v[2];
+#pragma unroll
+          for (int e = 0; e < 2; e++)
+          {
+            const int gx = mirror_once(x0 - RX + 2 * cp + e, p.w);
+            const int kx = gx >> 1;
             /* the clamps to the staged window only ever bind for cells that no in-image output reads */
             const int ax = min(max(max(((gx & 1) ? kx : kx - 1), 0) - sx_lo, 0), sw - 1);
             const int bx = min(max(min(((gx & 1) ? kx + 1 : kx), p.src_w - 1) - sx_lo, 0), sw - 1);
-            const int ay = min(max(max(((gy & 1) ? ky : ky - 1), 0) - sy_lo, 0), sh - 1);
-            const int by = min(max(min(((gy & 1) ? ky + 1 : ky), p.src_h - 1) - sy_lo, 0), sh - 1);
-            const float fx = (gx & 1) ? 0.25f : 0.75f, fy = (gy & 1) ? 0.25f : 0.75f;
+            const float fx = (gx & 1) ? 0.25f : 0.75f;
             const float top = vks_lerp(s_mid[ay * sw + ax], s_mid[ay * sw + bx], fx);
             const float bot = vks_lerp(s_mid[by * sw + ax], s_mid[by * sw + bx], fx);
-            v = vks_lerp(top, bot, fy);
+            v[e] = vks_lerp(top, bot, fy);
           }
-          else
-            v = s_mid[min(max(gy - sy_lo, 0), sh - 1) * sw + min(max(gx - sx_lo, 0), sw - 1)];
-          s_in[(m >> 1) * SS + c * 2 + (m & 1)] = v;
+          *(float2 *)(s_in + m * S + 2 * cp) = make_float2(v[0], v[1]);
         }
       }
       else
       {
         for (int i = tid; i < n_el; i += FT_THREADS)
         {
-          const int m = i / IN_W, c = i - m * IN_W;
-          s_in[(m >> 1) * SS + c * 2 + (m & 1)] = fetch_src(p, x0 - RX + c, y0 - R + m);
+          const int m = i / S, c = i - m * S;
+          const int gx = mirror_once(x0 - RX + c, p.w), gy = mirror_once(y0 - R + m, p.h);
+          s_in[i] = s_mid[min(max(gy - sy_lo, 0), sh - 1) * sw + min(max(gx - sx_lo, 0), sw - 1)];
         }
+      }
+    }
+    else
+    {
+      for (int i = tid; i < n_el; i += FT_THREADS)
+      {
+        const int m = i / S, c = i - m * S;
+        s_in[i] = fetch_src(p, x0 - RX + c, y0 - R + m);
+      }
+    }
+    __syncthreads();
+  }
+
+  /* ---- stage 2: horizontal pass, warp unit = (8 rows, 64 columns) = the rows of one TMA request;
+   *      lane = (row, 16-column group): 8 consecutive lanes read 8 rows, conflict free because stride/4 is odd ---- */
+  {
+    constexpr int WN = 16 + 2 * RX; /* window floats, float4 aligned */
+    const int n_units = (rows_in + 7) >> 3;
+    for (int wu = wi; wu < n_units; wu += FT_THREADS / 32)
+    {
+      const int g = lane >> 3;
+      const int r = min(wu * 8 + (lane & 7), IN_H - 1);
+      if (KIND != FT_KIND_SEED)
+      {
+        const int need = min(wu, NBOX - 1) * FT_NB / NBOX;
+        while (bands_seen <= need)
+        {
+          tma_mbar_wait(bar0 + 8 * bands_seen, 0);
+          bands_seen++;
+        }
+      }
+      const ulonglong2 *wsrc = (const ulonglong2 *)(s_in + r * S + g * 16);
+      pk2 wp[WN / 2]; /* wp[j] = (in[2j], in[2j+1]) relative to column g*16 - RX */
+#pragma unroll
+      for (int j = 0; j < WN / 4; j++)
+      {
+        const ulonglong2 v = wsrc[j];
+        wp[2 * j] = v.x;
+        wp[2 * j + 1] = v.y;
+      }
+      ulonglong2 *dst = (ulonglong2 *)(s_mid + r * FT_MS + g * 16);
+#pragma unroll
+      for (int hb = 0; hb < 2; hb++)
+      {
+        /* four output pairs at a time: four independent accumulator chains */
+        pk2 acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          acc[j] = pk_mul(wp[RX / 2 + 4 * hb + j], FT_TAP(0));
+#pragma unroll
+        for (int i = 1; i <= R; i++)
+        {
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+          {
+            const int c = RX / 2 + 4 * hb + j; /* pair index of the centre */
+            pk2 sum;
+            if ((i & 1) == 0)
+              sum = pk_add(wp[c + i / 2], wp[c - i / 2]);
+            else
+            {
+              /* (in[x+i], in[x+1+i]) straddles two register pairs: add the scalars into a fresh pair */
+              const float s0 = __fadd_rn(pk_hi(wp[c + (i - 1) / 2]), pk_hi(wp[c - (i + 1) / 2]));
+              const float s1 = __fadd_rn(pk_lo(wp[c + (i + 1) / 2]), pk_lo(wp[c - (i - 1) / 2]));
+              sum = pk_make(s0, s1);
+            }
+            acc[j] = pk_fma(sum, FT_TAP(i), acc[j]);
+          }
+        }
+        dst[2 * hb] = make_ulonglong2(acc[0], acc[1]);
+        dst[2 * hb + 1] = make_ulonglong2(acc[2], acc[3]);
       }
     }
   }
   __syncthreads();
 
-  /* ---- stage 2: horizontal pass, unit = (row pair, 8 columns), lanes along row pairs ---- */
-  for (int u = tid; u < nrp * ncg; u += FT_THREADS)
+  /* ---- stage 3: vertical pass, unit = (column pair, 16 rows), lanes along column pairs ---- */
+  const int ry = wi * FT_VR; /* first output row of this warp inside the tile */
+  if (ry >= rows_valid)
+    return;
+  const int nrows = min(FT_VR, rows_valid - ry);
+  const int yb = y0 + ry; /* even */
+  if (x0 + FT_W <= p.w)
   {
-    const int cg = u / nrp, rp = u - cg * nrp;
-    const ulonglong2 *wsrc = (const ulonglong2 *)(s_in + rp * SS + (cg * 8 + RX - R) * 2);
-    pk2 wv[8 + 2 * R];
+    /* every lane owns a full pixel pair */
+    const int x = x0 + 2 * lane;
+    const float *mcol = s_mid + ry * FT_MS + 2 * lane;
+    const float *ccol = s_in + (R + ry) * S + RX + 2 * lane;
+    /* G and DoG share pitch and offset: one 32-bit byte offset walks down both layers */
+    char *const gbase = (char *)p.dst_g;
+    char *const dbase = (char *)p.dst_d;
+    char *const nbase = (char *)p.dst_next;
+    uint32_t off = ((uint32_t)yb * (uint32_t)p.dst_pitch + (uint32_t)x) * 4u;
+    uint32_t noff = ((uint32_t)(yb >> 1) * (uint32_t)p.next_pitch + (uint32_t)(x >> 1)) * 4u;
+    const uint32_t pitch4 = (uint32_t)p.dst_pitch * 4u, npitch4 = (uint32_t)p.next_pitch * 4u;
+    pk2 wv[FT_VR + 2 * R];
 #pragma unroll
-    for (int j = 0; j < (8 + 2 * R) / 2; j++)
+    for (int j = 0; j < 2 * R; j++)
+      wv[j] = *(const pk2 *)(mcol + j * FT_MS);
+#pragma unroll
+    for (int qb = 0; qb < FT_VR; qb += 4)
     {
-      const ulonglong2 v = wsrc[j];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        wv[2 * R + qb + j] = *(const pk2 *)(mcol + (2 * R + qb + j) * FT_MS);
+      pk2 acc[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        acc[j] = pk_mul(wv[R + qb + j], FT_TAP(0));
+#pragma unroll
+      for (int i = 1; i <= R; i++)
+      {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          acc[j] = pk_fma(pk_add(wv[R + qb + j + i], wv[R + qb + j - i]), FT_TAP(i), acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+      {
+        const int q = qb + j;
+        if (q < nrows)
+        {
+          *(pk2 *)(gbase + off) = acc[j];
+          if (KIND != FT_KIND_SEED)
+            *(pk2 *)(dbase + off) = pk_sub(acc[j], *(const pk2 *)(ccol + q * S));
+          if (KIND == FT_KIND_NEXT && (q & 1))
+          {
+            /* x even, y odd: the odd column of the pair feeds next(x>>1, y>>1) */
+            *(float *)(nbase + noff) = pk_hi(acc[j]);
+            noff += npitch4;
+          }
+        }
+        off += pitch4;
+      }
+    }
+  }
+  else
+  {
+    /* last tile column of a layer whose width is not a multiple of 64: plain scalar loop */
+    for (int idx = lane; idx < FT_W * nrows; idx += 32)
+    {
+      const int col = idx & (FT_W - 1), q = idx >> 6;
+      const int x = x0 + col, y = yb + q;
+      if (x >= p.w)
+        continue;
+      const float *mc = s_mid + (ry + q + R) * FT_MS + col;
+      float acc = vks_mul(mc[0], P.taps2[0].x);
+      for (int i = 1; i <= R; i++)
+        acc = vks_blur_tap(acc, mc[i * FT_MS], mc[-i * FT_MS], P.taps2[i].x);
+      p.dst_g[(size_t)y * p.dst_pitch + x] = acc;
+      if (KIND != FT_KIND_SEED)
+        p.dst_d[(size_t)y * p.dst_pitch + x] = vks_sub(acc, s_in[(R + ry + q) * S + RX + col]);
+      if (KIND == FT_KIND_NEXT && (x & 1) && (y & 1))
+      {
+        const int nx = x >> 1, ny = y >> 1;
+        if (nx < p.next_w && ny < p.next_h)
+          p.dst_next[(size_t)ny * p.next_pitch + nx] = acc;
+      }
+    }
+  }
+}
+
+/* ==========================================================================
+ * Fused kernel for the small octaves.
+ *
+ * Below ~1000x600 a layer is a handful of tiles and the pyramid becomes a chain of dependent launches
+ * (layer s needs layer s-1, the next octave needs layer ns): latency, not throughput.  This kernel
+ * produces up to FZ_MAXL consecutive layers of one octave in ONE launch: a CTA owns a 48x48 output tile,
+ * loads it with a halo of the summed radii and recomputes the halo of the intermediate layers itself
+ * (a few percent of the pyramid's pixels, so the redundant arithmetic is irrelevant).  Recomputing a
+ * layer outside the image on the MIRRORED_REPEAT extension of its source yields bit for bit the value of
+ * the mirror pixel (the tap pairs a+b only swap their operands), so borders need no special handling
+ * beyond the mirrored load.  Same per-pixel operation sequence as everywhere.
+ * ========================================================================== */
+#define FZ_T 48       /* output tile edge */
+#define FZ_MAXHALO 24 /* summed radii of a launch */
+#define FZ_WB 98      /* buffer row stride, floats: /2 odd -> LDS.64 down a column is conflict free */
+#define FZ_HB (FZ_T + 2 * FZ_MAXHALO)
+#define FZ_THREADS 512
+#define FZ_BUF (FZ_HB * FZ_WB)
+#define FZ_SMEM (3 * FZ_BUF * 4)
+
+/* rows [r_lo, r_lo+n_rows) x columns [c_lo, c_lo+n_cols) of `out` <- horizontal blur of `in`; n_cols % 4 == 0, c_lo even */
+template <int R>
+__device__ __forceinline__ void fz_blur_h(const float *__restrict__ in, float *__restrict__ out, const float2 *__restrict__ taps2, int r_lo, int n_rows,
+                                          int c_lo, int n_cols)
+{
+  const int n_cg = n_cols >> 2;
+  const int rr = threadIdx.x & 127; /* lanes along rows (n_rows <= 96), four column groups in flight */
+  if (rr >= n_rows)
+    return;
+  const int r = r_lo + rr;
+  for (int cg = threadIdx.x >> 7; cg < n_cg; cg += FZ_THREADS / 128)
+  {
+    const int c0 = c_lo + 4 * cg;
+    const float2 *src = (const float2 *)(in + r * FZ_WB + c0 - R);
+    float wv[4 + 2 * R];
+#pragma unroll
+    for (int j = 0; j < (4 + 2 * R) / 2; j++)
+    {
+      const float2 v = src[j];
       wv[2 * j] = v.x;
       wv[2 * j + 1] = v.y;
     }
-    pk2 o[8];
+    float acc[4];
 #pragma unroll
-    for (int q = 0; q < 8; q++)
-    {
-      pk2 acc = pk_mul(wv[R + q], taps2[0]);
+    for (int q = 0; q < 4; q++)
+      acc[q] = vks_mul(wv[R + q], taps2[0].x);
 #pragma unroll
-      for (int i = 1; i <= R; i++)
-        acc = pk_fma(pk_add(wv[R + q + i], wv[R + q - i]), taps2[i], acc);
-      o[q] = acc;
-    }
-    float *r0 = s_mid + (2 * rp) * FT_MS + cg * 8;
-    float *r1 = r0 + FT_MS;
+    for (int i = 1; i <= R; i++)
 #pragma unroll
-    for (int q = 0; q < 8; q += 2)
-    {
-      *(float2 *)(r0 + q) = make_float2(pk_lo(o[q]), pk_lo(o[q + 1]));
-      *(float2 *)(r1 + q) = make_float2(pk_hi(o[q]), pk_hi(o[q + 1]));
-    }
+      for (int q = 0; q < 4; q++)
+        acc[q] = vks_blur_tap(acc[q], wv[R + q + i], wv[R + q - i], taps2[i].x);
+    float2 *dst = (float2 *)(out + r * FZ_WB + c0);
+    dst[0] = make_float2(acc[0], acc[1]);
+    dst[1] = make_float2(acc[2], acc[3]);
   }
-  __syncthreads();
+}
 
-  /* ---- stage 3: vertical pass, unit = (column pair, 8 rows), lanes along column pairs ---- */
-  for (int u = tid; u < (FT_W / 2) * (TH / 8); u += FT_THREADS)
+/* vertical blur of `mid` over rows [lo, lo+n) x columns [lo, lo+n) (n % 4 == 0, lo even) -> `out`, plus the global stores of
+ * the pixels that lie in the tile core [core, core+FZ_T)^2 and in the image */
+template <int R>
+__device__ __forceinline__ void fz_blur_v(const FusedLaunch &P, int k, const float *__restrict__ mid, const float *__restrict__ cur, float *__restrict__ out,
+                                          const float2 *__restrict__ taps2, int lo, int n, int core, int x0, int y0)
+{
+  const int n_cp = n >> 1, n_rg = n >> 2;
+  float *gl = P.g0 + (size_t)k * P.layer_stride;
+  float *dl = P.d0 + (size_t)k * P.layer_stride;
+  const int cp = threadIdx.x & 63; /* lanes along column pairs (n_cp <= 48), eight row groups in flight */
+  if (cp >= n_cp)
+    return;
+  for (int rg = threadIdx.x >> 6; rg < n_rg; rg += FZ_THREADS / 64)
   {
-    const int rg = u / (FT_W / 2), cp = u - rg * (FT_W / 2);
-    const int x = x0 + 2 * cp;
-    const int yb = y0 + rg * 8;
-    if (x >= p.w || yb >= p.h)
-      continue;
-    pk2 wv[8 + 2 * R];
+    const int c = lo + 2 * cp, r0 = lo + 4 * rg;
+    const float *mcol = mid + (r0 - R) * FZ_WB + c;
+    pk2 wv[4 + 2 * R];
 #pragma unroll
-    for (int j = 0; j < 8 + 2 * R; j++)
-      wv[j] = *(const pk2 *)(s_mid + (rg * 8 + j) * FT_MS + 2 * cp);
-    pk2 o[8];
+    for (int j = 0; j < 4 + 2 * R; j++)
+      wv[j] = *(const pk2 *)(mcol + j * FZ_WB);
+    pk2 acc[4];
 #pragma unroll
-    for (int q = 0; q < 8; q++)
+    for (int q = 0; q < 4; q++)
+      acc[q] = pk_mul(wv[R + q], *(const pk2 *)&taps2[0]);
+#pragma unroll
+    for (int i = 1; i <= R; i++)
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        acc[q] = pk_fma(pk_add(wv[R + q + i], wv[R + q - i]), *(const pk2 *)&taps2[i], acc[q]);
+    const int gx = x0 + (c - core);
+    const bool col_ok = (c >= core) && (c < core + FZ_T) && (gx < P.w);
+    const bool pair_ok = col_ok && (gx + 1 < P.w);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
     {
-      pk2 acc = pk_mul(wv[R + q], taps2[0]);
-#pragma unroll
-      for (int i = 1; i <= R; i++)
-        acc = pk_fma(pk_add(wv[R + q + i], wv[R + q - i]), taps2[i], acc);
-      o[q] = acc;
-    }
-    const bool pair_ok = (x + 1 < p.w);
-#pragma unroll
-    for (int q = 0; q < 8; q += 2)
-    {
-      /* centre values of rows q, q+1: {in[y][x], in[y+1][x], in[y][x+1], in[y+1][x+1]} */
-      const float4 c = *(const float4 *)(s_in + ((R + rg * 8 + q) >> 1) * SS + (RX + 2 * cp) * 2);
-#pragma unroll
-      for (int e = 0; e < 2; e++)
+      const int r = r0 + q;
+      *(pk2 *)(out + r * FZ_WB + c) = acc[q];
+      const int gy = y0 + (r - core);
+      if (col_ok && r >= core && r < core + FZ_T && gy < P.h)
       {
-        const int y = yb + q + e;
-        if (y >= p.h)
-          continue;
-        const pk2 g = o[q + e];
-        const pk2 cen = e ? pk_make(c.y, c.w) : pk_make(c.x, c.z);
-        float *gp = p.dst_g + (size_t)y * p.dst_pitch + x;
+        const pk2 d = pk_sub(acc[q], *(const pk2 *)(cur + r * FZ_WB + c));
+        const size_t o = (size_t)gy * P.pitch + gx;
         if (pair_ok)
-          *(pk2 *)gp = g;
-        else
-          *gp = pk_lo(g);
-        if (p.dst_d)
         {
-          const pk2 d = pk_sub(g, cen);
-          float *dp = p.dst_d + (size_t)y * p.dst_pitch + x;
-          if (pair_ok)
-            *(pk2 *)dp = d;
-          else
-            *dp = pk_lo(d);
+          *(pk2 *)(gl + o) = acc[q];
+          *(pk2 *)(dl + o) = d;
         }
-        if (p.dst_next && (y & 1) && pair_ok)
+        else
         {
-          /* x is even: the odd column of the pair feeds next(x>>1, y>>1) */
-          const int nx = x >> 1, ny = y >> 1;
-          if (nx < p.next_w && ny < p.next_h)
-            p.dst_next[(size_t)ny * p.next_pitch + nx] = pk_hi(g);
+          gl[o] = pk_lo(acc[q]);
+          dl[o] = pk_lo(d);
+        }
+        if (k == P.next_k && (gy & 1) && pair_ok)
+        {
+          /* gx is even (tile origin and core offset are even): the odd column of the pair feeds next(gx>>1, gy>>1) */
+          const int nx = gx >> 1, ny = gy >> 1;
+          if (nx < P.next_w && ny < P.next_h)
+            P.dst_next[(size_t)ny * P.next_pitch + nx] = pk_hi(acc[q]);
         }
       }
     }
   }
 }
 
-struct BlurStepFast
+__global__ void __launch_bounds__(FZ_THREADS, 1) octave_fused_kernel(const __grid_constant__ FusedLaunch P)
 {
-  BlurStep s;
-  float2 taps2[VKS_MAX_PASSES_PER_STEP][14]; /* (k,k) pairs, zero padded to the even radius */
-};
-
-template <int TH>
-__device__ __forceinline__ void blur_tile_dispatch(const BlurPass &p, const pk2 *taps2, float *smem, int x0, int y0)
-{
-  switch ((p.radius + 1) & ~1)
+  extern __shared__ __align__(16) float fz_smem[];
+  float *cur = fz_smem, *mid = fz_smem + FZ_BUF, *nxt = fz_smem + 2 * FZ_BUF;
+  const int t = (int)blockIdx.x;
+  const int x0 = (t % P.tiles_x) * FZ_T, y0 = (t / P.tiles_x) * FZ_T;
+  int halo = 0;
+#pragma unroll
+  for (int k = 0; k < FZ_MAXL; k++)
+    if (k < P.n_layers)
+      halo += P.radius[k];
+  /* buffer cell (r, c) <-> image pixel (x0 - FZ_MAXHALO + c, y0 - FZ_MAXHALO + r); the tile core starts at FZ_MAXHALO */
   {
-  case 2:
-    blur_tile_fast<2, TH>(p, taps2, smem, x0, y0);
-    break;
-  case 4:
-    blur_tile_fast<4, TH>(p, taps2, smem, x0, y0);
-    break;
-  case 6:
-    blur_tile_fast<6, TH>(p, taps2, smem, x0, y0);
-    break;
-  case 8:
-    blur_tile_fast<8, TH>(p, taps2, smem, x0, y0);
-    break;
-  case 10:
-    blur_tile_fast<10, TH>(p, taps2, smem, x0, y0);
-    break;
-  default:
-    blur_tile_fast<12, TH>(p, taps2, smem, x0, y0);
-    break;
+    const int lo = FZ_MAXHALO - halo, n = FZ_T + 2 * halo;
+    const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int gxs[3]; /* n <= 96: at most three columns per lane */
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      gxs[j] = vks_mirror(x0 - halo + lane + 32 * j, P.w);
+    for (int rr = wi; rr < n; rr += FZ_THREADS / 32)
+    {
+      const float *row = P.src + (size_t)vks_mirror(y0 - halo + rr, P.h) * P.pitch;
+      float *dst = cur + (lo + rr) * FZ_WB + lo + lane;
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+        if (lane + 32 * j < n)
+          dst[32 * j] = __ldg(row + gxs[j]);
+    }
+  }
+  __syncthreads();
+  int m = halo;
+#pragma unroll
+  for (int k = 0; k < FZ_MAXL; k++)
+  {
+    if (k >= P.n_layers)
+      break;
+    const int R = P.radius[k];
+    m -= R;
+    const int lo = FZ_MAXHALO - m, n = FZ_T + 2 * m;
+    switch (R)
+    {
+    case 2:
+      fz_blur_h<2>(cur, mid, P.taps2[k], lo - R, n + 2 * R, lo, n);
+      break;
+    case 4:
+      fz_blur_h<4>(cur, mid, P.taps2[k], lo - R, n + 2 * R, lo, n);
+      break;
+    case 6:
+      fz_blur_h<6>(cur, mid, P.taps2[k], lo - R, n + 2 * R, lo, n);
+      break;
+    case 8:
+      fz_blur_h<8>(cur, mid, P.taps2[k], lo - R, n + 2 * R, lo, n);
+      break;
+    case 10:
+      fz_blur_h<10>(cur, mid, P.taps2[k], lo - R, n + 2 * R, lo, n);
+      break;
+    default:
+      fz_blur_h<12>(cur, mid, P.taps2[k], lo - R, n + 2 * R, lo, n);
+      break;
+    }
+    __syncthreads();
+    switch (R)
+    {
+    case 2:
+      fz_blur_v<2>(P, k, mid, cur, nxt, P.taps2[k], lo, n, FZ_MAXHALO, x0, y0);
+      break;
+    case 4:
+      fz_blur_v<4>(P, k, mid, cur, nxt, P.taps2[k], lo, n, FZ_MAXHALO, x0, y0);
+      break;
+    case 6:
+      fz_blur_v<6>(P, k, mid, cur, nxt, P.taps2[k], lo, n, FZ_MAXHALO, x0, y0);
+      break;
+    case 8:
+      fz_blur_v<8>(P, k, mid, cur, nxt, P.taps2[k], lo, n, FZ_MAXHALO, x0, y0);
+      break;
+    case 10:
+      fz_blur_v<10>(P, k, mid, cur, nxt, P.taps2[k], lo, n, FZ_MAXHALO, x0, y0);
+      break;
+    default:
+      fz_blur_v<12>(P, k, mid, cur, nxt, P.taps2[k], lo, n, FZ_MAXHALO, x0, y0);
+      break;
+    }
+    __syncthreads();
+    float *tmp = cur;
+    cur = nxt;
+    nxt = tmp;
   }
 }
 
-__global__ void __launch_bounds__(FT_THREADS, 2) blur_step_fast_kernel(const __grid_constant__ BlurStepFast S)
+/* Groups the passes of one octave (consecutive layers, same octave, float sources) into fused launches: a group
+ * ends after the layer that seeds the next octave, after FZ_MAXL layers or before the summed radii exceed FZ_MAXHALO.
+ * Returns false when a pass cannot be fused (radius > 12): the caller falls back to the compact kernel. */
+bool fused_plan_octave(const BlurPass *passes, int n_pass, std::vector<FusedLaunch> *out)
 {
-  extern __shared__ __align__(16) float ft_smem[];
-  int pi = 0;
-#pragma unroll
-  for (int i = 1; i < VKS_MAX_PASSES_PER_STEP; i++)
-    if (i < S.s.n_pass && (int)blockIdx.x >= S.s.pass[i].tile_begin)
-      pi = i;
-  const BlurPass &p = S.s.pass[pi];
-  const pk2 *taps2 = reinterpret_cast<const pk2 *>(S.taps2[pi]);
-  const int t = (int)blockIdx.x - p.tile_begin;
-  const int x0 = (t % p.tiles_x) * FT_W;
-  const int y0 = (t / p.tiles_x) * FT_H;
-  blur_tile_dispatch<FT_H>(p, taps2, ft_smem, x0, y0);
+  int i = 0;
+  while (i < n_pass)
+  {
+    FusedLaunch F;
+    memset(&F, 0, sizeof(F));
+    const BlurPass &first = passes[i];
+    if (first.src_kind != BLUR_SRC_LAYER)
+      return false;
+    F.src = (const float *)first.src;
+    F.g0 = first.dst_g;
+    F.d0 = first.dst_d;
+    F.w = first.w;
+    F.h = first.h;
+    F.pitch = first.dst_pitch;
+    F.next_k = -1;
+    F.tiles_x = (F.w + FZ_T - 1) / FZ_T;
+    int halo = 0;
+    while (i < n_pass && F.n_layers < FZ_MAXL)
+    {
+      const BlurPass &bp = passes[i];
+      if (bp.radius < 1 || bp.radius > 12)
+        return false;
+      const int re = ft_even(bp.radius);
+      if (halo + re > FZ_MAXHALO)
+        break;
+      const int k = F.n_layers;
+      if (k == 1)
+        F.layer_stride = (int)(bp.dst_g - F.g0);
+      F.radius[k] = re;
+      for (int j = 0; j < 14; j++)
+      {
+        const float v = (j <= bp.radius) ? bp.taps[j] : 0.f;
+        F.taps2[k][j] = make_float2(v, v);
+      }
+      halo += re;
+      F.n_layers++;
+      i++;
+      if (bp.dst_next)
+      {
+        F.next_k = k;
+        F.dst_next = bp.dst_next;
+        F.next_w = bp.next_w;
+        F.next_h = bp.next_h;
+        F.next_pitch = bp.next_pitch;
+        break;
+      }
+    }
+    if (F.n_layers == 0)
+      return false;
+    out->push_back(F);
+  }
+  return true;
 }
 
-/* A pass goes to the fast kernel when its radius is covered and the layer is large enough for
- * throughput to matter (more 64x128 tiles than SMs); everything else runs on the compact kernel. */
+cudaError_t launch_fused(const FusedLaunch &F, cudaStream_t st)
+{
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_done[dev])
+  {
+    cudaError_t e = cudaFuncSetAttribute(octave_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM);
+    if (e != cudaSuccess)
+      return e;
+    attr_done[dev] = true;
+  }
+  const int tiles = F.tiles_x * ((F.h + FZ_T - 1) / FZ_T);
+  octave_fused_kernel<<<tiles, FZ_THREADS, FZ_SMEM, st>>>(F);
+  return cudaGetLastError();
+}
+
+/* A pass goes to the fast per-layer kernel when its radius is covered and the layer is large enough for
+ * throughput to matter (one 64x128 tile per SM or more); smaller octaves are latency bound and take the
+ * fused kernel (or, when their radii do not fit it, the compact kernel). */
 bool blur_pass_is_fast(const BlurPass &bp)
 {
   if (bp.radius < 1 || bp.radius > 12)
@@ -507,63 +925,100 @@ bool blur_pass_is_fast(const BlurPass &bp)
   return ((bp.w + FT_W - 1) / FT_W) * ((bp.h + FT_H - 1) / FT_H) >= 148;
 }
 
-bool blur_step_is_fast(const BlurStep &step) { return step.n_pass > 0 && blur_pass_is_fast(step.pass[0]); }
-
-void blur_step_tiles(BlurStep *step)
+bool blur_step_tiles(BlurStep *step)
 {
-  /* tile geometry depends on the kernel that will run the step; a step never mixes the two kinds */
-  const bool fast = blur_step_is_fast(*step);
-  const int tw = fast ? FT_W : SB_W, th = fast ? FT_H : SB_H;
   int begin = 0;
   for (int i = 0; i < step->n_pass; i++)
   {
     BlurPass &bp = step->pass[i];
-    bp.tile_h = th;
-    bp.tiles_x = (bp.w + tw - 1) / tw;
-    bp.tiles_y = (bp.h + th - 1) / th;
+    bp.tile_h = SB_H;
+    bp.tiles_x = (bp.w + SB_W - 1) / SB_W;
+    bp.tiles_y = (bp.h + SB_H - 1) / SB_H;
     bp.tile_begin = begin;
     begin += bp.tiles_x * bp.tiles_y;
   }
   step->n_tiles = begin;
+  return true;
 }
 
-static cudaError_t launch_blur_step_fast(const BlurStep &step, cudaStream_t st)
+bool blur_pass_prepare_fast(BlurPass *bpp)
+{
+  BlurPass &bp = *bpp;
+  bp.tile_h = FT_H;
+  bp.tiles_x = (bp.w + FT_W - 1) / FT_W;
+  bp.tiles_y = (bp.h + FT_H - 1) / FT_H;
+  bp.tile_begin = 0;
+  if (bp.src_kind == BLUR_SRC_LAYER)
+  {
+    /* one TMA box = source tile + halo; cells outside the layer read as zero and are patched by the kernel */
+    const int re = ft_even(bp.radius);
+    const uint64_t dims[2] = {(uint64_t)bp.w, (uint64_t)bp.h};
+    const uint64_t strides[1] = {(uint64_t)bp.src_pitch * 4};
+    const uint32_t box[2] = {(uint32_t)ft_s(re), (uint32_t)FT_BOX_H};
+    if (!tma_make_map_f32(&bp.tmap, (const float *)bp.src, 2, dims, strides, box))
+      return false;
+  }
+  return true;
+}
+
+template <int R, int KIND>
+static cudaError_t launch_fast_rk(const BlurPassFast &F, int n_tiles, cudaStream_t st)
 {
   static bool attr_done[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_done[dev])
   {
-    cudaError_t e =
-        cudaFuncSetAttribute(blur_step_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(float) * ft_smem_floats(12, FT_H));
+    cudaError_t e = cudaFuncSetAttribute(blur_pass_fast_kernel<R, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes(R));
     if (e != cudaSuccess)
       return e;
     attr_done[dev] = true;
   }
-  BlurStepFast F;
-  F.s = step;
-  size_t smem = 0;
-  for (int i = 0; i < step.n_pass; i++)
-  {
-    const int re = (step.pass[i].radius + 1) & ~1;
-    const size_t need = sizeof(float) * (size_t)ft_smem_floats(re < 2 ? 2 : re, FT_H);
-    smem = need > smem ? need : smem;
-    for (int k = 0; k < 14; k++)
-    {
-      const float v = (k <= step.pass[i].radius) ? step.pass[i].taps[k] : 0.f;
-      F.taps2[i][k] = make_float2(v, v);
-    }
-  }
-  blur_step_fast_kernel<<<step.n_tiles, FT_THREADS, smem, st>>>(F);
+  blur_pass_fast_kernel<R, KIND><<<n_tiles, FT_THREADS, ft_smem_bytes(R), st>>>(F);
   return cudaGetLastError();
+}
+
+template <int R>
+static cudaError_t launch_fast_r(const BlurPassFast &F, int n_tiles, cudaStream_t st)
+{
+  if (F.p.src_kind != BLUR_SRC_LAYER)
+    return launch_fast_rk<R, FT_KIND_SEED>(F, n_tiles, st);
+  if (F.p.dst_next)
+    return launch_fast_rk<R, FT_KIND_NEXT>(F, n_tiles, st);
+  return launch_fast_rk<R, FT_KIND_LAYER>(F, n_tiles, st);
+}
+
+cudaError_t launch_blur_pass_fast(const BlurPass &bp, cudaStream_t st)
+{
+  BlurPassFast F;
+  F.p = bp;
+  for (int k = 0; k < 14; k++)
+  {
+    const float v = (k <= bp.radius) ? bp.taps[k] : 0.f;
+    F.taps2[k] = make_float2(v, v);
+  }
+  const int n_tiles = bp.tiles_x * bp.tiles_y;
+  switch (ft_even(bp.radius))
+  {
+  case 2:
+    return launch_fast_r<2>(F, n_tiles, st);
+  case 4:
+    return launch_fast_r<4>(F, n_tiles, st);
+  case 6:
+    return launch_fast_r<6>(F, n_tiles, st);
+  case 8:
+    return launch_fast_r<8>(F, n_tiles, st);
+  case 10:
+    return launch_fast_r<10>(F, n_tiles, st);
+  default:
+    return launch_fast_r<12>(F, n_tiles, st);
+  }
 }
 
 cudaError_t launch_blur_step(const BlurStep &step, cudaStream_t st)
 {
   if (step.n_tiles <= 0)
     return cudaSuccess;
-  if (blur_step_is_fast(step))
-    return launch_blur_step_fast(step, st);
   blur_step_small_kernel<<<step.n_tiles, 256, 0, st>>>(step);
   return cudaGetLastError();
 }

@@ -11,8 +11,11 @@
  */
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <vector>
 
 #include "vksift_arith.h"
 #include "vksift_b200_ext.h"
@@ -115,6 +118,7 @@ struct BlurPass
   int tiles_x, tiles_y, tile_begin; /* CTA range of this pass inside the launch */
   int tile_h;                       /* output rows per tile chosen for this pass */
   float taps[VKS_MAX_TAPS];
+  alignas(64) CUtensorMap tmap; /* source layer, box = tile + halo (fast kernel, float sources) */
 };
 #define VKS_MAX_PASSES_PER_STEP 4
 struct BlurStep
@@ -122,6 +126,24 @@ struct BlurStep
   BlurPass pass[VKS_MAX_PASSES_PER_STEP];
   int n_pass;
   int n_tiles;
+};
+
+/* up to FZ_MAXL consecutive layers of one (small) octave produced by one launch of the fused kernel */
+#define FZ_MAXL 3
+struct FusedLaunch
+{
+  const float *src; /* layer s_begin-1 of the octave */
+  float *g0;        /* Gaussian layer s_begin */
+  float *d0;        /* DoG layer s_begin-1 */
+  int layer_stride; /* floats between consecutive layers */
+  int w, h, pitch;
+  int n_layers;
+  int radius[FZ_MAXL]; /* rounded up to even, taps zero padded */
+  int next_k;          /* layer (0-based inside the launch) whose NEAREST decimation seeds the next octave, or -1 */
+  float *dst_next;
+  int next_w, next_h, next_pitch;
+  int tiles_x;
+  float2 taps2[FZ_MAXL][14];
 };
 
 /* ---- host-side plan ------------------------------------------------------ */
@@ -146,10 +168,16 @@ struct FeatureBuffer;
 struct Instance;
 
 /* fills tiles_x/tiles_y/tile_begin/n_tiles of a step for the kernel that will run it */
-void blur_step_tiles(BlurStep *step);
+bool blur_step_tiles(BlurStep *step);
 /* true when the pass runs on the unrolled packed-fp32 kernel, false for the compact kernel */
 bool blur_pass_is_fast(const BlurPass &bp);
+/* tile geometry + TMA tensor map of a pass for the fast kernel */
+bool blur_pass_prepare_fast(BlurPass *bp);
+cudaError_t launch_blur_pass_fast(const BlurPass &bp, cudaStream_t st);
 cudaError_t launch_blur_step(const BlurStep &step, cudaStream_t st);
+/* groups consecutive layer passes of one octave into fused launches; false when a pass cannot be fused */
+bool fused_plan_octave(const BlurPass *passes, int n_pass, std::vector<FusedLaunch> *out);
+cudaError_t launch_fused(const FusedLaunch &F, cudaStream_t st);
 struct ExtremaPlan; /* TMA tensor maps over the DoG layers of the current pyramid */
 cudaError_t extrema_plan_build(const DetectParams &P, ExtremaPlan **plan_io);
 void extrema_plan_destroy(ExtremaPlan *pl);
