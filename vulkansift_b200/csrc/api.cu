@@ -119,6 +119,19 @@ struct vksift_Instance_T
 
   uint8_t *h_image = nullptr; /* pinned */
   uint8_t *d_image = nullptr;
+  const uint8_t **h_src_slot = nullptr; /* pinned: pointer of the image the next detection reads */
+  const uint8_t **d_src_slot = nullptr; /* device copy, read by the seed pass */
+  /* the detection pipeline of a buffer as a CUDA graph (the reference's pre-recorded command buffer, sift_detector.c:1369-1393):
+   * ~25 launches and ~15 cross-stream event operations cost more CPU time than the GPU needs to run them */
+  struct DetectGraph
+  {
+    cudaGraphExec_t exec = nullptr;
+    bool prof = false;
+    uint32_t uses = 0; /* the first use runs eagerly (lazy kernel attributes), the second one captures */
+    uint64_t launches = 0;
+  };
+  std::vector<DetectGraph> graphs;
+  bool use_graph = true;
 
   std::vector<FeatureBuffer> buffers;
   Candidate *cand = nullptr;
@@ -299,7 +312,7 @@ bool build_blur_plan(vksift_Instance inst)
     bp.dst_g = p.G[o] + layer * s;
     if (s == 0)
     {
-      bp.src = inst->d_image; /* patched per call when the image already lives in HBM */
+      bp.src = inst->d_src_slot; /* slot holding the address of the image (staging copy or caller's device buffer) */
       bp.src_kind = inst->cfg.use_input_upsampling ? BLUR_SRC_U8_UP2 : BLUR_SRC_U8;
       bp.src_w = (int)inst->cur_w;
       bp.src_h = (int)inst->cur_h;
@@ -426,8 +439,11 @@ bool build_blur_plan(vksift_Instance inst)
 
 void fill_detect_params(vksift_Instance inst, const FeatureBuffer &fb, DetectParams *P);
 
+void invalidate_graphs(vksift_Instance inst);
+
 bool set_resolution(vksift_Instance inst, uint32_t w, uint32_t h)
 {
+  invalidate_graphs(inst); /* captured launches carry the old geometry */
   inst->cur_w = w;
   inst->cur_h = h;
   Pyramid &p = inst->pyr;
@@ -448,6 +464,7 @@ bool set_resolution(vksift_Instance inst, uint32_t w, uint32_t h)
 
 void update_buffer_sections(vksift_Instance inst, FeatureBuffer &fb)
 {
+  invalidate_graphs(inst);
   fb.cur_w = inst->cur_w;
   fb.cur_h = inst->cur_h;
   fb.n_oct = inst->pyr.n_oct;
@@ -539,6 +556,10 @@ void destroy_instance(vksift_Instance inst)
   if (inst->h_image)
     cudaFreeHost(inst->h_image);
   cudaFree(inst->d_image);
+  invalidate_graphs(inst);
+  if (inst->h_src_slot)
+    cudaFreeHost(inst->h_src_slot);
+  cudaFree(inst->d_src_slot);
   cudaFree(inst->cand);
   cudaFree(inst->raw);
   cudaFree(inst->prim);
@@ -615,6 +636,12 @@ bool create_resources(vksift_Instance inst)
 
   CU_TRY(cudaHostAlloc(&inst->h_image, inst->max_image_size, cudaHostAllocDefault));
   CU_TRY(cudaMalloc(&inst->d_image, inst->max_image_size));
+  CU_TRY(cudaHostAlloc(&inst->h_src_slot, sizeof(void *), cudaHostAllocDefault));
+  CU_TRY(cudaMalloc(&inst->d_src_slot, sizeof(void *)));
+  {
+    const char *ng = getenv("VKSIFT_NO_GRAPH");
+    inst->use_graph = !(ng && ng[0] == '1');
+  }
 
   const size_t maxf = c.max_nb_sift_per_buffer;
   inst->ori_stride = (c.max_nb_orientation_per_keypoint == 0 || c.max_nb_orientation_per_keypoint > VKS_MAX_ORI) ? VKS_MAX_ORI
@@ -631,6 +658,7 @@ bool create_resources(vksift_Instance inst)
   CU_TRY(match_workspace_create(&inst->match_ws, c.max_nb_sift_per_buffer));
 
   inst->buffers.resize(c.sift_buffer_count);
+  inst->graphs.resize(c.sift_buffer_count);
   for (auto &fb : inst->buffers)
   {
     /* +256 rows: the matcher's TMA boxes and |b|^2 loads may run past the last feature */
@@ -696,18 +724,24 @@ void trace_dump(vksift_Instance inst)
   fprintf(stderr, "[trace] scale space done at %.1f us\n", d1 * 1e3f);
 }
 
-/* enqueue the whole detection pipeline (sift_detector.c:1369-1393) */
-bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t buf)
+/* every operation of one detection on the instance's streams, in an order that stream capture accepts
+ * (the side streams fork from and join the main stream through events) */
+bool record_detection(vksift_Instance inst, uint32_t buf)
 {
   FeatureBuffer &fb = inst->buffers[buf];
   cudaStream_t st = inst->stream;
   DetectParams P;
   fill_detect_params(inst, fb, &P);
   const bool prof = inst->profiling;
+  /* stage-time events must become event-record nodes when the sequence is captured into a graph */
+  cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+  CU_TRY(cudaStreamIsCapturing(st, &cap_status));
+  const bool capturing = (cap_status == cudaStreamCaptureStatusActive);
 
   inst->trace_used = 0;
+  CU_TRY(cudaMemcpyAsync(inst->d_src_slot, inst->h_src_slot, sizeof(void *), cudaMemcpyHostToDevice, st));
   if (prof)
-    CU_TRY(cudaEventRecord(inst->ev[EV_D0], st));
+    CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D0], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   CU_TRY(cudaMemsetAsync(fb.cnt, 0, sizeof(DetectCounters), st));
   const int ns = inst->cfg.nb_scales_per_octave;
   const int n_fast = (int)inst->fast_oct.size();
@@ -718,8 +752,6 @@ bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t bu
       CU_TRY(cudaStreamWaitEvent(so, inst->ev_seed[o], 0));
     for (BlurPass &bp : inst->fast_oct[o])
     {
-      if (bp.src_kind != BLUR_SRC_LAYER)
-        bp.src = d_image;
       {
         TraceScope ts(inst, so, "fast o%d r%d", o, bp.radius);
         CU_TRY(launch_blur_pass_fast(bp, so));
@@ -743,7 +775,6 @@ bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t bu
       auto &fo = inst->fused_oct[j];
       if (fo.has_seed_step)
       {
-        fo.seed_step.pass[0].src = d_image;
         CU_TRY(launch_blur_step(fo.seed_step, ss));
         inst->launches++;
       }
@@ -784,9 +815,6 @@ bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t bu
       CU_TRY(cudaStreamWaitEvent(ss, inst->ev_seed[n_fast], 0));
     for (BlurStep &step : inst->steps_side)
     {
-      for (int i = 0; i < step.n_pass; i++)
-        if (step.pass[i].src_kind != BLUR_SRC_LAYER)
-          step.pass[i].src = d_image;
       CU_TRY(launch_blur_step(step, ss));
       inst->launches++;
     }
@@ -799,25 +827,91 @@ bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t bu
   for (int o = 1; o < n_fast; o++)
     CU_TRY(cudaStreamWaitEvent(st, inst->ev_oct_done[o], 0));
   if (prof)
-    CU_TRY(cudaEventRecord(inst->ev[EV_D1], st));
+    CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D1], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+  {
+    const cudaError_t pe = cudaPeekAtLastError();
+    if (pe != cudaSuccess)
+      LOGE(TAG, "pending CUDA error before the extrema scan: %s", cudaGetErrorName(pe));
+  }
   CU_TRY(launch_extrema(P, inst->extrema_plan, inst->raw, inst->cand, fb.cnt, st));
   inst->launches += 2;
   CU_TRY(launch_order_primaries(P, inst->cand, fb.cnt, inst->prim, st));
   inst->launches++;
   if (prof)
-    CU_TRY(cudaEventRecord(inst->ev[EV_D2], st));
+    CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D2], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   CU_TRY(launch_orientation(P, fb.cnt, inst->prim, inst->ori, inst->n_ori, st));
   inst->launches++;
   if (prof)
-    CU_TRY(cudaEventRecord(inst->ev[EV_D3], st));
+    CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D3], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   CU_TRY(launch_assemble(P, fb.cnt, inst->n_ori, inst->feat_src, fb.host_counts_dev, st));
   CU_TRY(launch_descriptors(P, fb.cnt, inst->prim, inst->ori, inst->feat_src, fb.heads, fb.desc, st));
   inst->launches += 2;
   if (prof)
+    CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D4], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+  return true;
+}
+
+void invalidate_graphs(vksift_Instance inst)
+{
+  for (auto &g : inst->graphs)
   {
-    CU_TRY(cudaEventRecord(inst->ev[EV_D4], st));
-    inst->ev_detect_valid = true;
+    if (g.exec)
+      cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+    g.uses = 0;
   }
+}
+
+/* enqueue the whole detection pipeline (sift_detector.c:1369-1393): replay of the buffer's graph, captured on its second use */
+bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t buf)
+{
+  FeatureBuffer &fb = inst->buffers[buf];
+  cudaStream_t st = inst->stream;
+  *inst->h_src_slot = d_image;
+  auto &g = inst->graphs[buf];
+  const bool want_graph = inst->use_graph && !inst->trace;
+  if (g.exec && (g.prof != inst->profiling || !want_graph))
+  {
+    cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+  }
+  if (want_graph && !g.exec && g.uses >= 1)
+  {
+    const uint64_t l0 = inst->launches;
+    CU_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const bool ok = record_detection(inst, buf);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    g.launches = inst->launches - l0;
+    inst->launches = l0;
+    if (ok && e == cudaSuccess && graph)
+    {
+      if (cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess)
+      {
+        g.exec = nullptr;
+        cudaGetLastError();
+      }
+      g.prof = inst->profiling;
+    }
+    else
+    {
+      LOGW(TAG, "CUDA graph capture of the detection pipeline failed (%s), launching eagerly", cudaGetErrorName(e));
+      cudaGetLastError();
+      inst->use_graph = false;
+    }
+    if (graph)
+      cudaGraphDestroy(graph);
+  }
+  g.uses++;
+  if (g.exec)
+  {
+    CU_TRY(cudaGraphLaunch(g.exec, st));
+    inst->launches += g.launches;
+  }
+  else if (!record_detection(inst, buf))
+    return false;
+  if (inst->profiling)
+    inst->ev_detect_valid = true;
   CU_TRY(cudaEventRecord(inst->ev_detect_done, st));
   inst->detect_pending = true;
   inst->detect_buffer = buf;

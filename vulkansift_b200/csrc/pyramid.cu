@@ -20,6 +20,7 @@
 #include "vksift_internal.h"
 #include "tma_util.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -77,8 +78,8 @@ __device__ __forceinline__ float fetch_src(const BlurPass &p, int x, int y)
   if (p.src_kind == BLUR_SRC_LAYER)
     return ((const float *)p.src)[(size_t)y * p.src_pitch + x];
   if (p.src_kind == BLUR_SRC_U8_UP2)
-    return fetch_u8_up2((const uint8_t *)p.src, p.src_w, p.src_h, x, y);
-  return vks_unorm8(((const uint8_t *)p.src)[(size_t)y * p.src_w + x]);
+    return fetch_u8_up2(*(const uint8_t *const *)p.src, p.src_w, p.src_h, x, y);
+  return vks_unorm8((*(const uint8_t *const *)p.src)[(size_t)y * p.src_w + x]);
 }
 
 /* ---- compact tile kernel ----------------------------------------------------
@@ -244,6 +245,12 @@ __device__ __forceinline__ pk2 pk_make(float lo, float hi)
   return d;
 }
 
+/* Programmatic dependent launch: a kernel lets the next launch of its stream be scheduled while it is still
+ * running (its CTAs take over SMs as ours drain and run their prologue), and waits for the completion and
+ * memory flush of the previous launch before it touches anything that launch wrote. */
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 #define FT_W 64
 #define FT_H 128
 #define FT_THREADS 256
@@ -302,6 +309,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) blur_pass_fast_kernel(const __g
   int bands_seen = FT_NB;                      /* TMA bands this thread has already waited for */
 
   /* ---- stage 1: source tile -> smem ---- */
+  pdl_launch_dependents();
   if (KIND != FT_KIND_SEED)
   {
     if (tid == 0)
@@ -310,6 +318,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) blur_pass_fast_kernel(const __g
       for (int b = 0; b < FT_NB; b++)
         tma_mbar_init(bar0 + 8 * b, 1);
       tma_mbar_fence_init();
+      pdl_wait(); /* the source layer is written by the previous launch of the stream */
 #pragma unroll
       for (int b = 0; b < FT_NB; b++)
       {
@@ -366,12 +375,13 @@ __global__ void __launch_bounds__(FT_THREADS, 2) blur_pass_fast_kernel(const __g
   }
   else
   {
+    pdl_wait();
     /* octave 0 seed.  s_mid serves as scratch: the u8 source window as float (one UNORM division per
      * source pixel, MIRRORED_REPEAT / clamp-to-edge resolved here), then the LINEAR 2x blit (or the 1:1
      * copy) out of shared memory.  Destination cell (m, c) <-> image pixel (x0-RX+c, y0-R+m). */
     const bool up = (p.src_kind == BLUR_SRC_U8_UP2);
     const bool once = (x0 - RX >= -p.w) && (x0 - RX + S <= 2 * p.w) && (y0 - R >= -p.h) && (y0 + FT_H + R <= 2 * p.h);
-    const uint8_t *__restrict__ img = (const uint8_t *)p.src;
+    const uint8_t *__restrict__ img = *(const uint8_t *const *)p.src; /* u8 sources are reached through a pointer slot (see BlurPass) */
     const int n_el = S * rows_in;
     /* mirrored destination coordinates stay inside [lo, hi] of the image */
     const int dx_lo = max(0, min(x0 - RX, p.w - 1)), dx_hi = min(p.w - 1, max(0, x0 - RX + S - 1));
@@ -633,146 +643,57 @@ __global__ void __launch_bounds__(FT_THREADS, 2) blur_pass_fast_kernel(const __g
  * Fused kernel for the small octaves.
  *
  * Below ~1000x600 a layer is a handful of tiles and the pyramid becomes a chain of dependent launches
- * (layer s needs layer s-1, the next octave needs layer ns): latency, not throughput.  This kernel
- * produces up to FZ_MAXL consecutive layers of one octave in ONE launch: a CTA owns a 48x48 output tile,
- * loads it with a halo of the summed radii and recomputes the halo of the intermediate layers itself
- * (a few percent of the pyramid's pixels, so the redundant arithmetic is irrelevant).  Recomputing a
- * layer outside the image on the MIRRORED_REPEAT extension of its source yields bit for bit the value of
- * the mirror pixel (the tap pairs a+b only swap their operands), so borders need no special handling
- * beyond the mirrored load.  Same per-pixel operation sequence as everywhere.
+ * (layer s needs layer s-1, the next octave needs layer ns): latency, not throughput.  Two measured facts
+ * shape this kernel (B200, profiles/): a launch on a cold SM pays roughly 0.5-1 us per KB of straight-line
+ * code it runs once, so the unrolled kernels above need 10+ us for a one-tile grid; and the per-launch
+ * dependency gap is ~2.5 us.  So: ONE launch produces up to FZ_MAXL consecutive layers of an octave, and
+ * its code is a few hundred bytes of rolled loops that stay in the instruction cache.
+ * A CTA owns a 32x32 output tile, loads it with a halo of the summed radii and recomputes the halo of the
+ * intermediate layers itself (the small octaves hold ~6 % of the pyramid's pixels; small tiles keep the
+ * per-CTA critical path short and spread an octave over many SMs).  Recomputing a layer outside the
+ * image on the MIRRORED_REPEAT extension of its source yields bit for bit the value of the mirror pixel
+ * (the tap pairs a+b only swap their operands), so borders need no special handling beyond the mirrored
+ * load.  One thread = one pixel, lanes along x in both passes (conflict-free LDS.32); the loops are bound
+ * by the shared-memory pipe, which is fine at this size.
  * ========================================================================== */
-#define FZ_T 48       /* output tile edge */
+#define FZ_T 32       /* output tile edge */
 #define FZ_MAXHALO 24 /* summed radii of a launch */
-#define FZ_WB 98      /* buffer row stride, floats: /2 odd -> LDS.64 down a column is conflict free */
 #define FZ_HB (FZ_T + 2 * FZ_MAXHALO)
-#define FZ_THREADS 512
+#define FZ_WB (FZ_HB + 1)
+#define FZ_THREADS 1024
 #define FZ_BUF (FZ_HB * FZ_WB)
 #define FZ_SMEM (3 * FZ_BUF * 4)
-
-/* rows [r_lo, r_lo+n_rows) x columns [c_lo, c_lo+n_cols) of `out` <- horizontal blur of `in`; n_cols % 4 == 0, c_lo even */
-template <int R>
-__device__ __forceinline__ void fz_blur_h(const float *__restrict__ in, float *__restrict__ out, const float2 *__restrict__ taps2, int r_lo, int n_rows,
-                                          int c_lo, int n_cols)
-{
-  const int n_cg = n_cols >> 2;
-  const int rr = threadIdx.x & 127; /* lanes along rows (n_rows <= 96), four column groups in flight */
-  if (rr >= n_rows)
-    return;
-  const int r = r_lo + rr;
-  for (int cg = threadIdx.x >> 7; cg < n_cg; cg += FZ_THREADS / 128)
-  {
-    const int c0 = c_lo + 4 * cg;
-    const float2 *src = (const float2 *)(in + r * FZ_WB + c0 - R);
-    float wv[4 + 2 * R];
-#pragma unroll
-    for (int j = 0; j < (4 + 2 * R) / 2; j++)
-    {
-      const float2 v = src[j];
-      wv[2 * j] = v.x;
-      wv[2 * j + 1] = v.y;
-    }
-    float acc[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-      acc[q] = vks_mul(wv[R + q], taps2[0].x);
-#pragma unroll
-    for (int i = 1; i <= R; i++)
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-        acc[q] = vks_blur_tap(acc[q], wv[R + q + i], wv[R + q - i], taps2[i].x);
-    float2 *dst = (float2 *)(out + r * FZ_WB + c0);
-    dst[0] = make_float2(acc[0], acc[1]);
-    dst[1] = make_float2(acc[2], acc[3]);
-  }
-}
-
-/* vertical blur of `mid` over rows [lo, lo+n) x columns [lo, lo+n) (n % 4 == 0, lo even) -> `out`, plus the global stores of
- * the pixels that lie in the tile core [core, core+FZ_T)^2 and in the image */
-template <int R>
-__device__ __forceinline__ void fz_blur_v(const FusedLaunch &P, int k, const float *__restrict__ mid, const float *__restrict__ cur, float *__restrict__ out,
-                                          const float2 *__restrict__ taps2, int lo, int n, int core, int x0, int y0)
-{
-  const int n_cp = n >> 1, n_rg = n >> 2;
-  float *gl = P.g0 + (size_t)k * P.layer_stride;
-  float *dl = P.d0 + (size_t)k * P.layer_stride;
-  const int cp = threadIdx.x & 63; /* lanes along column pairs (n_cp <= 48), eight row groups in flight */
-  if (cp >= n_cp)
-    return;
-  for (int rg = threadIdx.x >> 6; rg < n_rg; rg += FZ_THREADS / 64)
-  {
-    const int c = lo + 2 * cp, r0 = lo + 4 * rg;
-    const float *mcol = mid + (r0 - R) * FZ_WB + c;
-    pk2 wv[4 + 2 * R];
-#pragma unroll
-    for (int j = 0; j < 4 + 2 * R; j++)
-      wv[j] = *(const pk2 *)(mcol + j * FZ_WB);
-    pk2 acc[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-      acc[q] = pk_mul(wv[R + q], *(const pk2 *)&taps2[0]);
-#pragma unroll
-    for (int i = 1; i <= R; i++)
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-        acc[q] = pk_fma(pk_add(wv[R + q + i], wv[R + q - i]), *(const pk2 *)&taps2[i], acc[q]);
-    const int gx = x0 + (c - core);
-    const bool col_ok = (c >= core) && (c < core + FZ_T) && (gx < P.w);
-    const bool pair_ok = col_ok && (gx + 1 < P.w);
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-    {
-      const int r = r0 + q;
-      *(pk2 *)(out + r * FZ_WB + c) = acc[q];
-      const int gy = y0 + (r - core);
-      if (col_ok && r >= core && r < core + FZ_T && gy < P.h)
-      {
-        const pk2 d = pk_sub(acc[q], *(const pk2 *)(cur + r * FZ_WB + c));
-        const size_t o = (size_t)gy * P.pitch + gx;
-        if (pair_ok)
-        {
-          *(pk2 *)(gl + o) = acc[q];
-          *(pk2 *)(dl + o) = d;
-        }
-        else
-        {
-          gl[o] = pk_lo(acc[q]);
-          dl[o] = pk_lo(d);
-        }
-        if (k == P.next_k && (gy & 1) && pair_ok)
-        {
-          /* gx is even (tile origin and core offset are even): the odd column of the pair feeds next(gx>>1, gy>>1) */
-          const int nx = gx >> 1, ny = gy >> 1;
-          if (nx < P.next_w && ny < P.next_h)
-            P.dst_next[(size_t)ny * P.next_pitch + nx] = pk_hi(acc[q]);
-        }
-      }
-    }
-  }
-}
 
 __global__ void __launch_bounds__(FZ_THREADS, 1) octave_fused_kernel(const __grid_constant__ FusedLaunch P)
 {
   extern __shared__ __align__(16) float fz_smem[];
+  __shared__ float s_taps[FZ_MAXL][16];
   float *cur = fz_smem, *mid = fz_smem + FZ_BUF, *nxt = fz_smem + 2 * FZ_BUF;
+  const int tid = threadIdx.x;
+  const int wi = tid >> 5, lane = tid & 31;
   const int t = (int)blockIdx.x;
   const int x0 = (t % P.tiles_x) * FZ_T, y0 = (t / P.tiles_x) * FZ_T;
   int halo = 0;
-#pragma unroll
-  for (int k = 0; k < FZ_MAXL; k++)
-    if (k < P.n_layers)
-      halo += P.radius[k];
-  /* buffer cell (r, c) <-> image pixel (x0 - FZ_MAXHALO + c, y0 - FZ_MAXHALO + r); the tile core starts at FZ_MAXHALO */
+  for (int k = 0; k < P.n_layers; k++)
+    halo += P.radius[k];
+  if (tid < FZ_MAXL * 16)
+    s_taps[tid >> 4][tid & 15] = (tid & 15) < 14 ? P.taps2[tid >> 4][tid & 15].x : 0.f;
+  pdl_launch_dependents();
+  pdl_wait(); /* the source layer is written by the previous launch of the stream */
+  /* buffer cell (r, c) <-> image pixel (x0 - halo + c, y0 - halo + r) */
   {
-    const int lo = FZ_MAXHALO - halo, n = FZ_T + 2 * halo;
-    const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int gxs[3]; /* n <= 96: at most three columns per lane */
+    const int n = FZ_T + 2 * halo;
+    /* a halo of at most 24 pixels reflects once unless the octave itself is tiny */
+    const bool once = (FZ_MAXHALO <= P.w) && (FZ_MAXHALO <= P.h) && (x0 + FZ_T + FZ_MAXHALO <= 2 * P.w) && (y0 + FZ_T + FZ_MAXHALO <= 2 * P.h);
+    int gxs[3]; /* n <= 80: at most three columns per lane */
 #pragma unroll
     for (int j = 0; j < 3; j++)
-      gxs[j] = vks_mirror(x0 - halo + lane + 32 * j, P.w);
+      gxs[j] = once ? mirror_once(x0 - halo + lane + 32 * j, P.w) : vks_mirror(x0 - halo + lane + 32 * j, P.w);
     for (int rr = wi; rr < n; rr += FZ_THREADS / 32)
     {
-      const float *row = P.src + (size_t)vks_mirror(y0 - halo + rr, P.h) * P.pitch;
-      float *dst = cur + (lo + rr) * FZ_WB + lo + lane;
+      const int gy = once ? mirror_once(y0 - halo + rr, P.h) : vks_mirror(y0 - halo + rr, P.h);
+      const float *row = P.src + (size_t)gy * P.pitch;
+      float *dst = cur + rr * FZ_WB + lane;
 #pragma unroll
       for (int j = 0; j < 3; j++)
         if (lane + 32 * j < n)
@@ -780,63 +701,89 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) octave_fused_kernel(const __gri
     }
   }
   __syncthreads();
-  int m = halo;
-#pragma unroll
-  for (int k = 0; k < FZ_MAXL; k++)
+  int lo = 0; /* the region of the current source is [lo, lo+n)^2 in buffer cells */
+#pragma unroll 1
+  for (int k = 0; k < P.n_layers; k++)
   {
-    if (k >= P.n_layers)
-      break;
     const int R = P.radius[k];
-    m -= R;
-    const int lo = FZ_MAXHALO - m, n = FZ_T + 2 * m;
-    switch (R)
-    {
-    case 2:
-      fz_blur_h<2>(cur, mid, P.taps2[k], lo - R, n + 2 * R, lo, n);
-      break;
-    case 4:
-      fz_blur_h<4>(cur, mid, P.taps2[k], lo - R, n + 2 * R, lo, n);
-      break;
-    case 6:
-      fz_blur_h<6>(cur, mid, P.taps2[k], lo - R, n + 2 * R, lo, n);
-      break;
-    case 8:
-      fz_blur_h<8>(cur, mid, P.taps2[k], lo - R, n + 2 * R, lo, n);
-      break;
-    case 10:
-      fz_blur_h<10>(cur, mid, P.taps2[k], lo - R, n + 2 * R, lo, n);
-      break;
-    default:
-      fz_blur_h<12>(cur, mid, P.taps2[k], lo - R, n + 2 * R, lo, n);
-      break;
-    }
+    const float *tp = s_taps[k];
+    const int n_src = FZ_T + 2 * (halo - lo);
+    const int n = n_src - 2 * R; /* region of this layer: [lo+R, lo+R+n)^2 */
+    /* horizontal: rows [lo, lo+n_src), columns [lo+R, lo+R+n) */
+#pragma unroll 1
+    for (int r = lo + wi; r < lo + n_src; r += FZ_THREADS / 32)
+#pragma unroll 1
+      for (int c = lo + R + lane; c < lo + R + n; c += 32)
+      {
+        const float *q = cur + r * FZ_WB + c;
+        float acc = vks_mul(q[0], tp[0]);
+#pragma unroll 2
+        for (int i = 1; i <= R; i++)
+          acc = vks_blur_tap(acc, q[i], q[-i], tp[i]);
+        mid[r * FZ_WB + c] = acc;
+      }
     __syncthreads();
-    switch (R)
+    /* vertical over [lo+R, lo+R+n)^2, plus the global stores of the pixels that lie in the tile core and in the image */
     {
-    case 2:
-      fz_blur_v<2>(P, k, mid, cur, nxt, P.taps2[k], lo, n, FZ_MAXHALO, x0, y0);
-      break;
-    case 4:
-      fz_blur_v<4>(P, k, mid, cur, nxt, P.taps2[k], lo, n, FZ_MAXHALO, x0, y0);
-      break;
-    case 6:
-      fz_blur_v<6>(P, k, mid, cur, nxt, P.taps2[k], lo, n, FZ_MAXHALO, x0, y0);
-      break;
-    case 8:
-      fz_blur_v<8>(P, k, mid, cur, nxt, P.taps2[k], lo, n, FZ_MAXHALO, x0, y0);
-      break;
-    case 10:
-      fz_blur_v<10>(P, k, mid, cur, nxt, P.taps2[k], lo, n, FZ_MAXHALO, x0, y0);
-      break;
-    default:
-      fz_blur_v<12>(P, k, mid, cur, nxt, P.taps2[k], lo, n, FZ_MAXHALO, x0, y0);
-      break;
+      float *gl = P.g0 + (size_t)k * P.layer_stride;
+      float *dl = P.d0 + (size_t)k * P.layer_stride;
+      const bool is_next = (k == P.next_k);
+#pragma unroll 1
+      for (int r = lo + R + wi; r < lo + R + n; r += FZ_THREADS / 32)
+      {
+        const int gy = y0 - halo + r;
+        const bool row_ok = (r >= halo) && (r < halo + FZ_T) && (gy < P.h);
+#pragma unroll 1
+        for (int c = lo + R + lane; c < lo + R + n; c += 32)
+        {
+          const float *q = mid + r * FZ_WB + c;
+          float acc = vks_mul(q[0], tp[0]);
+#pragma unroll 2
+          for (int i = 1; i <= R; i++)
+            acc = vks_blur_tap(acc, q[i * FZ_WB], q[-i * FZ_WB], tp[i]);
+          nxt[r * FZ_WB + c] = acc;
+          const int gx = x0 - halo + c;
+          if (row_ok && c >= halo && c < halo + FZ_T && gx < P.w)
+          {
+            const size_t o = (size_t)gy * P.pitch + gx;
+            gl[o] = acc;
+            dl[o] = vks_sub(acc, cur[r * FZ_WB + c]);
+            if (is_next && (gx & 1) && (gy & 1))
+            {
+              const int nx = gx >> 1, ny = gy >> 1;
+              if (nx < P.next_w && ny < P.next_h)
+                P.dst_next[(size_t)ny * P.next_pitch + nx] = acc;
+            }
+          }
+        }
+      }
     }
     __syncthreads();
     float *tmp = cur;
     cur = nxt;
     nxt = tmp;
+    lo += R;
   }
+}
+
+/* launch with programmatic stream serialization: the kernel may be scheduled before the previous kernel of the
+ * stream has finished; it orders itself with pdl_wait() */
+template <typename P>
+static cudaError_t launch_pdl(void (*kernel)(P), int grid, int block, size_t smem, cudaStream_t st, const P &params)
+{
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  static const bool no_pdl = [] { const char *e = getenv("VKSIFT_NO_PDL"); return e && e[0] == '1'; }();
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, params);
 }
 
 /* Groups the passes of one octave (consecutive layers, same octave, float sources) into fused launches: a group
@@ -866,7 +813,7 @@ bool fused_plan_octave(const BlurPass *passes, int n_pass, std::vector<FusedLaun
       const BlurPass &bp = passes[i];
       if (bp.radius < 1 || bp.radius > 12)
         return false;
-      const int re = ft_even(bp.radius);
+      const int re = bp.radius;
       if (halo + re > FZ_MAXHALO)
         break;
       const int k = F.n_layers;
@@ -911,8 +858,7 @@ cudaError_t launch_fused(const FusedLaunch &F, cudaStream_t st)
     attr_done[dev] = true;
   }
   const int tiles = F.tiles_x * ((F.h + FZ_T - 1) / FZ_T);
-  octave_fused_kernel<<<tiles, FZ_THREADS, FZ_SMEM, st>>>(F);
-  return cudaGetLastError();
+  return launch_pdl(octave_fused_kernel, tiles, FZ_THREADS, FZ_SMEM, st, F);
 }
 
 /* A pass goes to the fast per-layer kernel when its radius is covered and the layer is large enough for
@@ -922,7 +868,7 @@ bool blur_pass_is_fast(const BlurPass &bp)
 {
   if (bp.radius < 1 || bp.radius > 12)
     return false;
-  return ((bp.w + FT_W - 1) / FT_W) * ((bp.h + FT_H - 1) / FT_H) >= 148;
+  return ((bp.w + FT_W - 1) / FT_W) * ((bp.h + FT_H - 1) / FT_H) >= 64;
 }
 
 bool blur_step_tiles(BlurStep *step)
@@ -974,8 +920,7 @@ static cudaError_t launch_fast_rk(const BlurPassFast &F, int n_tiles, cudaStream
       return e;
     attr_done[dev] = true;
   }
-  blur_pass_fast_kernel<R, KIND><<<n_tiles, FT_THREADS, ft_smem_bytes(R), st>>>(F);
-  return cudaGetLastError();
+  return launch_pdl(blur_pass_fast_kernel<R, KIND>, n_tiles, FT_THREADS, ft_smem_bytes(R), st, F);
 }
 
 template <int R>

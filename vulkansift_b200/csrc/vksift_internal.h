@@ -105,7 +105,8 @@ enum BlurSrcKind
 
 struct BlurPass
 {
-  const void *src; /* float layer or u8 image */
+  const void *src; /* float layer, or (u8 kinds) the address of a device slot holding the image pointer: the launch
+                      sequence is captured in a CUDA graph once and replayed for every image */
   float *dst_g;    /* Gaussian layer written */
   float *dst_d;    /* DoG layer (dst_g - src) or NULL */
   float *dst_next; /* next octave layer 0 (NEAREST blit of this layer) or NULL */
