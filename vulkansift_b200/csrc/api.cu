@@ -109,6 +109,8 @@ struct vksift_Instance_T
     std::vector<FusedLaunch> rest;   /* remaining layers, second side stream */
   };
   std::vector<FusedOct> fused_oct;             /* small octaves [k,n): fused kernel, one or two launches per octave */
+  MegaPlan *mega = nullptr;                    /* whole scale space as one persistent launch, when the configuration allows it */
+  bool use_mega = false;
   cudaStream_t side_stream = nullptr, side2_stream = nullptr;
   cudaEvent_t ev_chain[VKS_MAX_OCT] = {nullptr}; /* chain launches of octave o enqueued on the side stream */
   cudaEvent_t ev_join2 = nullptr;
@@ -131,7 +133,7 @@ struct vksift_Instance_T
     uint64_t launches = 0;
   };
   std::vector<DetectGraph> graphs;
-  bool use_graph = true;
+  bool use_graph = false;
 
   std::vector<FeatureBuffer> buffers;
   Candidate *cand = nullptr;
@@ -347,9 +349,30 @@ bool build_blur_plan(vksift_Instance inst)
    * (all passes that are ready share a launch) in a side stream and join before the extrema scan. */
   inst->fast_oct.clear();
   inst->steps_side.clear();
+  mega_plan_destroy(inst->mega);
+  inst->mega = nullptr;
   if (p.n_oct == 0)
     return true;
   bool ok = true;
+  if (inst->use_mega)
+  {
+    /* preferred: one persistent launch for the whole scale space */
+    std::vector<std::vector<BlurPass>> all;
+    bool prepared = true;
+    for (int o = 0; o < (int)p.n_oct && prepared; o++)
+    {
+      std::vector<BlurPass> passes;
+      for (int s = (o == 0 ? 0 : 1); s < ns + 3 && prepared; s++)
+      {
+        BlurPass bp = make_pass((uint32_t)o, s);
+        prepared = bp.radius <= 12 && blur_pass_prepare_fast(&bp);
+        passes.push_back(bp);
+      }
+      all.push_back(passes);
+    }
+    if (prepared && mega_plan_build(all, ns, &inst->mega))
+      return true;
+  }
   int k = 0;
   for (; k < (int)p.n_oct; k++)
   {
@@ -568,6 +591,7 @@ void destroy_instance(vksift_Instance inst)
   cudaFree(inst->feat_src);
   cudaFree(inst->d_aos);
   cudaFree(inst->d_matches);
+  mega_plan_destroy(inst->mega);
   match_workspace_destroy(inst->match_ws);
   extrema_plan_destroy(inst->extrema_plan);
   for (int i = 0; i < EV_COUNT; i++)
@@ -639,8 +663,14 @@ bool create_resources(vksift_Instance inst)
   CU_TRY(cudaHostAlloc(&inst->h_src_slot, sizeof(void *), cudaHostAllocDefault));
   CU_TRY(cudaMalloc(&inst->d_src_slot, sizeof(void *)));
   {
-    const char *ng = getenv("VKSIFT_NO_GRAPH");
-    inst->use_graph = !(ng && ng[0] == '1');
+    /* Two alternative schedules of the same kernels, off by default because they measured slower on B200:
+     * VKSIFT_MEGA=1: the whole scale space as one persistent dataflow launch instead of per-layer launches.
+     * VKSIFT_GRAPH=1: replay of the detection as a CUDA graph (per-layer path only: the persistent kernel takes a
+     * new epoch per launch). */
+    const char *g = getenv("VKSIFT_GRAPH");
+    const char *m = getenv("VKSIFT_MEGA");
+    inst->use_mega = (m && m[0] == '1');
+    inst->use_graph = (g && g[0] == '1') && !inst->use_mega;
   }
 
   const size_t maxf = c.max_nb_sift_per_buffer;
@@ -745,6 +775,12 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   CU_TRY(cudaMemsetAsync(fb.cnt, 0, sizeof(DetectCounters), st));
   const int ns = inst->cfg.nb_scales_per_octave;
   const int n_fast = (int)inst->fast_oct.size();
+  if (inst->mega)
+  {
+    TraceScope ts(inst, st, "persistent pyramid", 0, 0);
+    CU_TRY(launch_mega(inst->mega, st));
+    inst->launches++;
+  }
   for (int o = 0; o < n_fast; o++)
   {
     cudaStream_t so = (o == 0) ? st : inst->oct_stream[o];

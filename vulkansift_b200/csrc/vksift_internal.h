@@ -179,6 +179,11 @@ cudaError_t launch_blur_step(const BlurStep &step, cudaStream_t st);
 /* groups consecutive layer passes of one octave into fused launches; false when a pass cannot be fused */
 bool fused_plan_octave(const BlurPass *passes, int n_pass, std::vector<FusedLaunch> *out);
 cudaError_t launch_fused(const FusedLaunch &F, cudaStream_t st);
+/* the whole scale space as one persistent launch (pyramid.cu); build returns false for configurations it is not compiled for */
+struct MegaPlan;
+bool mega_plan_build(const std::vector<std::vector<BlurPass>> &oct_passes, int ns, MegaPlan **io);
+void mega_plan_destroy(MegaPlan *pl);
+cudaError_t launch_mega(MegaPlan *pl, cudaStream_t st);
 struct ExtremaPlan; /* TMA tensor maps over the DoG layers of the current pyramid */
 cudaError_t extrema_plan_build(const DetectParams &P, ExtremaPlan **plan_io);
 void extrema_plan_destroy(ExtremaPlan *pl);
