@@ -70,7 +70,8 @@ struct Pyramid
 enum
 {
   EV_D0 = 0, /* detect start */
-  EV_D1,     /* after pyramid */
+  EV_D1,     /* after pyramid (of the large octaves when the small ones finish on the side stream) */
+  EV_D1B,    /* after the pyramid of the small octaves (side stream) */
   EV_D2,     /* after extrema+order */
   EV_D3,     /* after orientation */
   EV_D4,     /* after descriptors */
@@ -111,6 +112,7 @@ struct vksift_Instance_T
   std::vector<FusedOct> fused_oct;             /* small octaves [k,n): fused kernel, one or two launches per octave */
   MegaPlan *mega = nullptr;                    /* whole scale space as one persistent launch, when the configuration allows it */
   bool use_mega = false;
+  bool no_split = false; /* VKSIFT_NO_SPLIT=1: extrema/orientation of all octaves after the whole pyramid (debug) */
   cudaStream_t side_stream = nullptr, side2_stream = nullptr;
   cudaEvent_t ev_chain[VKS_MAX_OCT] = {nullptr}; /* chain launches of octave o enqueued on the side stream */
   cudaEvent_t ev_join2 = nullptr;
@@ -163,6 +165,7 @@ struct vksift_Instance_T
   size_t trace_used = 0;
   cudaEvent_t ev[EV_COUNT] = {nullptr};
   bool ev_detect_valid = false, ev_match_valid = false;
+  bool ev_d1b_valid = false;
   uint64_t launches = 0;
 };
 
@@ -513,6 +516,8 @@ void fill_detect_params(vksift_Instance inst, const FeatureBuffer &fb, DetectPar
     off += fb.cap[o];
   }
   P->n_oct = (int)p.n_oct;
+  P->ob = 0;
+  P->oe = (int)p.n_oct;
   P->ns = c.nb_scales_per_octave;
   P->upsample = c.use_input_upsampling ? 1 : 0;
   P->sigma0 = c.seed_scale_sigma;
@@ -670,6 +675,8 @@ bool create_resources(vksift_Instance inst)
     const char *g = getenv("VKSIFT_GRAPH");
     const char *m = getenv("VKSIFT_MEGA");
     inst->use_mega = (m && m[0] == '1');
+    const char *nsp = getenv("VKSIFT_NO_SPLIT");
+    inst->no_split = (nsp && nsp[0] == '1');
     inst->use_graph = (g && g[0] == '1') && !inst->use_mega;
   }
 
@@ -800,6 +807,9 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
       CU_TRY(cudaEventRecord(inst->ev_oct_done[o], so));
   }
   (void)ns;
+  /* large octaves on per-layer launches, small ones fused on the side streams: the stages after the pyramid are split too */
+  const bool split = (n_fast > 0) && !inst->fused_oct.empty() && n_fast < P.n_oct && !inst->no_split;
+  inst->ev_d1b_valid = split && prof;
   if (!inst->fused_oct.empty())
   {
     cudaStream_t ss = (n_fast == 0) ? st : inst->side_stream;
@@ -833,15 +843,42 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
         used2 = true;
       }
     }
-    if (n_fast > 0)
+    if (split)
     {
+      /* The octaves after the first are a latency chain that leaves the GPU nearly idle at its end: their extrema
+       * scan, ordering and orientation pass follow on the side stream while the main stream already does the same
+       * for octave 0, whose layers are complete much earlier and which holds ~3/4 of the pixels (the per-octave
+       * sections of these stages are independent); both meet again before the feature assembly. */
+      if (used2)
+      {
+        CU_TRY(cudaEventRecord(inst->ev_join2, inst->side2_stream));
+        CU_TRY(cudaStreamWaitEvent(ss, inst->ev_join2, 0));
+      }
+      for (int o = 1; o < n_fast; o++)
+        CU_TRY(cudaStreamWaitEvent(ss, inst->ev_oct_done[o], 0));
+      if (prof)
+        CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D1B], ss, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+      DetectParams PB = P;
+      PB.ob = 1;
+      PB.oe = P.n_oct;
+      CU_TRY(launch_extrema(PB, inst->extrema_plan, inst->raw, inst->cand, fb.cnt, ss));
+      CU_TRY(launch_order_primaries(PB, inst->cand, fb.cnt, inst->prim, ss));
+      CU_TRY(launch_orientation(PB, fb.cnt, inst->prim, inst->ori, inst->n_ori, ss));
+      inst->launches += 4;
       CU_TRY(cudaEventRecord(inst->ev_join, ss));
-      CU_TRY(cudaStreamWaitEvent(st, inst->ev_join, 0));
     }
-    if (used2)
+    else
     {
-      CU_TRY(cudaEventRecord(inst->ev_join2, inst->side2_stream));
-      CU_TRY(cudaStreamWaitEvent(st, inst->ev_join2, 0));
+      if (n_fast > 0)
+      {
+        CU_TRY(cudaEventRecord(inst->ev_join, ss));
+        CU_TRY(cudaStreamWaitEvent(st, inst->ev_join, 0));
+      }
+      if (used2)
+      {
+        CU_TRY(cudaEventRecord(inst->ev_join2, inst->side2_stream));
+        CU_TRY(cudaStreamWaitEvent(st, inst->ev_join2, 0));
+      }
     }
   }
   if (!inst->steps_side.empty())
@@ -860,8 +897,9 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
       CU_TRY(cudaStreamWaitEvent(st, inst->ev_join, 0));
     }
   }
-  for (int o = 1; o < n_fast; o++)
-    CU_TRY(cudaStreamWaitEvent(st, inst->ev_oct_done[o], 0));
+  if (!split)
+    for (int o = 1; o < n_fast; o++)
+      CU_TRY(cudaStreamWaitEvent(st, inst->ev_oct_done[o], 0));
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D1], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   {
@@ -869,14 +907,19 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
     if (pe != cudaSuccess)
       LOGE(TAG, "pending CUDA error before the extrema scan: %s", cudaGetErrorName(pe));
   }
-  CU_TRY(launch_extrema(P, inst->extrema_plan, inst->raw, inst->cand, fb.cnt, st));
+  DetectParams PA = P;
+  if (split)
+    PA.oe = 1; /* octave 0 (its layers are complete on this stream); the other octaves follow on the side stream */
+  CU_TRY(launch_extrema(PA, inst->extrema_plan, inst->raw, inst->cand, fb.cnt, st));
   inst->launches += 2;
-  CU_TRY(launch_order_primaries(P, inst->cand, fb.cnt, inst->prim, st));
+  CU_TRY(launch_order_primaries(PA, inst->cand, fb.cnt, inst->prim, st));
   inst->launches++;
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D2], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
-  CU_TRY(launch_orientation(P, fb.cnt, inst->prim, inst->ori, inst->n_ori, st));
+  CU_TRY(launch_orientation(PA, fb.cnt, inst->prim, inst->ori, inst->n_ori, st));
   inst->launches++;
+  if (split)
+    CU_TRY(cudaStreamWaitEvent(st, inst->ev_join, 0)); /* the small octaves' keypoints are oriented too */
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D3], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   CU_TRY(launch_assemble(P, fb.cnt, inst->n_ori, inst->feat_src, fb.host_counts_dev, st));
@@ -1578,6 +1621,13 @@ extern "C"
       cudaEventSynchronize(inst->ev[EV_D4]);
       trace_dump(inst);
       cudaEventElapsedTime(&t[0], inst->ev[EV_D0], inst->ev[EV_D1]);
+      if (inst->ev_d1b_valid)
+      {
+        /* scale space = large octaves (main stream) and small octaves (side stream), whichever finishes last */
+        float tb = 0.f;
+        if (cudaEventElapsedTime(&tb, inst->ev[EV_D0], inst->ev[EV_D1B]) == cudaSuccess && tb > t[0])
+          t[0] = tb;
+      }
       cudaEventElapsedTime(&t[1], inst->ev[EV_D1], inst->ev[EV_D2]);
       cudaEventElapsedTime(&t[2], inst->ev[EV_D2], inst->ev[EV_D3]);
       cudaEventElapsedTime(&t[3], inst->ev[EV_D3], inst->ev[EV_D4]);

@@ -44,12 +44,12 @@ __global__ void __launch_bounds__(ORI_THREADS) orientation_kernel(const __grid_c
   const int tid = threadIdx.x, lane = tid & 31;
 
   uint32_t total = 0;
-  for (int o = 0; o < P.n_oct; o++)
+  for (int o = P.ob; o < P.oe; o++)
     total += cnt->n_prim[o];
   for (uint32_t item = blockIdx.x; item < total; item += gridDim.x)
   {
     /* item -> (octave, index in section) */
-    int o = 0;
+    int o = P.ob;
     uint32_t idx = item;
     while (idx >= cnt->n_prim[o])
     {

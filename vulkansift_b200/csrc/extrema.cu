@@ -141,8 +141,8 @@ __device__ __forceinline__ bool extrema_tile_coords(const DetectParams &P, int t
   return false;
 }
 
-__global__ void __launch_bounds__(256) extrema_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ ExtremaMaps maps, int n_tiles,
-                                                      unsigned long long *__restrict__ raw, DetectCounters *__restrict__ cnt)
+__global__ void __launch_bounds__(256) extrema_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ ExtremaMaps maps, int t_begin,
+                                                      int n_tiles, unsigned long long *__restrict__ raw, DetectCounters *__restrict__ cnt)
 {
   extern __shared__ __align__(128) float ex_smem[];
   __shared__ __align__(8) uint64_t s_bar[2];
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) extrema_kernel(const __grid_constant__ De
     tma_mbar_init(bar0 + 8, 1);
     tma_mbar_fence_init();
     int o, x0, y0;
-    if (extrema_tile_coords(P, (int)blockIdx.x, &o, &x0, &y0))
+    if (t_begin + (int)blockIdx.x < n_tiles && extrema_tile_coords(P, t_begin + (int)blockIdx.x, &o, &x0, &y0))
     {
       tma_mbar_expect_tx(bar0, tile_bytes);
       for (int l = 0; l < nl; l++) /* one request per layer: the TMA unit pipelines independent requests */
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) extrema_kernel(const __grid_constant__ De
   __syncthreads();
 
   int it = 0;
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it++)
+  for (int t = t_begin + (int)blockIdx.x; t < n_tiles; t += gridDim.x, it++) /* tiles [t_begin, n_tiles) = the octaves [P.ob, P.oe) */
   {
     const int cur = it & 1;
     int o, x0, y0;
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) extrema_kernel(const __grid_constant__ De
 __global__ void __launch_bounds__(128) refine_kernel(const __grid_constant__ DetectParams P, const unsigned long long *__restrict__ raw,
                                                      Candidate *__restrict__ cand, DetectCounters *__restrict__ cnt)
 {
-  const int o = blockIdx.y;
+  const int o = P.ob + (int)blockIdx.y;
   const uint32_t n = min(cnt->n_raw[o], P.cand_cap);
   const OctaveView &ov = P.oct[o];
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -317,8 +317,16 @@ void extrema_plan_destroy(ExtremaPlan *pl) { delete pl; }
 cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, unsigned long long *raw, Candidate *cand, DetectCounters *cnt,
                            cudaStream_t st)
 {
-  if (!pl || !pl->valid || pl->n_tiles == 0)
+  if (!pl || !pl->valid || pl->n_tiles == 0 || P.oe <= P.ob)
     return cudaSuccess;
+  int t_begin = 0, t_end = 0;
+  for (int o = 0; o < P.oe; o++)
+  {
+    const int n = ((P.oct[o].w + EX_TW - 1) / EX_TW) * ((P.oct[o].h + EX_TH - 1) / EX_TH);
+    if (o < P.ob)
+      t_begin += n;
+    t_end += n;
+  }
   const size_t smem = 2 * sizeof(float) * (size_t)((((P.ns + 2) * EX_SH * EX_SW) + 31) & ~31);
   if (smem > 220 * 1024)
     return cudaErrorInvalidConfiguration; /* nb_scales_per_octave too large for the double-buffered tile */
@@ -335,13 +343,13 @@ cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, unsigne
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int per_sm = (int)((220 * 1024) / smem) < 1 ? 1 : (int)((220 * 1024) / smem);
   int grid = sms * (per_sm > 2 ? 2 : per_sm);
-  if (grid > pl->n_tiles)
-    grid = pl->n_tiles;
-  extrema_kernel<<<grid, 256, smem, st>>>(P, pl->maps, pl->n_tiles, raw, cnt);
+  if (grid > t_end - t_begin)
+    grid = t_end - t_begin;
+  extrema_kernel<<<grid, 256, smem, st>>>(P, pl->maps, t_begin, t_end, raw, cnt);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
-  refine_kernel<<<dim3(32, P.n_oct, 1), 128, 0, st>>>(P, raw, cand, cnt);
+  refine_kernel<<<dim3(32, P.oe - P.ob, 1), 128, 0, st>>>(P, raw, cand, cnt);
   return cudaGetLastError();
 }
 
@@ -353,7 +361,7 @@ __global__ void __launch_bounds__(ORD_THREADS) order_primaries_kernel(const __gr
                                                                       DetectCounters *__restrict__ cnt, FeatHead *__restrict__ prim)
 {
   __shared__ unsigned long long s_keys[ORD_THREADS];
-  const int o = blockIdx.y;
+  const int o = P.ob + (int)blockIdx.y;
   const uint32_t n_all = cnt->n_cand[o];
   const uint32_t n = min(n_all, P.cand_cap);
   if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -380,14 +388,14 @@ __global__ void __launch_bounds__(ORD_THREADS) order_primaries_kernel(const __gr
 
 cudaError_t launch_order_primaries(const DetectParams &P, const Candidate *cand, DetectCounters *cnt, FeatHead *prim, cudaStream_t st)
 {
-  if (P.n_oct == 0)
+  if (P.oe <= P.ob)
     return cudaSuccess;
   /* worst case grid; CTAs beyond the candidate count exit immediately */
   uint32_t max_cap = 0;
   for (int o = 0; o < P.n_oct; o++)
     max_cap = P.cap[o] > max_cap ? P.cap[o] : max_cap;
   uint32_t bx = (P.cand_cap + ORD_THREADS - 1) / ORD_THREADS;
-  dim3 grid(bx, P.n_oct, 1);
+  dim3 grid(bx, P.oe - P.ob, 1);
   order_primaries_kernel<<<grid, ORD_THREADS, 0, st>>>(P, cand, cnt, prim);
   return cudaGetLastError();
 }

@@ -73,6 +73,7 @@ struct DetectParams
   uint32_t cap[VKS_MAX_OCT];     /* section capacity (updateBufferInfo) */
   uint32_t sec_off[VKS_MAX_OCT]; /* prefix sum of cap */
   int n_oct, ns, upsample;
+  int ob, oe; /* octave range [ob, oe) a launch of the extrema / ordering / orientation kernels works on */
   float sigma0, thr, prefilter, edge_limit;
   uint32_t max_ori;    /* 0 = unlimited */
   uint32_t ori_stride; /* orientation slots per primary */
