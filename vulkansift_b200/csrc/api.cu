@@ -368,7 +368,7 @@ bool build_blur_plan(vksift_Instance inst)
       for (int s = (o == 0 ? 0 : 1); s < ns + 3 && prepared; s++)
       {
         BlurPass bp = make_pass((uint32_t)o, s);
-        prepared = bp.radius <= 12 && blur_pass_prepare_fast(&bp);
+        prepared = bp.radius <= 12 && blur_pass_prepare_fast(&bp, true);
         passes.push_back(bp);
       }
       all.push_back(passes);

@@ -268,10 +268,16 @@ enum
 __host__ __device__ constexpr int ft_rx(int R) { return (R + 3) & ~3; } /* x halo rounded to float4 */
 /* source tile row stride (= TMA box width), floats: covers 64 + 2 halos, stride/4 odd -> LDS.128 down a column is conflict free */
 __host__ __device__ constexpr int ft_s(int R) { return (((FT_W + 2 * ft_rx(R)) / 4) | 1) * 4; }
-__host__ __device__ constexpr int ft_in_h(int R) { return FT_H + 2 * R; }
+__host__ __device__ constexpr int ft_in_h(int R, int TH = FT_H) { return TH + 2 * R; }
 #define FT_BOX_H 8 /* rows per TMA request: 8 rows of a stride that is a multiple of 4 floats keep every destination 128-byte aligned */
-__host__ __device__ constexpr int ft_n_box(int R) { return (ft_in_h(R) + FT_BOX_H - 1) / FT_BOX_H; }
-__host__ __device__ constexpr int ft_in_ha(int R) { return ft_n_box(R) * FT_BOX_H; } /* rows allocated for the source tile */
+__host__ __device__ constexpr int ft_n_box(int R, int TH = FT_H) { return (ft_in_h(R, TH) + FT_BOX_H - 1) / FT_BOX_H; }
+__host__ __device__ constexpr int ft_in_ha(int R, int TH = FT_H) { return ft_n_box(R, TH) * FT_BOX_H; } /* rows allocated for the source tile */
+/* Tile height of the per-layer launches: the passes with small radii wait for their loads more than they compute, so
+ * they take 96-row tiles, which fit three CTAs per SM instead of two (the extra halo rows cost little at these radii) */
+__host__ __device__ constexpr int ft_tile_h(int R) { return R <= 4 ? 64 : (R <= 8 ? 96 : 128); }
+__host__ __device__ constexpr int ft_ctas_per_sm(int R) { return R <= 4 ? 4 : (R <= 8 ? 3 : 2); }
+__host__ __device__ constexpr int ft_bar_off(int R, int TH) { return ft_in_ha(R, TH) * ft_s(R) + ft_in_h(R, TH) * FT_MS; }
+__host__ __device__ constexpr int ft_smem_bytes(int R, int TH) { return 4 * ft_bar_off(R, TH) + 8 * FT_NB + 1024; }
 /* source tile, horizontal-pass result, TMA barriers, UNORM table of the seed pass */
 /* one shared-memory layout for every radius (a persistent CTA runs tiles of several layers): source tile and
  * horizontal-pass result sized by R inside the first FT_BAR_OFF floats, then the TMA barriers and the UNORM table */
@@ -290,23 +296,25 @@ struct BlurPassFast
 /* One 64x128 tile of one layer.  The TMA barriers at the end of the shared memory block are initialised by the
  * caller; `parity` is the phase they complete next (a persistent caller flips it for every float-source tile).
  * `taps2` must point into the kernel parameters at a compile-time offset (constant operands). */
-template <int R, int KIND>
+template <int R, int KIND, int TH, int BAR_OFF>
 __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *tmap, const float2 *__restrict__ taps2, float *ft_smem, int x0, int y0,
                                           uint32_t parity, bool pdl)
 {
+  constexpr int VR = TH / (FT_THREADS / 32); /* output rows per warp in the vertical pass */
+  static_assert(VR % 4 == 0, "vertical pass works in blocks of 4 rows");
   constexpr int RX = ft_rx(R);
   constexpr int S = ft_s(R);
-  constexpr int IN_H = ft_in_h(R);
-  constexpr int IN_HA = ft_in_ha(R);
-  constexpr int NBOX = ft_n_box(R); /* TMA requests per tile; request j signals barrier j*FT_NB/NBOX */
+  constexpr int IN_H = ft_in_h(R, TH);
+  constexpr int IN_HA = ft_in_ha(R, TH);
+  constexpr int NBOX = ft_n_box(R, TH); /* TMA requests per tile; request j signals barrier j*FT_NB/NBOX */
   float *s_in = ft_smem;
   float *s_mid = ft_smem + IN_HA * S;
-  const uint32_t bar0 = tma_smem_u32(ft_smem + FT_BAR_OFF);
+  const uint32_t bar0 = tma_smem_u32(ft_smem + BAR_OFF);
   const int tid = threadIdx.x;
   const int wi = tid >> 5, lane = tid & 31;
 
   /* rows of this tile that can influence a pixel inside the image */
-  const int rows_valid = min(FT_H, p.h - y0); /* output rows */
+  const int rows_valid = min(TH, p.h - y0); /* output rows */
   const int rows_in = rows_valid + 2 * R;     /* source rows the vertical pass will read */
   int bands_seen = FT_NB;                      /* TMA bands this thread has already waited for */
 
@@ -379,7 +387,7 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
      * source pixel, MIRRORED_REPEAT / clamp-to-edge resolved here), then the LINEAR 2x blit (or the 1:1
      * copy) out of shared memory.  Destination cell (m, c) <-> image pixel (x0-RX+c, y0-R+m). */
     const bool up = (p.src_kind == BLUR_SRC_U8_UP2);
-    const bool once = (x0 - RX >= -p.w) && (x0 - RX + S <= 2 * p.w) && (y0 - R >= -p.h) && (y0 + FT_H + R <= 2 * p.h);
+    const bool once = (x0 - RX >= -p.w) && (x0 - RX + S <= 2 * p.w) && (y0 - R >= -p.h) && (y0 + TH + R <= 2 * p.h);
     const uint8_t *__restrict__ img = *(const uint8_t *const *)p.src; /* u8 sources are reached through a pointer slot (see BlurPass) */
     const int n_el = S * rows_in;
     /* mirrored destination coordinates stay inside [lo, hi] of the image */
@@ -394,7 +402,7 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
     if (sw * sh <= IN_H * FT_MS && once)
     {
       /* UNORM conversion through a 256-entry table (one IEEE division per CTA thread instead of one per pixel) */
-      float *lut = ft_smem + FT_BAR_OFF + 2 * FT_NB;
+      float *lut = ft_smem + BAR_OFF + 2 * FT_NB;
       lut[tid] = vks_unorm8((uint8_t)tid);
       __syncthreads();
       for (int i = tid; i < sw * sh; i += FT_THREADS)
@@ -553,8 +561,8 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
   __syncthreads();
 
   /* ---- stage 3: vertical pass, unit = (column pair, 16 rows), lanes along column pairs ---- */
-  const int ry = wi * FT_VR; /* first output row of this warp inside the tile */
-  const int nrows = min(FT_VR, rows_valid - ry);
+  const int ry = wi * VR; /* first output row of this warp inside the tile */
+  const int nrows = min(VR, rows_valid - ry);
   const int yb = y0 + ry; /* even */
   if (nrows <= 0)
   {
@@ -572,12 +580,12 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
     uint32_t off = ((uint32_t)yb * (uint32_t)p.dst_pitch + (uint32_t)x) * 4u;
     uint32_t noff = ((uint32_t)(yb >> 1) * (uint32_t)p.next_pitch + (uint32_t)(x >> 1)) * 4u;
     const uint32_t pitch4 = (uint32_t)p.dst_pitch * 4u, npitch4 = (uint32_t)p.next_pitch * 4u;
-    pk2 wv[FT_VR + 2 * R];
+    pk2 wv[VR + 2 * R];
 #pragma unroll
     for (int j = 0; j < 2 * R; j++)
       wv[j] = *(const pk2 *)(mcol + j * FT_MS);
 #pragma unroll
-    for (int qb = 0; qb < FT_VR; qb += 4)
+    for (int qb = 0; qb < VR; qb += 4)
     {
 #pragma unroll
       for (int j = 0; j < 4; j++)
@@ -643,13 +651,15 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
  * taps are constant operands of the FFMA2s.  Passes that are independent (different octaves) run
  * concurrently from different streams; the block scheduler fills the tail of one with the head of another. */
 template <int R, int KIND>
-__global__ void __launch_bounds__(FT_THREADS, 2) blur_pass_fast_kernel(const __grid_constant__ BlurPassFast P)
+__global__ void __launch_bounds__(FT_THREADS, ft_ctas_per_sm(R)) blur_pass_fast_kernel(const __grid_constant__ BlurPassFast P)
 {
   extern __shared__ __align__(128) float ft_smem[];
+  constexpr int TH = ft_tile_h(R);
+  constexpr int BAR_OFF = ft_bar_off(R, TH);
   pdl_launch_dependents();
   if (threadIdx.x == 0)
   {
-    const uint32_t bar0 = tma_smem_u32(ft_smem + FT_BAR_OFF);
+    const uint32_t bar0 = tma_smem_u32(ft_smem + BAR_OFF);
 #pragma unroll
     for (int b = 0; b < FT_NB; b++)
       tma_mbar_init(bar0 + 8 * b, 1);
@@ -658,8 +668,8 @@ __global__ void __launch_bounds__(FT_THREADS, 2) blur_pass_fast_kernel(const __g
   __syncthreads(); /* barriers initialised before anybody polls them */
   const int t = (int)blockIdx.x;
   const int x0 = (t % P.p.tiles_x) * FT_W;
-  const int y0 = (t / P.p.tiles_x) * FT_H;
-  blur_tile<R, KIND>(P.p, &P.p.tmap, P.taps2, ft_smem, x0, y0, 0u, true);
+  const int y0 = (t / P.p.tiles_x) * TH;
+  blur_tile<R, KIND, TH, BAR_OFF>(P.p, &P.p.tmap, P.taps2, ft_smem, x0, y0, 0u, true);
 }
 
 /* --------------------------------------------------------------------------
@@ -831,27 +841,27 @@ __global__ void __launch_bounds__(FT_THREADS, 2) pyramid_mega_kernel(const __gri
     {
     case 0:
       if (P.seed_radius == 4)
-        blur_tile<4, FT_KIND_SEED>(p, tmap, P.taps2[0], ft_smem, x0, y0, parity, false);
+        blur_tile<4, FT_KIND_SEED, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[0], ft_smem, x0, y0, parity, false);
       else
-        blur_tile<6, FT_KIND_SEED>(p, tmap, P.taps2[0], ft_smem, x0, y0, parity, false);
+        blur_tile<6, FT_KIND_SEED, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[0], ft_smem, x0, y0, parity, false);
       break;
     case 1:
-      blur_tile<4, FT_KIND_LAYER>(p, tmap, P.taps2[1], ft_smem, x0, y0, parity, false);
+      blur_tile<4, FT_KIND_LAYER, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[1], ft_smem, x0, y0, parity, false);
       break;
     case 2:
-      blur_tile<6, FT_KIND_LAYER>(p, tmap, P.taps2[2], ft_smem, x0, y0, parity, false);
+      blur_tile<6, FT_KIND_LAYER, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[2], ft_smem, x0, y0, parity, false);
       break;
     case 3:
       if (p.dst_next)
-        blur_tile<8, FT_KIND_NEXT>(p, tmap, P.taps2[3], ft_smem, x0, y0, parity, false);
+        blur_tile<8, FT_KIND_NEXT, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[3], ft_smem, x0, y0, parity, false);
       else /* last octave: nothing to seed */
-        blur_tile<8, FT_KIND_LAYER>(p, tmap, P.taps2[3], ft_smem, x0, y0, parity, false);
+        blur_tile<8, FT_KIND_LAYER, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[3], ft_smem, x0, y0, parity, false);
       break;
     case 4:
-      blur_tile<10, FT_KIND_LAYER>(p, tmap, P.taps2[4], ft_smem, x0, y0, parity, false);
+      blur_tile<10, FT_KIND_LAYER, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[4], ft_smem, x0, y0, parity, false);
       break;
     default:
-      blur_tile<12, FT_KIND_LAYER>(p, tmap, P.taps2[5], ft_smem, x0, y0, parity, false);
+      blur_tile<12, FT_KIND_LAYER, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[5], ft_smem, x0, y0, parity, false);
       break;
     }
     if (s_layer.scale != 0)
@@ -1295,12 +1305,12 @@ bool blur_step_tiles(BlurStep *step)
   return true;
 }
 
-bool blur_pass_prepare_fast(BlurPass *bpp)
+bool blur_pass_prepare_fast(BlurPass *bpp, bool persistent)
 {
   BlurPass &bp = *bpp;
-  bp.tile_h = FT_H;
+  bp.tile_h = persistent ? FT_H : ft_tile_h(ft_even(bp.radius));
   bp.tiles_x = (bp.w + FT_W - 1) / FT_W;
-  bp.tiles_y = (bp.h + FT_H - 1) / FT_H;
+  bp.tiles_y = (bp.h + bp.tile_h - 1) / bp.tile_h;
   bp.tile_begin = 0;
   if (bp.src_kind == BLUR_SRC_LAYER)
   {
@@ -1323,12 +1333,13 @@ static cudaError_t launch_fast_rk(const BlurPassFast &F, int n_tiles, cudaStream
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_done[dev])
   {
-    cudaError_t e = cudaFuncSetAttribute(blur_pass_fast_kernel<R, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES);
+    cudaError_t e =
+        cudaFuncSetAttribute(blur_pass_fast_kernel<R, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes(R, ft_tile_h(R)));
     if (e != cudaSuccess)
       return e;
     attr_done[dev] = true;
   }
-  return launch_pdl(blur_pass_fast_kernel<R, KIND>, n_tiles, FT_THREADS, FT_SMEM_BYTES, st, F);
+  return launch_pdl(blur_pass_fast_kernel<R, KIND>, n_tiles, FT_THREADS, ft_smem_bytes(R, ft_tile_h(R)), st, F);
 }
 
 template <int R>

@@ -174,7 +174,7 @@ bool blur_step_tiles(BlurStep *step);
 /* true when the pass runs on the unrolled packed-fp32 kernel, false for the compact kernel */
 bool blur_pass_is_fast(const BlurPass &bp);
 /* tile geometry + TMA tensor map of a pass for the fast kernel */
-bool blur_pass_prepare_fast(BlurPass *bp);
+bool blur_pass_prepare_fast(BlurPass *bp, bool persistent = false);
 cudaError_t launch_blur_pass_fast(const BlurPass &bp, cudaStream_t st);
 cudaError_t launch_blur_step(const BlurStep &step, cudaStream_t st);
 /* groups consecutive layer passes of one octave into fused launches; false when a pass cannot be fused */
