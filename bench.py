@@ -57,6 +57,29 @@ def algorithmic_bytes_pyramid(w, h, octaves, ns):
     return w * h + 4 * sp * (ns + 3) + 4 * sp * (ns + 2)
 
 
+def dominant_kernel_roofline(trace_acc, octaves, hbm, peak_src):
+    """Roofline of the dominant kernel = the per-layer blur launches of octave 0 (blur_pass_fast_kernel<R, LAYER>, 5 of the
+    ~25 launches, ~60 % of the stage's bytes).  Algorithmic bytes per launch: the Gaussian layer and the DoG layer
+    it writes, 2 * 4 * w0 * h0; duration = CUDA event pair around the launch on the launching stream (vksiftx launch trace),
+    averaged over the octave-0 layer launches.  traffic = ncu dram read+write of the same kernel, profiles/traffic_r1.json."""
+    w0, h0 = octaves[0]
+    per_launch = 2 * 4 * w0 * h0
+    durs = [v for k, v in trace_acc.items() if k.startswith("fast o0 r") and not k.endswith("#1")]
+    if not durs:
+        return {"bound": "hbm", "kernel": "blur_pass_fast_kernel (octave 0 layer launches)", "achieved": None, "peak": hbm, "unit": "GB/s",
+                "frac": None, "traffic": None, "peak_source": peak_src}
+    us = sum(durs) / len(durs)
+    ach = per_launch / (us * 1e-6) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("blur_pass_fast_kernel_octave0_layer_bytes_per_launch")
+    return {"bound": "hbm", "kernel": "blur_pass_fast_kernel<R, LAYER>, octave 0 (3840x2160) layer launches, mean of %d" % len(durs),
+            "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "algorithmic_bytes": per_launch,
+            "launch_us": us, "peak_source": peak_src,
+            "note": "the launch also reads its 33 MB source layer (L2 or HBM); event pairs add ~1-2 us to each traced launch"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -244,24 +267,45 @@ def main():
     octaves = [inst.octave_resolution(o) for o in range(inst.nb_octaves())]
     ns = inst.config.nb_scales_per_octave
 
-    inst.set_profiling(True)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     launches0 = inst.kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_acc = {}
     n_feat = 0
     ev0.record(stream)
     for i in range(K):
+        # vksift semantics: a detection waits for the previous one of the instance, so K calls are K serial pipelines
         inst.detect_device(d_images[i % N_IMAGES].data_ptr(), w, h, i % 2)
-        for k, v in inst.stage_times_ms().items():  # waits for this step (the next detect would wait anyway)
-            stage_acc[k] = stage_acc.get(k, 0.0) + v
         n_feat += counts[i % N_IMAGES]
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = inst.kernel_launch_count() - launches0
+
+    # stage times: CUDA events of the library on its own stream, one synchronised detection at a time
+    inst.set_profiling(True)
+    stage_acc = {}
+    KP = max(3, min(K, 20))
+    for i in range(KP):
+        inst.detect_device(d_images[i % N_IMAGES].data_ptr(), w, h, i % 2)
+        for k, v in inst.stage_times_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v / KP
+    # per-launch times of the scale-space stage (event pair around every launch; traced runs are not timed runs)
+    inst.set_launch_trace(True)
+    trace_acc = {}
+    KT = 5
+    for i in range(KT + 1):
+        inst.detect_device(d_images[i % N_IMAGES].data_ptr(), w, h, i % 2)
+        tr = inst.launch_trace()
+        if i == 0:
+            continue
+        seen = {}
+        for name, t0, t1 in tr:
+            seen[name] = seen.get(name, 0) + 1
+            key = "%s #%d" % (name, seen[name]) if name.startswith("fast o0 r4") else name
+            trace_acc[key] = trace_acc.get(key, 0.0) + (t1 - t0) / KT
+    inst.set_launch_trace(False)
     inst.set_profiling(False)
 
     # ---------------- end to end through the reference API (e2e) ----------------
@@ -345,7 +389,7 @@ def main():
                     "ms_gather": 1e3 * ap[1].item(), "matched_rows": rows.item()}
 
     # ---------------- reduce over ranks ----------------
-    vals = torch.tensor([dev_ms, e2e_s, match_ms, match_kernel_ms, stage_acc.get("pyramid_dog", 0.0) / K], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([dev_ms, e2e_s, match_ms, match_kernel_ms, stage_acc.get("pyramid_dog", 0.0)], dtype=torch.float64, device="cuda")
     sums = torch.tensor([float(n_feat), float(e2e_feat)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
@@ -367,9 +411,12 @@ def main():
             "e2e": {"value": e2e_feat_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": w * h, "d2h_bytes_per_step": d2h // K,
                     "ms_per_step": 1e3 * e2e_s / K},
             "gpu_launches": launches,
-            "stage_ms": {k: v / K for k, v in stage_acc.items() if k.startswith(("pyramid", "extrema", "orient", "descr", "detect"))},
-            "roofline": {"bound": "hbm", "kernel": "pyramid+DoG stage (blur_step_kernel launches)", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                         "frac": ach / hbm, "traffic": None, "algorithmic_bytes": alg, "stage_ms": pyr_ms, "peak_source": peak_src},
+            "stage_ms": {k: v for k, v in stage_acc.items() if k.startswith(("pyramid", "extrema", "orient", "descr", "detect"))},
+            "roofline": dominant_kernel_roofline(trace_acc, octaves, hbm, peak_src),
+            "roofline_stage": {"bound": "hbm", "kernel": "whole pyramid+DoG stage (all blur launches of all octaves, CUDA events of the library)",
+                               "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "algorithmic_bytes": alg, "stage_ms": pyr_ms,
+                               "peak_source": peak_src},
+            "scale_space_launches_us": {k: round(v, 2) for k, v in trace_acc.items()},
             "match": {"metric": "2nn_matches_per_sec", "value": world * MATCH_N / (match_ms * 1e-3), "unit": "matches/s",
                       "workload": "configs[3]: 10000 x 10000 x 128-D u8, tcgen05 kind::i8 path", "ms_per_match_call": match_ms,
                       "kernel_ms": match_kernel_ms, "e2e_value": MATCH_N / match_e2e_s, "e2e_ms": 1e3 * match_e2e_s,

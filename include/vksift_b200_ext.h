@@ -66,6 +66,13 @@ extern "C"
   VKSIFT_EXPORT void vksiftx_setProfiling(vksift_Instance instance, const bool enabled);
   VKSIFT_EXPORT void vksiftx_getStageTimesMs(vksift_Instance instance, float *times_ms);
 
+  /* Launch trace of the scale-space stage of the last detection: with tracing enabled every launch of that stage is
+   * bracketed by a CUDA event pair on its stream (this costs a few microseconds per launch, so traced detections are for
+   * analysis, not for timing the pipeline).  vksiftx_getLaunchTrace waits for the detection, fills up to `capacity`
+   * entries (name: 32 chars, start/end in microseconds from the start of the detection) and returns the launch count. */
+  VKSIFT_EXPORT void vksiftx_setLaunchTrace(vksift_Instance instance, const bool enabled);
+  VKSIFT_EXPORT uint32_t vksiftx_getLaunchTrace(vksift_Instance instance, char (*names)[32], float *start_us, float *end_us, const uint32_t capacity);
+
   /* Number of kernels this library launched on the instance since creation
    * (graph nodes count as launches). */
   VKSIFT_EXPORT uint64_t vksiftx_getKernelLaunchCount(vksift_Instance instance);

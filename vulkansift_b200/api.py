@@ -99,6 +99,8 @@ def _load_library():
         "vksiftx_getMatchesDevice": (C.c_void_p, [I]),
         "vksiftx_setProfiling": (None, [I, C.c_bool]),
         "vksiftx_getStageTimesMs": (None, [I, P(C.c_float)]),
+        "vksiftx_setLaunchTrace": (None, [I, C.c_bool]),
+        "vksiftx_getLaunchTrace": (C.c_uint32, [I, C.c_void_p, P(C.c_float), P(C.c_float), C.c_uint32]),
         "vksiftx_getKernelLaunchCount": (C.c_uint64, [I]),
         "vksiftx_getEffectiveTaps": (None, [I, C.c_void_p, C.c_void_p]),
         "vksiftx_getSectionCapacities": (None, [I, u32, C.c_void_p]),
@@ -300,6 +302,17 @@ class Instance:
         t = (C.c_float * NB_STAGES)()
         lib.vksiftx_getStageTimesMs(self._h, t)
         return dict(zip(STAGE_NAMES, [float(v) for v in t]))
+
+    def set_launch_trace(self, enabled=True):
+        lib.vksiftx_setLaunchTrace(self._h, bool(enabled))
+
+    def launch_trace(self, capacity=256):
+        """[(name, start_us, end_us)] of the scale-space launches of the last (traced) detection."""
+        names = (C.c_char * 32 * capacity)()
+        t0 = (C.c_float * capacity)()
+        t1 = (C.c_float * capacity)()
+        n = int(lib.vksiftx_getLaunchTrace(self._h, C.cast(names, C.c_void_p), t0, t1, capacity))
+        return [(bytes(names[i]).split(b"\0")[0].decode(), float(t0[i]), float(t1[i])) for i in range(min(n, capacity))]
 
     def kernel_launch_count(self):
         return int(lib.vksiftx_getKernelLaunchCount(self._h))

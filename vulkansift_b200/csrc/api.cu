@@ -161,6 +161,7 @@ struct vksift_Instance_T
     cudaEvent_t e0, e1;
   };
   bool trace = false;
+  bool trace_dump_stderr = false;
   std::vector<TraceMark> trace_marks;
   size_t trace_used = 0;
   cudaEvent_t ev[EV_COUNT] = {nullptr};
@@ -745,7 +746,7 @@ struct TraceScope
 
 void trace_dump(vksift_Instance inst)
 {
-  if (!inst->trace || inst->trace_used == 0 || !inst->profiling)
+  if (!inst->trace || !inst->trace_dump_stderr || inst->trace_used == 0 || !inst->profiling)
     return;
   cudaEventSynchronize(inst->ev[EV_D4]);
   fprintf(stderr, "[trace] %-24s %9s %9s %9s\n", "launch", "start_us", "end_us", "dur_us");
@@ -1607,7 +1608,36 @@ extern "C"
   {
     inst->profiling = enabled;
     const char *t = getenv("VKSIFT_TRACE");
-    inst->trace = enabled && t && t[0] == '1';
+    if (t && t[0] == '1')
+      inst->trace = enabled;
+    inst->trace_dump_stderr = (t && t[0] == '1');
+  }
+
+  void vksiftx_setLaunchTrace(vksift_Instance inst, const bool enabled)
+  {
+    inst->trace = enabled;
+    if (enabled)
+      inst->profiling = true; /* the trace is relative to the detection's start event */
+  }
+
+  uint32_t vksiftx_getLaunchTrace(vksift_Instance inst, char (*names)[32], float *start_us, float *end_us, const uint32_t capacity)
+  {
+    DeviceGuard g(inst->device);
+    wait_pipelines(inst, true, true);
+    if (!inst->ev_detect_valid)
+      return 0;
+    cudaEventSynchronize(inst->ev[EV_D4]);
+    const uint32_t n = (uint32_t)inst->trace_used;
+    for (uint32_t i = 0; i < n && i < capacity; i++)
+    {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, inst->ev[EV_D0], inst->trace_marks[i].e0);
+      cudaEventElapsedTime(&b, inst->ev[EV_D0], inst->trace_marks[i].e1);
+      memcpy(names[i], inst->trace_marks[i].name, 32);
+      start_us[i] = a * 1e3f;
+      end_us[i] = b * 1e3f;
+    }
+    return n;
   }
 
   void vksiftx_getStageTimesMs(vksift_Instance inst, float *t)
