@@ -6,5 +6,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
 ncu --set full --clock-control none --import-source on -k regex:blur_pass_fast -s 16 -c 6 -f -o gpurun_out/blur_$tag python tools/profile_run.py 2 0 >> gpurun_out/prof_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:octave_fused -s 8 -c 2 -f -o gpurun_out/fused_$tag python tools/profile_run.py 2 0 >> gpurun_out/prof_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on -k "regex:extrema|refine|order_prim|orientation|assemble|descriptor" -s 11 -c 11 -f -o gpurun_out/features_$tag python tools/profile_run.py 2 0 >> gpurun_out/prof_$tag.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:match -s 3 -c 3 -f -o gpurun_out/match_$tag python tools/profile_run.py 1 2 >> gpurun_out/prof_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:match_ -s 2 -c 2 -f -o gpurun_out/match_$tag python tools/profile_run.py 1 2 >> gpurun_out/prof_$tag.log 2>&1
 tail -3 gpurun_out/prof_$tag.log

@@ -38,6 +38,7 @@ namespace vks
 #define MT_WARP_TMA 8
 #define MT_WARP_MMA 9
 #define MT_TMEM_COLS 256
+#define MT_GROUP 16      /* columns per group of the epilogue (minimum per group, winner group rescanned by the merge) */
 #define MT_SMEM_BYTES (1024 + MT_M * 128 + MT_STAGES * (MT_TILE_BYTES + MT_N * 4) + 512)
 
 /* ---- PTX wrappers --------------------------------------------------------- */
@@ -307,27 +308,32 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
       const uint32_t nbs = smem_u32(s_nb + st * MT_N);
       const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + buf * MT_N;
       int32_t c1 = 0x7fffffff, c2 = 0x7fffffff;
-      /* 32 columns at a time; the load of the next 32 is in flight while the current 32 are reduced */
-      auto reduce32 = [&](const int32_t(&a)[32], int c0) {
+      /* 32 columns at a time; the load of the next 32 is in flight while the current 32 are reduced.
+       * An exact running top-2 costs 2.5 min/max per accumulator and made the ALU pipe the limit of the whole kernel.
+       * Instead: only the MINIMUM of every group of MT_GROUP = 16 consecutive columns (one 3-input min per two
+       * accumulators) and the top-2 of the group minima (5 operations per 32 columns).  The smallest group minimum is the
+       * row's nearest neighbour; the second nearest is either the second smallest group minimum or sits in the winner's
+       * own group, which the merge kernel rescans (16 columns per row) -- see match_merge_kernel. */
+      auto group_min = [&](const int32_t(&a)[32], int base, int c0) -> int32_t {
+        int32_t m = 0x7fffffff;
 #pragma unroll
-        for (int q = 0; q < 8; q++)
+        for (int q = 0; q < MT_GROUP / 4; q++)
         {
-          const int4 n4 = lds_v4(nbs + (uint32_t)(c0 + q * 4) * 4u);
+          const int4 n4 = lds_v4(nbs + (uint32_t)(c0 + base + q * 4) * 4u);
           /* key_scale = -512 arrives as a kernel argument so that this stays one IMAD on the FMA pipe; a literal
-           * power of two is strength-reduced to shift+add on the ALU pipe, which the min/max ops already load */
-          const int32_t e0 = a[q * 4 + 0] * key_scale + n4.x, e1 = a[q * 4 + 1] * key_scale + n4.y;
-          const int32_t e2 = a[q * 4 + 2] * key_scale + n4.z, e3 = a[q * 4 + 3] * key_scale + n4.w;
-          {
-            const int32_t lo = min(e0, e1), hi = max(e0, e1), tt = max(c1, lo);
-            c1 = min(c1, lo);
-            c2 = min(min(c2, tt), hi);
-          }
-          {
-            const int32_t lo = min(e2, e3), hi = max(e2, e3), tt = max(c1, lo);
-            c1 = min(c1, lo);
-            c2 = min(min(c2, tt), hi);
-          }
+           * power of two is strength-reduced to shift+add on the ALU pipe, which the min ops already load */
+          const int32_t e0 = a[base + q * 4 + 0] * key_scale + n4.x, e1 = a[base + q * 4 + 1] * key_scale + n4.y;
+          const int32_t e2 = a[base + q * 4 + 2] * key_scale + n4.z, e3 = a[base + q * 4 + 3] * key_scale + n4.w;
+          m = __vimin3_s32(m, e0, e1);
+          m = __vimin3_s32(m, e2, e3);
         }
+        return m;
+      };
+      auto reduce32 = [&](const int32_t(&a)[32], int c0) {
+        const int32_t g0 = group_min(a, 0, c0), g1 = group_min(a, MT_GROUP, c0);
+        const int32_t lo = min(g0, g1), hi = max(g0, g1), tt = max(c1, lo);
+        c1 = min(c1, lo);
+        c2 = __vimin3_s32(c2, tt, hi);
       };
       {
         int32_t acc0[32], acc1[32];
@@ -388,40 +394,96 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
   }
 }
 
-/* fold the segments of each row block, undo the pos permutation, sqrt (Get2NearestNeighbors.comp:98-102) */
-__global__ void match_merge_kernel(const unsigned long long *__restrict__ partial, uint32_t n_tiles, uint32_t units_per_cta, uint32_t max_segs,
-                                   uint32_t na, vksift_Match_2NN *__restrict__ out)
+/* One warp per A row.  Fold the segments of the row block: the partial keys are minima of disjoint 16-column groups, so
+ * the smallest one is the nearest neighbour K1 (exact) and the second smallest, K2', is the best column outside K1's
+ * group.  The second nearest neighbour is min(K2', best column of K1's group other than K1): the 16 columns of that
+ * group are rescanned here with exact integer arithmetic (lane = (column, half of the 128 bytes)).  Then undo the
+ * position permutation and take the square roots (Get2NearestNeighbors.comp:98-102). */
+__global__ void __launch_bounds__(256) match_merge_kernel(const unsigned long long *__restrict__ partial, uint32_t n_tiles, uint32_t units_per_cta,
+                                                          uint32_t max_segs, uint32_t na, uint32_t nb, const uint8_t *__restrict__ da,
+                                                          const uint8_t *__restrict__ db, const uint32_t *__restrict__ norm_a,
+                                                          const uint32_t *__restrict__ norm_b, vksift_Match_2NN *__restrict__ out)
 {
-  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (row >= na)
     return;
   const uint32_t rb = row / MT_M, lrow = row - rb * MT_M;
   const uint32_t first_cta = (rb * n_tiles) / units_per_cta, last_cta = ((rb + 1) * n_tiles - 1) / units_per_cta;
-  const uint32_t n_seg = last_cta - first_cta + 1;
+  const uint32_t n_keys = (last_cta - first_cta + 1) * 2 * 2; /* segments x warpgroups x (k1, k2) */
   unsigned long long k1 = ~0ull, k2 = ~0ull;
-  for (uint32_t s = 0; s < n_seg * 2; s++)
+  for (uint32_t i = (uint32_t)lane; i < n_keys; i += 32)
   {
+    const uint32_t s = i >> 1, q = i & 1u;
     const size_t slot = (((size_t)rb * max_segs) * 2 + s) * MT_M + lrow;
-#pragma unroll
-    for (int q = 0; q < 2; q++)
+    const unsigned long long key = partial[slot * 2 + q];
+    if (key < k1)
     {
-      const unsigned long long key = partial[slot * 2 + q];
-      if (key < k1)
-      {
-        k2 = k1;
-        k1 = key;
-      }
-      else if (key < k2)
-        k2 = key;
+      k2 = k1;
+      k1 = key;
     }
+    else if (key < k2)
+      k2 = key;
   }
-  vksift_Match_2NN m;
-  m.idx_a = row;
-  m.idx_b1 = mt_pos((uint32_t)k1);
-  m.idx_b2 = mt_pos((uint32_t)k2);
-  m.dist_a_b1 = vks_sqrt((float)(uint32_t)(k1 >> 32));
-  m.dist_a_b2 = vks_sqrt((float)(uint32_t)(k2 >> 32));
-  out[row] = m;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1)
+  {
+    const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, d), o2 = __shfl_xor_sync(0xffffffffu, k2, d);
+    /* top-2 of {k1, k2, o1, o2}; keys of real columns are unique, ~0 marks "none" */
+    const unsigned long long lo = k1 < o1 ? k1 : o1, hi = k1 < o1 ? o1 : k1;
+    const unsigned long long m2 = k2 < o2 ? k2 : o2;
+    k1 = lo;
+    k2 = hi < m2 ? hi : m2;
+  }
+  /* rescan the winner's group: positions [g*16, g*16+16) <-> the same set of B rows (pos swaps rows 0 and 1 only) */
+  if (k1 != ~0ull)
+  {
+    const uint32_t pos1 = (uint32_t)k1;
+    const uint32_t b = (pos1 & ~(uint32_t)(MT_GROUP - 1)) + (uint32_t)(lane >> 1);
+    const int half = lane & 1;
+    unsigned long long cand = ~0ull;
+    uint32_t dot = 0;
+    if (b < nb)
+    {
+      const uint4 *pa = reinterpret_cast<const uint4 *>(da + (size_t)row * 128 + half * 64);
+      const uint4 *pb = reinterpret_cast<const uint4 *>(db + (size_t)b * 128 + half * 64);
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+      {
+        const uint4 va = __ldg(pa + i), vb = __ldg(pb + i);
+        dot = __dp4a(va.x, vb.x, dot);
+        dot = __dp4a(va.y, vb.y, dot);
+        dot = __dp4a(va.z, vb.z, dot);
+        dot = __dp4a(va.w, vb.w, dot);
+      }
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    if (b < nb)
+    {
+      const uint32_t d2 = norm_a[row] + (norm_b[b] >> 8) - 2u * dot;
+      const uint32_t pos = mt_pos(b);
+      if (pos != pos1)
+        cand = ((unsigned long long)d2 << 32) | pos;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, cand, d);
+      cand = o < cand ? o : cand;
+    }
+    if (cand < k2)
+      k2 = cand;
+  }
+  if (lane == 0)
+  {
+    vksift_Match_2NN m;
+    m.idx_a = row;
+    m.idx_b1 = mt_pos((uint32_t)k1);
+    m.idx_b2 = mt_pos((uint32_t)k2);
+    m.dist_a_b1 = vks_sqrt((float)(uint32_t)(k1 >> 32));
+    m.dist_a_b2 = vks_sqrt((float)(uint32_t)(k2 >> 32));
+    out[row] = m;
+  }
 }
 
 /* ---- host side ------------------------------------------------------------ */
@@ -519,7 +581,7 @@ static cudaError_t match_tc_launch(void *p, const uint8_t *da, uint32_t na, cons
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
-  match_merge_kernel<<<(na + 255) / 256, 256, 0, st>>>(tc->partial, n_tiles, units_per_cta, max_segs, na, out);
+  match_merge_kernel<<<(na * 32 + 255) / 256, 256, 0, st>>>(tc->partial, n_tiles, units_per_cta, max_segs, na, nb, da, db, norm_a, norm_b, out);
   *launch_count += 2;
   return cudaGetLastError();
 }
