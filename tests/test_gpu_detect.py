@@ -215,3 +215,55 @@ def test_c2_full_size_matches_oracle(api, oracle_mod):
     g = inst.download_dog_image(0, 2)
     assert np.array_equal(g.view(np.uint32), orc.dog(0, 2).view(np.uint32))
     inst.close()
+
+
+@pytest.mark.parametrize("env", ["VKSIFT_MEGA", "VKSIFT_GRAPH", "VKSIFT_NO_SPLIT", "VKSIFT_NO_PDL"])
+def test_alternative_schedules_are_bit_exact(api, oracle_mod, env, monkeypatch):
+    """The scale space can be scheduled four ways (per-layer launches = default, one persistent dataflow kernel, CUDA-graph
+    replay, no stage overlap / no programmatic dependent launch): same kernels, same bytes out."""
+    from vulkansift_b200.synth import blob_image
+    monkeypatch.setenv(env, "1")
+    imgs = [blob_image(640, 480, 400, seed=11), blob_image(1000, 700, 600, seed=12)]
+    for img in imgs:
+        with api.Instance() as inst:
+            orc = oracle_mod.Oracle()
+            exp = orc.detect(img)
+            for rep in range(3):  # the graph is captured on the second use of a buffer and replayed on the third
+                inst.detect(img, 0)
+                got = inst.download_features(0)
+                assert_features_equal(got, exp)
+
+
+def test_launch_trace_reports_every_scale_space_launch(api):
+    from vulkansift_b200.synth import blob_image
+    img = blob_image(640, 480, 300, seed=5)
+    with api.Instance() as inst:
+        inst.set_launch_trace(True)
+        inst.detect(img, 0)
+        tr = inst.launch_trace()
+        inst.set_launch_trace(False)
+    assert len(tr) >= 5
+    assert all(t1 >= t0 >= 0.0 for _, t0, t1 in tr)
+    assert any(name.startswith("fast o0") for name, _, _ in tr)
+
+
+def test_fp16_pyramid_precision_mode_bit_exact(api, oracle_mod):
+    """VKSIFT_PYRAMID_PRECISION_FLOAT16 (sift_memory.c:139): every Gaussian and DoG value goes through binary16 when it is
+    stored (SURVEY B-D11); layers, keypoints and descriptors must equal the oracle's fp16 mode bit for bit."""
+    from vulkansift_b200.synth import blob_image
+    for img in (blob_image(640, 480, 400, seed=21), blob_image(1920, 1080, 1200, seed=22)):
+        with api.Instance(pyramid_precision_mode=api.VKSIFT_PYRAMID_PRECISION_FLOAT16) as inst:
+            orc = oracle_mod.Oracle(use_fp16_pyramid=1)
+            exp = orc.detect(img)
+            inst.detect(img, 0)
+            got = inst.download_features(0)
+            assert len(exp) > 50
+            assert_features_equal(got, exp)
+            for o in range(inst.nb_octaves()):
+                for s in (0, 3, 5):
+                    g = inst.download_scale_space_image(o, s)
+                    e = orc.gaussian(o, s)
+                    assert np.array_equal(g.view(np.uint32), e.view(np.uint32)), (o, s)
+                d = inst.download_dog_image(o, 2)
+                e = orc.dog(o, 2)
+                assert np.array_equal(d.view(np.uint32), e.view(np.uint32)), o

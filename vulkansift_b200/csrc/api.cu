@@ -145,6 +145,7 @@ struct vksift_Instance_T
   float *ori = nullptr;
   uint32_t *n_ori = nullptr;
   uint32_t *feat_src = nullptr;
+  float *desc_m_table = nullptr; /* fixed-point scale sums of the descriptor by window radius */
   uint32_t ori_stride = 4;
 
   uint8_t *d_aos = nullptr; /* device AoS staging for feature up/download */
@@ -236,7 +237,6 @@ bool config_valid(const vksift_Config *c)
   case VKSIFT_PYRAMID_PRECISION_FLOAT32:
     break;
   case VKSIFT_PYRAMID_PRECISION_FLOAT16:
-    need(false, "Invalid configuration: VKSIFT_PYRAMID_PRECISION_FLOAT16 is not available in this build yet");
     break;
   default:
     need(false, "Invalid configuration: invalid scale-space pyramid format precision specified");
@@ -339,6 +339,7 @@ bool build_blur_plan(vksift_Instance inst)
       bp.next_w = (int)p.w[o + 1];
       bp.next_h = (int)p.h[o + 1];
     }
+    bp.fp16 = (inst->cfg.pyramid_precision_mode == VKSIFT_PYRAMID_PRECISION_FLOAT16) ? 1 : 0;
     bp.radius = (int)inst->scales.radius[s];
     memcpy(bp.taps, inst->scales.taps[s], sizeof(bp.taps));
     return bp;
@@ -595,6 +596,7 @@ void destroy_instance(vksift_Instance inst)
   cudaFree(inst->ori);
   cudaFree(inst->n_ori);
   cudaFree(inst->feat_src);
+  cudaFree(inst->desc_m_table);
   cudaFree(inst->d_aos);
   cudaFree(inst->d_matches);
   mega_plan_destroy(inst->mega);
@@ -691,6 +693,8 @@ bool create_resources(vksift_Instance inst)
   CU_TRY(cudaMalloc(&inst->ori, sizeof(float) * (maxf + 1) * inst->ori_stride));
   CU_TRY(cudaMalloc(&inst->n_ori, sizeof(uint32_t) * (maxf + 1)));
   CU_TRY(cudaMalloc(&inst->feat_src, sizeof(uint32_t) * (maxf + 1)));
+  CU_TRY(cudaMalloc(&inst->desc_m_table, sizeof(float) * VKS_DESC_M_TABLE));
+  CU_TRY(launch_descriptor_scale_table(inst->desc_m_table, inst->stream));
   CU_TRY(cudaMalloc(&inst->d_aos, sizeof(vksift_Feature) * maxf));
   CU_TRY(cudaMalloc(&inst->d_matches, sizeof(vksift_Match_2NN) * maxf));
   CU_TRY(match_workspace_create(&inst->match_ws, c.max_nb_sift_per_buffer));
@@ -924,7 +928,7 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D3], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   CU_TRY(launch_assemble(P, fb.cnt, inst->n_ori, inst->feat_src, fb.host_counts_dev, st));
-  CU_TRY(launch_descriptors(P, fb.cnt, inst->prim, inst->ori, inst->feat_src, fb.heads, fb.desc, st));
+  CU_TRY(launch_descriptors(P, fb.cnt, inst->desc_m_table, inst->prim, inst->ori, inst->feat_src, fb.heads, fb.desc, st));
   inst->launches += 2;
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D4], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));

@@ -295,8 +295,37 @@ cudaError_t launch_assemble(const DetectParams &P, DetectCounters *cnt, const ui
 /* ---- descriptor ---------------------------------------------------------- */
 #define DESC_THREADS 128
 
-__global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_constant__ DetectParams P, const DetectCounters *__restrict__ cnt,
-                                                                  const FeatHead *__restrict__ prim, const float *__restrict__ ori,
+/* M(hr) of ComputeDescriptors.comp:116-124 for hr = R/2 < VKS_DESC_M_TABLE:
+ *   for i<hr { m += e(i,i)*sqrt2; for j in (i, hr) m += e(i,j)*sqrt2*2 },  e(i,j) = exp(-0.125*(i*i+j*j))
+ * in the shader's sequential fp32 order.  The sum only depends on the window radius, so it is tabulated once per instance
+ * instead of being rebuilt (2*hr block barriers and a serial sum) for every feature. */
+__global__ void descriptor_scale_table_kernel(float *__restrict__ table)
+{
+  const int hr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (hr >= VKS_DESC_M_TABLE)
+    return;
+  const float es = -0.125f;
+  float m = 0.f;
+  for (int i = 0; i < hr; i++)
+    for (int j = i; j < hr; j++)
+    {
+      float t = vks_expf(es * (float)((i * i) + (j * j))) * VKS_SQRT2_F;
+      if (j > i)
+        t = t * 2.f;
+      m += t;
+    }
+  table[hr] = m;
+}
+
+cudaError_t launch_descriptor_scale_table(float *table, cudaStream_t st)
+{
+  descriptor_scale_table_kernel<<<1, VKS_DESC_M_TABLE, 0, st>>>(table);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_constant__ DetectParams P, DetectCounters *__restrict__ cnt,
+                                                                  const float *__restrict__ m_table, const FeatHead *__restrict__ prim,
+                                                                  const float *__restrict__ ori,
                                                                   const uint32_t *__restrict__ feat_src, FeatHead *__restrict__ out_heads,
                                                                   uint8_t *__restrict__ out_desc)
 {
@@ -304,10 +333,18 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
   __shared__ uint32_t s_acc;
   __shared__ float s_terms[DESC_THREADS];
   __shared__ float s_m;
+  __shared__ uint32_t s_g;
   const int tid = threadIdx.x;
   const uint32_t total = cnt->n_total;
-  for (uint32_t g = blockIdx.x; g < total; g += gridDim.x)
+  for (;;)
   {
+    /* features cost between 1x and 4x (window area): hand them out one at a time instead of a fixed stride */
+    if (tid == 0)
+      s_g = atomicAdd(&cnt->desc_next, 1u);
+    __syncthreads();
+    const uint32_t g = s_g;
+    if (g >= total)
+      break;
     int o = 0;
     while (o + 1 < P.n_oct && g >= cnt->out_off[o + 1])
       o++;
@@ -333,6 +370,9 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
      * terms evaluated in parallel per row i, summed in reference order by thread 0. */
     const int hr = R / 2;
     float m = 0.f;
+    if (hr < VKS_DESC_M_TABLE)
+      m = __ldg(m_table + hr);
+    else
     for (int i = 0; i < hr; i++)
     {
       for (int j0 = i; j0 < hr; j0 += DESC_THREADS)
@@ -355,10 +395,14 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
         __syncthreads();
       }
     }
-    if (tid == 0)
-      s_m = m;
-    __syncthreads();
-    m = s_m;
+    if (hr >= VKS_DESC_M_TABLE)
+    {
+      if (tid == 0)
+        s_m = m;
+      __syncthreads();
+      m = s_m;
+    }
+    __syncthreads(); /* s_desc cleared */
     const float fp = (float)(1u << (uint32_t)(16 - vks_ceil_log2(m)));
 
     const float rsx = vks_rint(kp.scale_x), rsy = vks_rint(kp.scale_y);
@@ -443,10 +487,10 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
   }
 }
 
-cudaError_t launch_descriptors(const DetectParams &P, const DetectCounters *cnt, const FeatHead *prim, const float *ori, const uint32_t *feat_src,
-                               FeatHead *out_heads, uint8_t *out_desc, cudaStream_t st)
+cudaError_t launch_descriptors(const DetectParams &P, DetectCounters *cnt, const float *m_table, const FeatHead *prim, const float *ori,
+                               const uint32_t *feat_src, FeatHead *out_heads, uint8_t *out_desc, cudaStream_t st)
 {
-  descriptor_kernel<<<148 * 8, DESC_THREADS, 0, st>>>(P, cnt, prim, ori, feat_src, out_heads, out_desc);
+  descriptor_kernel<<<148 * 8, DESC_THREADS, 0, st>>>(P, cnt, m_table, prim, ori, feat_src, out_heads, out_desc);
   return cudaGetLastError();
 }
 

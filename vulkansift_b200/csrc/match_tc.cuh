@@ -165,6 +165,9 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
   uint32_t *s_tmem = (uint32_t *)(s_bar + 2 * MT_STAGES + 2 + 2 * MT_BUFS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  /* programmatic dependent launch: the merge kernel's CTAs may be scheduled while this grid drains; they wait for its
+   * completion (griddepcontrol.wait) before they read the partial keys */
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t u0 = blockIdx.x * units_per_cta;
   const uint32_t u1 = min(total_units, u0 + units_per_cta);
   const uint32_t my_tiles = (u1 > u0) ? (u1 - u0) : 0u;
@@ -399,18 +402,41 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
  * group.  The second nearest neighbour is min(K2', best column of K1's group other than K1): the 16 columns of that
  * group are rescanned here with exact integer arithmetic (lane = (column, half of the 128 bytes)).  Then undo the
  * position permutation and take the square roots (Get2NearestNeighbors.comp:98-102). */
-__global__ void __launch_bounds__(256) match_merge_kernel(const unsigned long long *__restrict__ partial, uint32_t n_tiles, uint32_t units_per_cta,
-                                                          uint32_t max_segs, uint32_t na, uint32_t nb, const uint8_t *__restrict__ da,
-                                                          const uint8_t *__restrict__ db, const uint32_t *__restrict__ norm_a,
-                                                          const uint32_t *__restrict__ norm_b, vksift_Match_2NN *__restrict__ out)
+/* smallest 64-bit key of the warp with two 32-bit REDUX steps (high words, then low words among the lanes that tie) */
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k)
 {
-  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const uint32_t hi = (uint32_t)(k >> 32), lo = (uint32_t)k;
+  const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+  const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  return ((unsigned long long)mhi << 32) | mlo;
+}
+
+#define MG_WARPS 8
+__global__ void __launch_bounds__(32 * MG_WARPS) match_merge_kernel(const unsigned long long *__restrict__ partial, uint32_t n_tiles,
+                                                                    uint32_t units_per_cta, uint32_t max_segs, uint32_t na, uint32_t nb,
+                                                                    const uint8_t *__restrict__ da, const uint8_t *__restrict__ db,
+                                                                    const uint32_t *__restrict__ norm_a, const uint32_t *__restrict__ norm_b,
+                                                                    vksift_Match_2NN *__restrict__ out)
+{
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row = blockIdx.x * MG_WARPS + (uint32_t)warp;
   if (row >= na)
     return;
+  const int half = lane & 1;
+  /* this lane's half of the A row, for the rescan below: independent of the fold, so the loads go out first */
+  uint4 va[4];
+  {
+    const uint4 *pa = reinterpret_cast<const uint4 *>(da + (size_t)row * 128 + half * 64);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      va[i] = __ldg(pa + i);
+  }
+  const uint32_t my_na = __ldg(norm_a + row);
+  asm volatile("griddepcontrol.wait;" ::: "memory"); /* everything above only reads inputs of the match call */
   const uint32_t rb = row / MT_M, lrow = row - rb * MT_M;
   const uint32_t first_cta = (rb * n_tiles) / units_per_cta, last_cta = ((rb + 1) * n_tiles - 1) / units_per_cta;
   const uint32_t n_keys = (last_cta - first_cta + 1) * 2 * 2; /* segments x warpgroups x (k1, k2) */
+  /* every lane folds its share of the partial keys (one key per lane unless a row block has more than 8 segments) */
   unsigned long long k1 = ~0ull, k2 = ~0ull;
   for (uint32_t i = (uint32_t)lane; i < n_keys; i += 32)
   {
@@ -425,63 +451,47 @@ __global__ void __launch_bounds__(256) match_merge_kernel(const unsigned long lo
     else if (key < k2)
       k2 = key;
   }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1)
-  {
-    const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, d), o2 = __shfl_xor_sync(0xffffffffu, k2, d);
-    /* top-2 of {k1, k2, o1, o2}; keys of real columns are unique, ~0 marks "none" */
-    const unsigned long long lo = k1 < o1 ? k1 : o1, hi = k1 < o1 ? o1 : k1;
-    const unsigned long long m2 = k2 < o2 ? k2 : o2;
-    k1 = lo;
-    k2 = hi < m2 ? hi : m2;
-  }
+  /* top-2 of the warp: keys of real columns are unique, ~0 marks "none" */
+  const unsigned long long best = warp_min_u64(k1);
+  const unsigned long long mine = (k1 == best) ? k2 : k1; /* the winner's lane offers its runner-up */
+  unsigned long long second = warp_min_u64(mine);
   /* rescan the winner's group: positions [g*16, g*16+16) <-> the same set of B rows (pos swaps rows 0 and 1 only) */
-  if (k1 != ~0ull)
+  if (best != ~0ull)
   {
-    const uint32_t pos1 = (uint32_t)k1;
+    const uint32_t pos1 = (uint32_t)best;
     const uint32_t b = (pos1 & ~(uint32_t)(MT_GROUP - 1)) + (uint32_t)(lane >> 1);
-    const int half = lane & 1;
-    unsigned long long cand = ~0ull;
-    uint32_t dot = 0;
+    uint32_t dot = 0, nbk = 0;
     if (b < nb)
     {
-      const uint4 *pa = reinterpret_cast<const uint4 *>(da + (size_t)row * 128 + half * 64);
       const uint4 *pb = reinterpret_cast<const uint4 *>(db + (size_t)b * 128 + half * 64);
+      nbk = __ldg(norm_b + b);
 #pragma unroll
       for (int i = 0; i < 4; i++)
       {
-        const uint4 va = __ldg(pa + i), vb = __ldg(pb + i);
-        dot = __dp4a(va.x, vb.x, dot);
-        dot = __dp4a(va.y, vb.y, dot);
-        dot = __dp4a(va.z, vb.z, dot);
-        dot = __dp4a(va.w, vb.w, dot);
+        const uint4 vb = __ldg(pb + i);
+        dot = __dp4a(va[i].x, vb.x, dot);
+        dot = __dp4a(va[i].y, vb.y, dot);
+        dot = __dp4a(va[i].z, vb.z, dot);
+        dot = __dp4a(va[i].w, vb.w, dot);
       }
     }
     dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-    if (b < nb)
-    {
-      const uint32_t d2 = norm_a[row] + (norm_b[b] >> 8) - 2u * dot;
-      const uint32_t pos = mt_pos(b);
-      if (pos != pos1)
-        cand = ((unsigned long long)d2 << 32) | pos;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1)
-    {
-      const unsigned long long o = __shfl_xor_sync(0xffffffffu, cand, d);
-      cand = o < cand ? o : cand;
-    }
-    if (cand < k2)
-      k2 = cand;
+    unsigned long long cand = ~0ull;
+    const uint32_t pos = mt_pos(b);
+    if (b < nb && pos != pos1)
+      cand = ((unsigned long long)(my_na + (nbk >> 8) - 2u * dot) << 32) | pos;
+    cand = warp_min_u64(cand);
+    if (cand < second)
+      second = cand;
   }
   if (lane == 0)
   {
     vksift_Match_2NN m;
     m.idx_a = row;
-    m.idx_b1 = mt_pos((uint32_t)k1);
-    m.idx_b2 = mt_pos((uint32_t)k2);
-    m.dist_a_b1 = vks_sqrt((float)(uint32_t)(k1 >> 32));
-    m.dist_a_b2 = vks_sqrt((float)(uint32_t)(k2 >> 32));
+    m.idx_b1 = mt_pos((uint32_t)best);
+    m.idx_b2 = mt_pos((uint32_t)second);
+    m.dist_a_b1 = vks_sqrt((float)(uint32_t)(best >> 32));
+    m.dist_a_b2 = vks_sqrt((float)(uint32_t)(second >> 32));
     out[row] = m;
   }
 }
@@ -581,9 +591,21 @@ static cudaError_t match_tc_launch(void *p, const uint8_t *da, uint32_t na, cons
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
-  match_merge_kernel<<<(na * 32 + 255) / 256, 256, 0, st>>>(tc->partial, n_tiles, units_per_cta, max_segs, na, nb, da, db, norm_a, norm_b, out);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((na + MG_WARPS - 1) / MG_WARPS);
+    cfg.blockDim = dim3(32 * MG_WARPS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const unsigned long long *partial_c = tc->partial;
+    e = cudaLaunchKernelEx(&cfg, match_merge_kernel, partial_c, n_tiles, units_per_cta, max_segs, na, nb, da, db, norm_a, norm_b, out);
+  }
   *launch_count += 2;
-  return cudaGetLastError();
+  return e;
 }
 
 } // namespace vks

@@ -20,6 +20,8 @@
 #include "vksift_internal.h"
 #include "tma_util.cuh"
 
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -179,9 +181,14 @@ __global__ void __launch_bounds__(256) blur_step_small_kernel(const __grid_const
     float acc = vks_mul(col[0], p.taps[0]);
     for (int k = 1; k <= R; k++)
       acc = vks_blur_tap(acc, col[k * SB_W], col[-k * SB_W], p.taps[k]);
+    if (p.fp16)
+      acc = __half2float(__float2half_rn(acc));
     p.dst_g[(size_t)y * p.dst_pitch + x] = acc;
     if (p.dst_d)
-      p.dst_d[(size_t)y * p.dst_pitch + x] = vks_sub(acc, s_in[(yy + R) * in_w + xx + R]);
+    {
+      const float d = vks_sub(acc, s_in[(yy + R) * in_w + xx + R]);
+      p.dst_d[(size_t)y * p.dst_pitch + x] = p.fp16 ? __half2float(__float2half_rn(d)) : d;
+    }
     if (p.dst_next && (x & 1) && (y & 1))
     {
       const int nx = x >> 1, ny = y >> 1;
@@ -243,6 +250,15 @@ __device__ __forceinline__ pk2 pk_make(float lo, float hi)
   pk2 d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
   return d;
+}
+
+/* fp16 precision mode: a value goes through binary16 (round to nearest even) on its way to memory */
+__device__ __forceinline__ float round_half1(float v) { return __half2float(__float2half_rn(v)); }
+__device__ __forceinline__ pk2 round_half2(pk2 v)
+{
+  const __half2 h = __floats2half2_rn(pk_lo(v), pk_hi(v));
+  const float2 f = __half22float2(h);
+  return pk_make(f.x, f.y);
 }
 
 /* Programmatic dependent launch: a kernel lets the next launch of its stream be scheduled while it is still
@@ -580,6 +596,7 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
     uint32_t off = ((uint32_t)yb * (uint32_t)p.dst_pitch + (uint32_t)x) * 4u;
     uint32_t noff = ((uint32_t)(yb >> 1) * (uint32_t)p.next_pitch + (uint32_t)(x >> 1)) * 4u;
     const uint32_t pitch4 = (uint32_t)p.dst_pitch * 4u, npitch4 = (uint32_t)p.next_pitch * 4u;
+    const bool fp16 = p.fp16 != 0;
     pk2 wv[VR + 2 * R];
 #pragma unroll
     for (int j = 0; j < 2 * R; j++)
@@ -607,9 +624,16 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
         const int q = qb + j;
         if (q < nrows)
         {
+          if (fp16)
+            acc[j] = round_half2(acc[j]);
           *(pk2 *)(gbase + off) = acc[j];
           if (KIND != FT_KIND_SEED)
-            *(pk2 *)(dbase + off) = pk_sub(acc[j], *(const pk2 *)(ccol + q * S));
+          {
+            pk2 d = pk_sub(acc[j], *(const pk2 *)(ccol + q * S));
+            if (fp16)
+              d = round_half2(d);
+            *(pk2 *)(dbase + off) = d;
+          }
           if (KIND == FT_KIND_NEXT && (q & 1))
           {
             /* x even, y odd: the odd column of the pair feeds next(x>>1, y>>1) */
@@ -634,9 +658,14 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
       float acc = vks_mul(mc[0], taps2[0].x);
       for (int i = 1; i <= R; i++)
         acc = vks_blur_tap(acc, mc[i * FT_MS], mc[-i * FT_MS], taps2[i].x);
+      if (p.fp16)
+        acc = round_half1(acc);
       p.dst_g[(size_t)y * p.dst_pitch + x] = acc;
       if (KIND != FT_KIND_SEED)
-        p.dst_d[(size_t)y * p.dst_pitch + x] = vks_sub(acc, s_in[(R + ry + q) * S + RX + col]);
+      {
+        const float d = vks_sub(acc, s_in[(R + ry + q) * S + RX + col]);
+        p.dst_d[(size_t)y * p.dst_pitch + x] = p.fp16 ? round_half1(d) : d;
+      }
       if (KIND == FT_KIND_NEXT && (x & 1) && (y & 1))
       {
         const int nx = x >> 1, ny = y >> 1;
@@ -976,13 +1005,16 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) octave_fused_kernel(const __gri
 #pragma unroll 2
           for (int i = 1; i <= R; i++)
             acc = vks_blur_tap(acc, q[i * FZ_WB], q[-i * FZ_WB], tp[i]);
+          if (P.fp16)
+            acc = round_half1(acc);
           nxt[r * FZ_WB + c] = acc;
           const int gx = x0 - halo + c;
           if (row_ok && c >= halo && c < halo + FZ_T && gx < P.w)
           {
             const size_t o = (size_t)gy * P.pitch + gx;
             gl[o] = acc;
-            dl[o] = vks_sub(acc, cur[r * FZ_WB + c]);
+            const float dd = vks_sub(acc, cur[r * FZ_WB + c]);
+            dl[o] = P.fp16 ? round_half1(dd) : dd;
             if (is_next && (gx & 1) && (gy & 1))
             {
               const int nx = gx >> 1, ny = gy >> 1;
@@ -1040,6 +1072,7 @@ bool fused_plan_octave(const BlurPass *passes, int n_pass, std::vector<FusedLaun
     F.h = first.h;
     F.pitch = first.dst_pitch;
     F.next_k = -1;
+    F.fp16 = first.fp16;
     F.tiles_x = (F.w + FZ_T - 1) / FZ_T;
     int halo = 0;
     while (i < n_pass && F.n_layers < FZ_MAXL)

@@ -94,6 +94,7 @@ struct DetectCounters
   uint32_t prim_off[VKS_MAX_OCT]; /* offset of the octave's primaries in the work list */
   uint32_t n_prim_total;
   uint32_t n_total; /* packed feature count */
+  uint32_t desc_next; /* work counter of the descriptor kernel (features are handed out one at a time) */
 };
 
 /* ---- separable blur work description (pyramid.cu) ----------------------- */
@@ -116,6 +117,7 @@ struct BlurPass
   int src_w, src_h; /* u8 input size for the seed pass */
   int next_w, next_h;
   int src_kind;
+  int fp16; /* VKSIFT_PYRAMID_PRECISION_FLOAT16: every layer value is rounded through binary16 when it is stored (SURVEY B-D11) */
   int radius;
   int tiles_x, tiles_y, tile_begin; /* CTA range of this pass inside the launch */
   int tile_h;                       /* output rows per tile chosen for this pass */
@@ -140,6 +142,7 @@ struct FusedLaunch
   int layer_stride; /* floats between consecutive layers */
   int w, h, pitch;
   int n_layers;
+  int fp16;
   int radius[FZ_MAXL]; /* rounded up to even, taps zero padded */
   int next_k;          /* layer (0-based inside the launch) whose NEAREST decimation seeds the next octave, or -1 */
   float *dst_next;
@@ -194,7 +197,10 @@ cudaError_t launch_order_primaries(const DetectParams &P, const Candidate *cand,
 cudaError_t launch_orientation(const DetectParams &P, DetectCounters *cnt, const FeatHead *prim, float *ori, uint32_t *n_ori, cudaStream_t st);
 cudaError_t launch_assemble(const DetectParams &P, DetectCounters *cnt, const uint32_t *n_ori, uint32_t *feat_src, uint32_t *host_counts,
                             cudaStream_t st);
-cudaError_t launch_descriptors(const DetectParams &P, const DetectCounters *cnt, const FeatHead *prim, const float *ori, const uint32_t *feat_src,
+/* table of the descriptor's fixed-point scale sums M(R/2) (ComputeDescriptors.comp:116-124 only depends on the window radius) */
+#define VKS_DESC_M_TABLE 128
+cudaError_t launch_descriptor_scale_table(float *table, cudaStream_t st);
+cudaError_t launch_descriptors(const DetectParams &P, DetectCounters *cnt, const float *m_table, const FeatHead *prim, const float *ori, const uint32_t *feat_src,
                                FeatHead *out_heads, uint8_t *out_desc, cudaStream_t st);
 /* AoS <-> SoA for host transfers */
 cudaError_t launch_pack_aos(const FeatHead *heads, const uint8_t *desc, uint32_t n, uint8_t *aos, cudaStream_t st);
