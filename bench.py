@@ -183,7 +183,8 @@ def run_reference_arm(args, rank, world):
         return
     images = workload_images()
     import oracle
-    orc = oracle.Oracle(nb_threads=0)
+    cores = os.cpu_count() or 1
+    orc = oracle.Oracle(nb_threads=cores)  # explicit: torchrun exports OMP_NUM_THREADS=1
     for _ in range(max(1, min(args.warmup, 2))):
         orc.detect(images[0])
     steps = max(1, min(args.steps, 10))
@@ -193,7 +194,6 @@ def run_reference_arm(args, rank, world):
         n_feat += len(orc.detect(images[i % len(images)]))
     dt = time.perf_counter() - t0
     v = n_feat / dt
-    cores = os.cpu_count() or 1
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world),
@@ -235,10 +235,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # stdout must carry the JSON line only, but NCCL (version banner) and native code print to fd 1: send fd 1 to stderr
+    # for the whole run and keep a private handle on the real stdout for the result line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL_DEBUG=VERSION makes NCCL print a banner on stdout; stdout must carry the JSON line only
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     api.lib.vksift_setLogLevel(api.VKSIFT_LOG_WARNING)
 
@@ -426,14 +428,15 @@ def main():
         }
         if allpairs:
             line["allpairs"] = allpairs
-        if not args.no_cpu_baseline and world >= 1:
-            cb = cpu_port_baseline(images)
+        if not args.no_cpu_baseline and world == 1:
+            cb = cpu_port_baseline(images, threads=os.cpu_count() or 1)
             line["cpu_baseline"] = cb
-            line["match"]["cpu_baseline"] = cpu_match_baseline()
+            line["match"]["cpu_baseline"] = cpu_match_baseline(threads=os.cpu_count() or 1)
             ocv = opencv_baseline(images)
             if ocv:
                 line["opencv_baseline"] = ocv
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
