@@ -294,6 +294,7 @@ cudaError_t launch_assemble(const DetectParams &P, DetectCounters *cnt, const ui
 
 /* ---- descriptor ---------------------------------------------------------- */
 #define DESC_THREADS 128
+#define DESC_MAXBOX 160 /* window rows the row-interval tables hold (2R+1 <= 77 for the default configuration) */
 
 /* M(hr) of ComputeDescriptors.comp:116-124 for hr = R/2 < VKS_DESC_M_TABLE:
  *   for i<hr { m += e(i,i)*sqrt2; for j in (i, hr) m += e(i,j)*sqrt2*2 },  e(i,j) = exp(-0.125*(i*i+j*j))
@@ -334,6 +335,8 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
   __shared__ float s_terms[DESC_THREADS];
   __shared__ float s_m;
   __shared__ uint32_t s_g;
+  __shared__ int s_row_lo[DESC_MAXBOX];
+  __shared__ int s_row_start[DESC_MAXBOX + 1];
   const int tid = threadIdx.x;
   const uint32_t total = cnt->n_total;
   for (;;)
@@ -408,12 +411,10 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
     const float rsx = vks_rint(kp.scale_x), rsy = vks_rint(kp.scale_y);
     const int cx = (int)rsx, cy = (int)rsy;
     const int box = 2 * R + 1;
-    for (int pix = tid; pix < box * box; pix += DESC_THREADS)
-    {
-      const int dy = pix / box - R, dx = pix % box - R;
+    auto add_pixel = [&](int dx, int dy) {
       const int ix = cx + dx, iy = cy + dy;
       if (ix < 1 || ix >= (ov.w - 1) || iy < 1 || iy >= (ov.h - 1))
-        continue;
+        return;
       const float sdx = (rsx + (float)dx) - kp.scale_x;
       const float sdy = (rsy + (float)dy) - kp.scale_y;
       const float ox = kc * sdx + ks * sdy;
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
        * skip them before the transcendental work (about half of the box after rotation) */
       const int hx0 = (int)floorf((ox + 2.f) - 0.5f), hy0 = (int)floorf((oy + 2.f) - 0.5f);
       if (hx0 < -1 || hx0 > 3 || hy0 < -1 || hy0 > 3)
-        continue;
+        return;
       const float *__restrict__ c = L + (size_t)iy * ov.pitch + ix;
       const float gX = 0.5f * (__ldg(c + 1) - __ldg(c - 1));
       const float gY = 0.5f * (__ldg(c + ov.pitch) - __ldg(c - ov.pitch));
@@ -454,6 +455,84 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
               const float val = fabsf(1.f - (float)i - rx) * fabsf(1.f - (float)j - ry) * fabsf(1.f - (float)q - rb) * mag;
               atomicAdd(&s_desc[idx], (uint32_t)(val * fp));
             }
+    };
+    if (box <= DESC_MAXBOX)
+    {
+      /* The rotated 4x4 grid covers exactly half of the (2R+1)^2 box.  Per row, the pixels that can pass the grid test
+       * form an interval: compute a conservative one (the exact test stays in add_pixel, so the result is unchanged),
+       * and let the threads walk the concatenated intervals, so that a warp's 32 lanes are (almost) all useful. */
+      for (int row = tid; row < box; row += DESC_THREADS)
+      {
+        const int dy = row - R, iy = cy + dy;
+        int lo = max(-R, 1 - cx), hi = min(R, ov.w - 2 - cx);
+        if (iy < 1 || iy >= ov.h - 1)
+          hi = lo - 1;
+        else
+        {
+          const float sdy = (rsy + (float)dy) - kp.scale_y;
+          const float T = 2.5f + 0.02f;
+          float lo_f = -(float)(R + 2), hi_f = (float)(R + 2);
+          if (fabsf(kc) >= 1e-4f)
+          {
+            const float a = (-T - ks * sdy) / kc, b = (T - ks * sdy) / kc;
+            lo_f = fmaxf(lo_f, fminf(a, b));
+            hi_f = fminf(hi_f, fmaxf(a, b));
+          }
+          if (fabsf(ks) >= 1e-4f)
+          {
+            const float a = (kc * sdy - T) / ks, b = (kc * sdy + T) / ks;
+            lo_f = fmaxf(lo_f, fminf(a, b));
+            hi_f = fminf(hi_f, fmaxf(a, b));
+          }
+          const float fx = rsx - kp.scale_x; /* sdx = dx + fx */
+          if (lo_f <= hi_f)
+          {
+            lo = max(lo, (int)floorf(lo_f - fx) - 1);
+            hi = min(hi, (int)ceilf(hi_f - fx) + 1);
+          }
+          else
+            hi = lo - 1;
+        }
+        s_row_lo[row] = lo;
+        s_row_start[row + 1] = max(0, hi - lo + 1);
+      }
+      if (tid == 0)
+        s_row_start[0] = 0;
+      __syncthreads();
+      /* exclusive prefix of the row lengths (box <= 160 rows: one warp, five shuffle steps per 32 rows) */
+      if (tid < 32)
+      {
+        int carry = 0;
+        for (int base = 0; base < box; base += 32)
+        {
+          const int i = base + tid;
+          int v = (i < box) ? s_row_start[i + 1] : 0;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1)
+          {
+            const int n = __shfl_up_sync(0xffffffffu, v, d);
+            if (tid >= d)
+              v += n;
+          }
+          if (i < box)
+            s_row_start[i + 1] = carry + v;
+          carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+      }
+      __syncthreads();
+      const int n_px = s_row_start[box];
+      int row = 0;
+      for (int idx = tid; idx < n_px; idx += DESC_THREADS)
+      {
+        while (idx >= s_row_start[row + 1])
+          row++;
+        add_pixel(s_row_lo[row] + (idx - s_row_start[row]), row - R);
+      }
+    }
+    else
+    {
+      for (int pix = tid; pix < box * box; pix += DESC_THREADS)
+        add_pixel(pix % box - R, pix / box - R);
     }
     if (tid == 0)
       s_acc = 0;
