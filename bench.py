@@ -326,6 +326,41 @@ def main():
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
+    # ---------------- small images (configs[2] pattern: 640x480, 8 images per GPU) ----------------
+    # One vksift instance keeps one pipeline in flight (reference semantics), which leaves a B200 mostly idle on a
+    # 640x480 image; several instances on one GPU overlap their pipelines.  Reported, not the headline.
+    from vulkansift_b200.synth import C1
+    small = [blob_image(**dict(C1, seed=C1["seed"] + i)) for i in range(8)]
+    d_small = [torch.from_numpy(im).cuda() for im in small]
+    sh_, sw_ = small[0].shape
+    small_res = {}
+    for n_inst in (1, 4):
+        insts = [api.Instance(gpu_device_index=local_rank, input_image_max_size=sw_ * sh_, max_nb_sift_per_buffer=20000) for _ in range(n_inst)]
+        for rep in range(3):
+            for i in range(8):
+                insts[i % n_inst].detect_device(d_small[i].data_ptr(), sw_, sh_, 0)
+        for it in insts:
+            it.wait_idle()
+        nf_small = 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 10
+        for rep in range(reps):
+            for i in range(8):
+                insts[i % n_inst].detect_device(d_small[i].data_ptr(), sw_, sh_, 0)
+        for it in insts:
+            it.wait_idle()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if n_inst == 1:
+            for i in range(8):
+                insts[0].detect_device(d_small[i].data_ptr(), sw_, sh_, 0)
+                nf_small += insts[0].features_number(0)
+            small_res["features_per_8_images"] = nf_small
+        small_res["images_per_s_%d_instance%s" % (n_inst, "" if n_inst == 1 else "s")] = 8 * reps / dt
+        for it in insts:
+            it.close()
+
     # ---------------- matcher (configs[3]) ----------------
     da, db = random_descriptors(MATCH_N, 1234), random_descriptors(MATCH_N, 1235)
     minst = api.Instance(gpu_device_index=local_rank, max_nb_sift_per_buffer=MATCH_N, input_image_max_size=1024 * 1024)
@@ -425,6 +460,8 @@ def main():
                       "roofline": {"bound": "tensor", "achieved": m_ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": m_ach / tf_burst,
                                    "flops": flops, "peak_source": peak_src + " bf16 dense burst (i8 operands run at 2x this rate)"}},
             "clocks": clocks,
+            "small_images": dict(small_res, workload="configs[2] pattern on one GPU: 8 x 640x480 (upsampled, default config), images resident in "
+                                                     "HBM, wall clock over 10 rounds; N > 1: every rank does the same (weak scaling)"),
         }
         if allpairs:
             line["allpairs"] = allpairs

@@ -70,6 +70,15 @@ extern "C"
    * bracketed by a CUDA event pair on its stream (this costs a few microseconds per launch, so traced detections are for
    * analysis, not for timing the pipeline).  vksiftx_getLaunchTrace waits for the detection, fills up to `capacity`
    * entries (name: 32 chars, start/end in microseconds from the start of the detection) and returns the launch count. */
+  /* Cross-checked, ratio-tested matching on the device: what the reference's callers do on the CPU after two
+   * vksift_matchFeatures / vksift_downloadMatches round trips (src/examples/test_sift_match.cpp:73-107,
+   * src/perf/perf_common.cpp:122-170).  Runs A->B and B->A 2-NN searches, keeps the pairs (i, j) with j = nn1(i), i = nn1(j) and
+   * dist1/dist2 < lowe_ratio in both directions, in increasing i.  Blocking; writes at most `capacity` pairs
+   * (idx in A, idx in B) to host memory and returns the number of pairs found.  The instance's retained match result
+   * (vksift_downloadMatches) is the A->B list afterwards. */
+  VKSIFT_EXPORT uint32_t vksiftx_matchFeaturesCrossChecked(vksift_Instance instance, const uint32_t gpu_buffer_id_A, const uint32_t gpu_buffer_id_B,
+                                                           const float lowe_ratio, uint32_t *pairs, const uint32_t capacity);
+
   VKSIFT_EXPORT void vksiftx_setLaunchTrace(vksift_Instance instance, const bool enabled);
   VKSIFT_EXPORT uint32_t vksiftx_getLaunchTrace(vksift_Instance instance, char (*names)[32], float *start_us, float *end_us, const uint32_t capacity);
 

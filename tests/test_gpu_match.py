@@ -135,3 +135,35 @@ def test_c4_full_size_10k_x_10k(api, oracle_mod):
     d2 = ((da[rows, None, :].astype(np.int32) - db[None, :, :].astype(np.int32)) ** 2).sum(-1)
     assert np.array_equal(np.sort(d2, axis=1)[:, 0], np.round(tc["dist_a_b1"][rows].astype(np.float64) ** 2).astype(np.int64))
     inst.close()
+
+
+def test_cross_checked_matcher_equals_the_reference_callers_loop(api):
+    """vksiftx_matchFeaturesCrossChecked == the CPU loop of src/examples/test_sift_match.cpp:90-107 applied to the two
+    downloaded 2-NN lists (mutual nearest neighbour, Lowe ratio 0.75 in both directions), pairs in increasing idx_a."""
+    from vulkansift_b200.synth import blob_image
+    img = blob_image(800, 600, 500, seed=31)
+    shifted = np.roll(img, (3, 5), axis=(0, 1))
+    with api.Instance() as inst:
+        inst.detect(img, 0)
+        inst.detect(shifted, 1)
+        inst.match(0, 1)
+        m12 = inst.download_matches()
+        inst.match(1, 0)
+        m21 = inst.download_matches()
+        exp = []
+        old = np.seterr(all="ignore")  # 0/0 for identical descriptors: NaN < 0.75 is False, as in the C++ loop
+        for i in range(len(m12)):
+            j = int(m12[i]["idx_b1"])
+            if int(m21[j]["idx_b1"]) != i:
+                continue
+            if not (np.float32(m12[i]["dist_a_b1"]) / np.float32(m12[i]["dist_a_b2"]) < 0.75):
+                continue
+            if not (np.float32(m21[j]["dist_a_b1"]) / np.float32(m21[j]["dist_a_b2"]) < 0.75):
+                continue
+            exp.append((i, j))
+        np.seterr(**old)
+        got = inst.match_cross_checked(0, 1, 0.75)
+        assert len(exp) > 50
+        assert [tuple(int(v) for v in r) for r in got] == exp
+        # the retained match list is the A->B one
+        assert inst.download_matches().tobytes() == m12.tobytes()

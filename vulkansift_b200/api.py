@@ -99,6 +99,7 @@ def _load_library():
         "vksiftx_getMatchesDevice": (C.c_void_p, [I]),
         "vksiftx_setProfiling": (None, [I, C.c_bool]),
         "vksiftx_getStageTimesMs": (None, [I, P(C.c_float)]),
+        "vksiftx_matchFeaturesCrossChecked": (C.c_uint32, [I, C.c_uint32, C.c_uint32, C.c_float, P(C.c_uint32), C.c_uint32]),
         "vksiftx_setLaunchTrace": (None, [I, C.c_bool]),
         "vksiftx_getLaunchTrace": (C.c_uint32, [I, C.c_void_p, P(C.c_float), P(C.c_float), C.c_uint32]),
         "vksiftx_getKernelLaunchCount": (C.c_uint64, [I]),
@@ -302,6 +303,14 @@ class Instance:
         t = (C.c_float * NB_STAGES)()
         lib.vksiftx_getStageTimesMs(self._h, t)
         return dict(zip(STAGE_NAMES, [float(v) for v in t]))
+
+    def match_cross_checked(self, buf_a, buf_b, lowe_ratio=0.75):
+        """(n,2) uint32 pairs (idx in A, idx in B): mutual nearest neighbours passing the ratio test in both directions."""
+        cap = max(1, self.features_number(buf_a))
+        out = np.zeros((cap, 2), np.uint32)
+        n = int(lib.vksiftx_matchFeaturesCrossChecked(self._h, buf_a, buf_b, lowe_ratio, out.ctypes.data_as(C.POINTER(C.c_uint32)), cap))
+        self._check("vksiftx_matchFeaturesCrossChecked")
+        return out[:min(n, cap)]
 
     def set_launch_trace(self, enabled=True):
         lib.vksiftx_setLaunchTrace(self._h, bool(enabled))

@@ -119,6 +119,8 @@ struct vksift_Instance_T
   cudaStream_t oct_stream[VKS_MAX_OCT] = {nullptr}; /* [0] unused: octave 0 runs on the main stream */
   cudaEvent_t ev_seed[VKS_MAX_OCT] = {nullptr};     /* layer 0 of octave o written (by the pass producing layer ns of octave o-1) */
   cudaEvent_t ev_oct_done[VKS_MAX_OCT] = {nullptr};
+  cudaEvent_t ev_pyr[VKS_MAX_OCT] = {nullptr}; /* timing: scale space of octave o complete (profiling, split schedule) */
+  int n_pyr_events = 0;
   cudaEvent_t ev_join = nullptr;
 
   uint8_t *h_image = nullptr; /* pinned */
@@ -151,6 +153,8 @@ struct vksift_Instance_T
   uint8_t *d_aos = nullptr; /* device AoS staging for feature up/download */
   MatchWorkspace *match_ws = nullptr;
   vksift_Match_2NN *d_matches = nullptr;
+  vksift_Match_2NN *d_matches_rev = nullptr; /* B->A list of the cross-checked matcher */
+  uint32_t *d_pairs = nullptr;               /* [2*max + 1]: filtered pairs, count at the end */
   uint32_t nb_matches = 0;
   int matcher_impl = 0;
 
@@ -599,6 +603,8 @@ void destroy_instance(vksift_Instance inst)
   cudaFree(inst->desc_m_table);
   cudaFree(inst->d_aos);
   cudaFree(inst->d_matches);
+  cudaFree(inst->d_matches_rev);
+  cudaFree(inst->d_pairs);
   mega_plan_destroy(inst->mega);
   match_workspace_destroy(inst->match_ws);
   extrema_plan_destroy(inst->extrema_plan);
@@ -624,6 +630,8 @@ void destroy_instance(vksift_Instance inst)
       cudaEventDestroy(inst->ev_seed[o]);
     if (inst->ev_oct_done[o])
       cudaEventDestroy(inst->ev_oct_done[o]);
+    if (inst->ev_pyr[o])
+      cudaEventDestroy(inst->ev_pyr[o]);
     if (inst->oct_stream[o])
       cudaStreamDestroy(inst->oct_stream[o]);
   }
@@ -655,6 +663,7 @@ bool create_resources(vksift_Instance inst)
     CU_TRY(cudaStreamCreateWithPriority(&inst->oct_stream[o], cudaStreamNonBlocking, prio(o >= 2 ? 2 : 1)));
     CU_TRY(cudaEventCreateWithFlags(&inst->ev_seed[o], cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&inst->ev_oct_done[o], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreate(&inst->ev_pyr[o]));
   }
   CU_TRY(cudaEventCreateWithFlags(&inst->ev_detect_done, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&inst->ev_match_done, cudaEventDisableTiming));
@@ -697,6 +706,8 @@ bool create_resources(vksift_Instance inst)
   CU_TRY(launch_descriptor_scale_table(inst->desc_m_table, inst->stream));
   CU_TRY(cudaMalloc(&inst->d_aos, sizeof(vksift_Feature) * maxf));
   CU_TRY(cudaMalloc(&inst->d_matches, sizeof(vksift_Match_2NN) * maxf));
+  CU_TRY(cudaMalloc(&inst->d_matches_rev, sizeof(vksift_Match_2NN) * maxf));
+  CU_TRY(cudaMalloc(&inst->d_pairs, sizeof(uint32_t) * (2 * maxf + 1)));
   CU_TRY(match_workspace_create(&inst->match_ws, c.max_nb_sift_per_buffer));
 
   inst->buffers.resize(c.sift_buffer_count);
@@ -793,6 +804,22 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
     CU_TRY(launch_mega(inst->mega, st));
     inst->launches++;
   }
+  /* Split schedule: the extrema scan, ordering and orientation pass of an octave (their per-octave sections are
+   * independent) follow that octave's scale space on the same stream, so they overlap the scale space of the later
+   * octaves, a latency chain that leaves the GPU nearly idle at its end; everything joins before the feature assembly. */
+  const bool split = (n_fast > 0) && !inst->fused_oct.empty() && n_fast < P.n_oct && !inst->no_split && !inst->mega;
+  inst->ev_d1b_valid = split && prof;
+  inst->n_pyr_events = (split && prof) ? n_fast : 0;
+  auto post_chain = [&](int ob, int oe, cudaStream_t s) -> bool {
+    DetectParams Q = P;
+    Q.ob = ob;
+    Q.oe = oe;
+    CU_TRY(launch_extrema(Q, inst->extrema_plan, inst->raw, inst->cand, fb.cnt, s));
+    CU_TRY(launch_order_primaries(Q, inst->cand, fb.cnt, inst->prim, s));
+    CU_TRY(launch_orientation(Q, fb.cnt, inst->prim, inst->ori, inst->n_ori, s));
+    inst->launches += 4;
+    return true;
+  };
   for (int o = 0; o < n_fast; o++)
   {
     cudaStream_t so = (o == 0) ? st : inst->oct_stream[o];
@@ -809,12 +836,18 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
         CU_TRY(cudaEventRecord(inst->ev_seed[o + 1], so)); /* written by the pass producing layer ns */
     }
     if (o > 0)
+    {
+      if (split)
+      {
+        if (prof)
+          CU_TRY(cudaEventRecordWithFlags(inst->ev_pyr[o], so, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+        if (!post_chain(o, o + 1, so))
+          return false;
+      }
       CU_TRY(cudaEventRecord(inst->ev_oct_done[o], so));
+    }
   }
   (void)ns;
-  /* large octaves on per-layer launches, small ones fused on the side streams: the stages after the pyramid are split too */
-  const bool split = (n_fast > 0) && !inst->fused_oct.empty() && n_fast < P.n_oct && !inst->no_split;
-  inst->ev_d1b_valid = split && prof;
   if (!inst->fused_oct.empty())
   {
     cudaStream_t ss = (n_fast == 0) ? st : inst->side_stream;
@@ -850,26 +883,15 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
     }
     if (split)
     {
-      /* The octaves after the first are a latency chain that leaves the GPU nearly idle at its end: their extrema
-       * scan, ordering and orientation pass follow on the side stream while the main stream already does the same
-       * for octave 0, whose layers are complete much earlier and which holds ~3/4 of the pixels (the per-octave
-       * sections of these stages are independent); both meet again before the feature assembly. */
       if (used2)
       {
         CU_TRY(cudaEventRecord(inst->ev_join2, inst->side2_stream));
         CU_TRY(cudaStreamWaitEvent(ss, inst->ev_join2, 0));
       }
-      for (int o = 1; o < n_fast; o++)
-        CU_TRY(cudaStreamWaitEvent(ss, inst->ev_oct_done[o], 0));
       if (prof)
         CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D1B], ss, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
-      DetectParams PB = P;
-      PB.ob = 1;
-      PB.oe = P.n_oct;
-      CU_TRY(launch_extrema(PB, inst->extrema_plan, inst->raw, inst->cand, fb.cnt, ss));
-      CU_TRY(launch_order_primaries(PB, inst->cand, fb.cnt, inst->prim, ss));
-      CU_TRY(launch_orientation(PB, fb.cnt, inst->prim, inst->ori, inst->n_ori, ss));
-      inst->launches += 4;
+      if (!post_chain(n_fast, P.n_oct, ss))
+        return false;
       CU_TRY(cudaEventRecord(inst->ev_join, ss));
     }
     else
@@ -924,7 +946,12 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   CU_TRY(launch_orientation(PA, fb.cnt, inst->prim, inst->ori, inst->n_ori, st));
   inst->launches++;
   if (split)
-    CU_TRY(cudaStreamWaitEvent(st, inst->ev_join, 0)); /* the small octaves' keypoints are oriented too */
+  {
+    /* the other octaves' keypoints are oriented too */
+    for (int o = 1; o < n_fast; o++)
+      CU_TRY(cudaStreamWaitEvent(st, inst->ev_oct_done[o], 0));
+    CU_TRY(cudaStreamWaitEvent(st, inst->ev_join, 0));
+  }
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D3], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   CU_TRY(launch_assemble(P, fb.cnt, inst->n_ori, inst->feat_src, fb.host_counts_dev, st));
@@ -1617,6 +1644,64 @@ extern "C"
     inst->trace_dump_stderr = (t && t[0] == '1');
   }
 
+  uint32_t vksiftx_matchFeaturesCrossChecked(vksift_Instance inst, const uint32_t gpu_buffer_id_A, const uint32_t gpu_buffer_id_B,
+                                             const float lowe_ratio, uint32_t *pairs, const uint32_t capacity)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id_A) || !buffer_idx_valid(inst, gpu_buffer_id_B) || (pairs == NULL && capacity > 0))
+    {
+      LOGE(TAG, "vksiftx_matchFeaturesCrossChecked() error: invalid input.");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return 0;
+    }
+    bool ok = true, invalid = false;
+    uint32_t n_pairs = 0;
+    {
+      DeviceGuard g(inst->device);
+      wait_pipelines(inst, true, true);
+      const uint32_t na = buffer_count(inst, gpu_buffer_id_A, false);
+      const uint32_t nb = buffer_count(inst, gpu_buffer_id_B, false);
+      if (na < 2 || nb < 2)
+      {
+        LOGE(TAG, "vksiftx_matchFeaturesCrossChecked() error: both buffers need at least 2 features (%u, %u).", na, nb);
+        invalid = true;
+      }
+      else
+      {
+        FeatureBuffer &A = inst->buffers[gpu_buffer_id_A], &B = inst->buffers[gpu_buffer_id_B];
+        const size_t maxf = inst->cfg.max_nb_sift_per_buffer;
+        auto run = [&]() -> bool {
+          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, B.desc, nb, A.desc, na, inst->d_matches_rev, inst->stream, nullptr, &inst->launches));
+          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, B.desc, nb, inst->d_matches, inst->stream, nullptr, &inst->launches));
+          CU_TRY(launch_match_filter(inst->d_matches, na, inst->d_matches_rev, nb, lowe_ratio, inst->d_pairs, (uint32_t)maxf, inst->d_pairs + 2 * maxf,
+                                     inst->stream));
+          inst->launches++;
+          CU_TRY(cudaMemcpyAsync(&n_pairs, inst->d_pairs + 2 * maxf, sizeof(uint32_t), cudaMemcpyDeviceToHost, inst->stream));
+          CU_TRY(cudaStreamSynchronize(inst->stream));
+          const uint32_t n_copy = n_pairs < capacity ? n_pairs : capacity;
+          if (n_copy > 0)
+            CU_TRY(cudaMemcpy(pairs, inst->d_pairs, sizeof(uint32_t) * 2 * n_copy, cudaMemcpyDeviceToHost));
+          return true;
+        };
+        ok = run();
+        inst->nb_matches = na;
+        inst->match_a = gpu_buffer_id_A;
+        inst->match_b = gpu_buffer_id_B;
+      }
+    }
+    if (invalid)
+    {
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return 0;
+    }
+    if (!ok)
+    {
+      LOGE(TAG, "vksiftx_matchFeaturesCrossChecked() error: Failed to run the matching pipeline.");
+      inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
+      return 0;
+    }
+    return n_pairs;
+  }
+
   void vksiftx_setLaunchTrace(vksift_Instance inst, const bool enabled)
   {
     inst->trace = enabled;
@@ -1661,6 +1746,9 @@ extern "C"
         float tb = 0.f;
         if (cudaEventElapsedTime(&tb, inst->ev[EV_D0], inst->ev[EV_D1B]) == cudaSuccess && tb > t[0])
           t[0] = tb;
+        for (int o = 1; o < inst->n_pyr_events; o++)
+          if (cudaEventElapsedTime(&tb, inst->ev[EV_D0], inst->ev_pyr[o]) == cudaSuccess && tb > t[0])
+            t[0] = tb;
       }
       cudaEventElapsedTime(&t[1], inst->ev[EV_D1], inst->ev[EV_D2]);
       cudaEventElapsedTime(&t[2], inst->ev[EV_D2], inst->ev[EV_D3]);

@@ -146,6 +146,76 @@ void match_workspace_destroy(MatchWorkspace *ws)
   delete ws;
 }
 
+/* ---- mutual-nearest-neighbour + Lowe ratio filter -------------------------------------------------
+ * What every caller of the reference does on the CPU right after downloading two match lists
+ * (src/examples/test_sift_match.cpp:90-107, src/perf/perf_common.cpp:122-170):
+ *   keep i iff m21[m12[i].idx_b1].idx_b1 == i  and  d1/d2 < ratio in both directions.
+ * One CTA, ordered compaction: the pairs come out in increasing idx_a, like the reference loop produces them. */
+#define FILT_THREADS 1024
+__global__ void __launch_bounds__(FILT_THREADS) match_filter_kernel(const vksift_Match_2NN *__restrict__ m12, uint32_t na,
+                                                                    const vksift_Match_2NN *__restrict__ m21, uint32_t nb, float ratio,
+                                                                    uint32_t *__restrict__ pairs, uint32_t capacity, uint32_t *__restrict__ count)
+{
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_base;
+  const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+  if (tid == 0)
+    s_base = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < na; base += FILT_THREADS)
+  {
+    const uint32_t i = base + tid;
+    bool keep = false;
+    uint32_t j = 0;
+    if (i < na)
+    {
+      const vksift_Match_2NN a = m12[i];
+      j = a.idx_b1;
+      if (j < nb)
+      {
+        const vksift_Match_2NN b = m21[j];
+        keep = (b.idx_b1 == i) && ((a.dist_a_b1 / a.dist_a_b2) < ratio) && ((b.dist_a_b1 / b.dist_a_b2) < ratio);
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0)
+      s_warp[wi] = __popc(bal);
+    __syncthreads();
+    if (wi == 0)
+    {
+      uint32_t v = s_warp[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
+      {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d)
+          v += t;
+      }
+      s_warp[lane] = v; /* inclusive */
+    }
+    __syncthreads();
+    const uint32_t start = s_base + (wi ? s_warp[wi - 1] : 0u) + __popc(bal & ((1u << lane) - 1u));
+    if (keep && start < capacity)
+    {
+      pairs[2 * start + 0] = i;
+      pairs[2 * start + 1] = j;
+    }
+    __syncthreads();
+    if (tid == 0)
+      s_base += s_warp[31];
+    __syncthreads();
+  }
+  if (tid == 0)
+    *count = s_base;
+}
+
+cudaError_t launch_match_filter(const vksift_Match_2NN *m12, uint32_t na, const vksift_Match_2NN *m21, uint32_t nb, float ratio, uint32_t *pairs,
+                                uint32_t capacity, uint32_t *count, cudaStream_t st)
+{
+  match_filter_kernel<<<1, FILT_THREADS, 0, st>>>(m12, na, m21, nb, ratio, pairs, capacity, count);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *da, uint32_t na, const uint8_t *db, uint32_t nb, vksift_Match_2NN *out,
                          cudaStream_t st, cudaEvent_t ev_after_prepare, uint64_t *launch_count)
 {

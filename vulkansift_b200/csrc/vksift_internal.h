@@ -213,4 +213,7 @@ void match_workspace_destroy(MatchWorkspace *ws);
 cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *desc_a, uint32_t na, const uint8_t *desc_b, uint32_t nb, vksift_Match_2NN *out,
                          cudaStream_t st, cudaEvent_t ev_after_prepare, uint64_t *launch_count);
 
+cudaError_t launch_match_filter(const vksift_Match_2NN *m12, uint32_t na, const vksift_Match_2NN *m21, uint32_t nb, float ratio, uint32_t *pairs,
+                                uint32_t capacity, uint32_t *count, cudaStream_t st);
+
 } // namespace vks
