@@ -61,7 +61,8 @@ def dominant_kernel_roofline(trace_acc, octaves, hbm, peak_src):
     """Roofline of the dominant kernel = the per-layer blur launches of octave 0 (blur_pass_fast_kernel<R, LAYER>, 5 of the
     ~25 launches, ~60 % of the stage's bytes).  Algorithmic bytes per launch: the Gaussian layer and the DoG layer
     it writes, 2 * 4 * w0 * h0; duration = CUDA event pair around the launch on the launching stream (vksiftx launch trace),
-    averaged over the octave-0 layer launches.  traffic = ncu dram read+write of the same kernel, profiles/traffic_r1.json."""
+    averaged over the octave-0 layer launches, taken in the library's serial schedule (all launches on one stream; in the
+    default schedule octaves overlap and a launch's event pair also covers the kernels it shares the GPU with).  traffic = ncu dram read+write of the same kernel, profiles/traffic_r1.json."""
     w0, h0 = octaves[0]
     per_launch = 2 * 4 * w0 * h0
     durs = [v for k, v in trace_acc.items() if k.startswith("fast o0 r") and not k.endswith("#1")]
@@ -295,6 +296,7 @@ def main():
             stage_acc[k] = stage_acc.get(k, 0.0) + v / KP
     # per-launch times of the scale-space stage (event pair around every launch; traced runs are not timed runs)
     inst.set_launch_trace(True)
+    inst.set_serial_schedule(True)  # one stream: the event pair around a launch then times that kernel alone
     trace_acc = {}
     KT = 5
     for i in range(KT + 1):
@@ -307,6 +309,7 @@ def main():
             seen[name] = seen.get(name, 0) + 1
             key = "%s #%d" % (name, seen[name]) if name.startswith("fast o0 r4") else name
             trace_acc[key] = trace_acc.get(key, 0.0) + (t1 - t0) / KT
+    inst.set_serial_schedule(False)
     inst.set_launch_trace(False)
     inst.set_profiling(False)
 

@@ -80,6 +80,10 @@ extern "C"
                                                            const float lowe_ratio, uint32_t *pairs, const uint32_t capacity);
 
   VKSIFT_EXPORT void vksiftx_setLaunchTrace(vksift_Instance instance, const bool enabled);
+  /* Analysis aid: run every launch of the detection on one stream, in dependency order.  With the default schedule the
+   * octaves overlap on several streams and the time between a launch's two events includes the kernels it shares the GPU
+   * with; in the serial schedule it is that kernel's own duration. */
+  VKSIFT_EXPORT void vksiftx_setSerialSchedule(vksift_Instance instance, const bool enabled);
   VKSIFT_EXPORT uint32_t vksiftx_getLaunchTrace(vksift_Instance instance, char (*names)[32], float *start_us, float *end_us, const uint32_t capacity);
 
   /* Number of kernels this library launched on the instance since creation

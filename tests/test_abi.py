@@ -97,3 +97,15 @@ def test_no_gpu_fails_loudly_not_silently():
             "try:\n api.Instance()\n print('CREATED')\nexcept api.VksiftError as e:\n print('ERR', e.code)\n")
     out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True).stdout.split("\n")
     assert out[0] == "ERR 2" and out[1] == "ERR 2", out
+
+
+def test_plain_c_caller_links_against_the_library(tmp_path):
+    """A C program written against the reference's header links against the B200 library unchanged (no compute call)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "vulkansift_b200", "lib")
+    out = tmp_path / "detect_match"
+    r = subprocess.run(["gcc", os.path.join(root, "examples", "detect_match.c"), "-I" + os.path.join(root, "include"), "-L" + lib_dir,
+                        "-lvulkansift", "-Wl,-rpath," + lib_dir, "-lm", "-o", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -267,3 +267,16 @@ def test_fp16_pyramid_precision_mode_bit_exact(api, oracle_mod):
                 d = inst.download_dog_image(o, 2)
                 e = orc.dog(o, 2)
                 assert np.array_equal(d.view(np.uint32), e.view(np.uint32)), o
+
+
+def test_serial_schedule_is_bit_exact(api, oracle_mod):
+    from vulkansift_b200.synth import blob_image
+    img = blob_image(1000, 700, 600, seed=12)
+    with api.Instance() as inst:
+        exp = oracle_mod.Oracle().detect(img)
+        inst.set_serial_schedule(True)
+        inst.detect(img, 0)
+        assert_features_equal(inst.download_features(0), exp)
+        inst.set_serial_schedule(False)
+        inst.detect(img, 1)
+        assert_features_equal(inst.download_features(1), exp)

@@ -101,6 +101,7 @@ def _load_library():
         "vksiftx_getStageTimesMs": (None, [I, P(C.c_float)]),
         "vksiftx_matchFeaturesCrossChecked": (C.c_uint32, [I, C.c_uint32, C.c_uint32, C.c_float, P(C.c_uint32), C.c_uint32]),
         "vksiftx_setLaunchTrace": (None, [I, C.c_bool]),
+        "vksiftx_setSerialSchedule": (None, [I, C.c_bool]),
         "vksiftx_getLaunchTrace": (C.c_uint32, [I, C.c_void_p, P(C.c_float), P(C.c_float), C.c_uint32]),
         "vksiftx_getKernelLaunchCount": (C.c_uint64, [I]),
         "vksiftx_getEffectiveTaps": (None, [I, C.c_void_p, C.c_void_p]),
@@ -314,6 +315,9 @@ class Instance:
 
     def set_launch_trace(self, enabled=True):
         lib.vksiftx_setLaunchTrace(self._h, bool(enabled))
+
+    def set_serial_schedule(self, enabled=True):
+        lib.vksiftx_setSerialSchedule(self._h, bool(enabled))
 
     def launch_trace(self, capacity=256):
         """[(name, start_us, end_us)] of the scale-space launches of the last (traced) detection."""

@@ -112,6 +112,7 @@ struct vksift_Instance_T
   std::vector<FusedOct> fused_oct;             /* small octaves [k,n): fused kernel, one or two launches per octave */
   MegaPlan *mega = nullptr;                    /* whole scale space as one persistent launch, when the configuration allows it */
   bool use_mega = false;
+  bool serial = false;   /* vksiftx_setSerialSchedule */
   bool no_split = false; /* VKSIFT_NO_SPLIT=1: extrema/orientation of all octaves after the whole pyramid (debug) */
   cudaStream_t side_stream = nullptr, side2_stream = nullptr;
   cudaEvent_t ev_chain[VKS_MAX_OCT] = {nullptr}; /* chain launches of octave o enqueued on the side stream */
@@ -807,7 +808,11 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   /* Split schedule: the extrema scan, ordering and orientation pass of an octave (their per-octave sections are
    * independent) follow that octave's scale space on the same stream, so they overlap the scale space of the later
    * octaves, a latency chain that leaves the GPU nearly idle at its end; everything joins before the feature assembly. */
-  const bool split = (n_fast > 0) && !inst->fused_oct.empty() && n_fast < P.n_oct && !inst->no_split && !inst->mega;
+  /* serial schedule (analysis only): every launch on the main stream in dependency order, so that the event pair around
+   * a launch times that kernel alone */
+  const bool serial = inst->serial;
+  cudaStream_t side2 = serial ? st : inst->side2_stream;
+  const bool split = (n_fast > 0) && !inst->fused_oct.empty() && n_fast < P.n_oct && !inst->no_split && !inst->mega && !serial;
   inst->ev_d1b_valid = split && prof;
   inst->n_pyr_events = (split && prof) ? n_fast : 0;
   auto post_chain = [&](int ob, int oe, cudaStream_t s) -> bool {
@@ -822,7 +827,7 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   };
   for (int o = 0; o < n_fast; o++)
   {
-    cudaStream_t so = (o == 0) ? st : inst->oct_stream[o];
+    cudaStream_t so = (o == 0 || serial) ? st : inst->oct_stream[o];
     if (o > 0)
       CU_TRY(cudaStreamWaitEvent(so, inst->ev_seed[o], 0));
     for (BlurPass &bp : inst->fast_oct[o])
@@ -850,7 +855,7 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   (void)ns;
   if (!inst->fused_oct.empty())
   {
-    cudaStream_t ss = (n_fast == 0) ? st : inst->side_stream;
+    cudaStream_t ss = (n_fast == 0 || serial) ? st : inst->side_stream;
     if (n_fast > 0)
       CU_TRY(cudaStreamWaitEvent(ss, inst->ev_seed[n_fast], 0));
     bool used2 = false;
@@ -871,11 +876,11 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
       if (!fo.rest.empty())
       {
         CU_TRY(cudaEventRecord(inst->ev_chain[j], ss));
-        CU_TRY(cudaStreamWaitEvent(inst->side2_stream, inst->ev_chain[j], 0));
+        CU_TRY(cudaStreamWaitEvent(side2, inst->ev_chain[j], 0));
         for (const FusedLaunch &F : fo.rest)
         {
-          TraceScope ts(inst, inst->side2_stream, "fused rest o%d n%d", n_fast + (int)j, F.n_layers);
-          CU_TRY(launch_fused(F, inst->side2_stream));
+          TraceScope ts(inst, side2, "fused rest o%d n%d", n_fast + (int)j, F.n_layers);
+          CU_TRY(launch_fused(F, side2));
           inst->launches++;
         }
         used2 = true;
@@ -885,7 +890,7 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
     {
       if (used2)
       {
-        CU_TRY(cudaEventRecord(inst->ev_join2, inst->side2_stream));
+        CU_TRY(cudaEventRecord(inst->ev_join2, side2));
         CU_TRY(cudaStreamWaitEvent(ss, inst->ev_join2, 0));
       }
       if (prof)
@@ -903,14 +908,14 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
       }
       if (used2)
       {
-        CU_TRY(cudaEventRecord(inst->ev_join2, inst->side2_stream));
+        CU_TRY(cudaEventRecord(inst->ev_join2, side2));
         CU_TRY(cudaStreamWaitEvent(st, inst->ev_join2, 0));
       }
     }
   }
   if (!inst->steps_side.empty())
   {
-    cudaStream_t ss = (n_fast == 0) ? st : inst->side_stream;
+    cudaStream_t ss = (n_fast == 0 || serial) ? st : inst->side_stream;
     if (n_fast > 0)
       CU_TRY(cudaStreamWaitEvent(ss, inst->ev_seed[n_fast], 0));
     for (BlurStep &step : inst->steps_side)
@@ -1700,6 +1705,13 @@ extern "C"
       return 0;
     }
     return n_pairs;
+  }
+
+  void vksiftx_setSerialSchedule(vksift_Instance inst, const bool enabled)
+  {
+    wait_pipelines(inst, true, true);
+    inst->serial = enabled;
+    invalidate_graphs(inst);
   }
 
   void vksiftx_setLaunchTrace(vksift_Instance inst, const bool enabled)

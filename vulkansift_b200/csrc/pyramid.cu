@@ -1319,7 +1319,7 @@ bool blur_pass_is_fast(const BlurPass &bp)
 {
   if (bp.radius < 1 || bp.radius > 12)
     return false;
-  return ((bp.w + FT_W - 1) / FT_W) * ((bp.h + FT_H - 1) / FT_H) >= 64;
+  return ((bp.w + FT_W - 1) / FT_W) * ((bp.h + FT_H - 1) / FT_H) >= 24;
 }
 
 bool blur_step_tiles(BlurStep *step)
