@@ -2,7 +2,8 @@
  * vksift_b200_ext.h -- vksiftx_* extension entry points of the B200 build.
  *
  * The reference API (include/vulkansift/vulkansift.h) only takes and returns
- * HOST memory and keeps one pipeline in flight.  These additions let a caller
+ * HOST memory and keeps one pipeline in flight (this build keeps one detection
+ * in flight per detection lane, see vksiftx_getLaneCount).  These additions let a caller
  * keep inputs and results resident in HBM (device-timed benchmarks, NCCL
  * descriptor exchange between GPUs) and read per-stage device timings.  They
  * are plain C ABI like the rest: pointers and sizes, no CUDA or torch types.
@@ -34,6 +35,17 @@ extern "C"
 
   /* Block until every pipeline of the instance has finished. */
   VKSIFT_EXPORT void vksiftx_waitIdle(vksift_Instance instance);
+
+  /* Detection lanes.  The reference makes vksift_detectFeatures wait for the previous detection because the instance owns
+   * one scale space and one command buffer (vulkansift.c:326-327).  This build gives the instance min(sift_buffer_count, 4)
+   * lanes (environment override VKSIFT_LANES=n), each with its own scale space, scratch memory and streams; a detection
+   * into buffer b runs on lane b % lanes and waits for that lane only, so detections into different buffers overlap on the
+   * GPU.  Results are identical to the one-lane schedule.  vksift_getScaleSpace* / vksift_download*Image show the scale
+   * space of the most recent detection.
+   * vksiftx_joinLanes makes the instance stream (vksiftx_getStream) wait, on the device, for every detection enqueued so
+   * far: an event recorded on that stream afterwards times them all. */
+  VKSIFT_EXPORT uint32_t vksiftx_getLaneCount(vksift_Instance instance);
+  VKSIFT_EXPORT void vksiftx_joinLanes(vksift_Instance instance);
 
   /* Packed device view of a feature buffer: n descriptors [n][128] u8 (row
    * pitch 128 B) and n 36-byte feature heads (the vksift_Feature fields before

@@ -280,3 +280,62 @@ def test_serial_schedule_is_bit_exact(api, oracle_mod):
         inst.set_serial_schedule(False)
         inst.detect(img, 1)
         assert_features_equal(inst.download_features(1), exp)
+
+
+def test_detection_lanes_overlap_and_stay_bit_exact(api, oracle_mod):
+    """Detections into different buffers run on different lanes (own scale space, scratch, streams) without waiting for
+    each other; every result must equal the oracle's, whatever the interleaving, resolution mix and input memory kind."""
+    import torch
+    from vulkansift_b200.synth import blob_image
+    shapes = [(320, 240), (257, 193), (320, 240), (400, 300)]
+    imgs = [blob_image(w, h, 120 + 10 * i, seed=20 + i) for i, (w, h) in enumerate(shapes)]
+    orc = oracle_mod.Oracle()
+    exp = [orc.detect(im) for im in imgs]
+    inst = api.Instance(sift_buffer_count=4)
+    assert inst.lane_count() == 4
+    pinned = [torch.from_numpy(im).pin_memory() for im in imgs]
+    dev = [torch.from_numpy(im).cuda() for im in imgs]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        # all four enqueued back to back: pageable host, page-locked host (read by the copy engine) and device inputs
+        for b, im in enumerate(imgs):
+            h, w = im.shape
+            if (b + rep) % 3 == 0:
+                inst.detect(im, b)
+            elif (b + rep) % 3 == 1:
+                inst.detect_raw(pinned[b].data_ptr(), w, h, b)
+            else:
+                inst.detect_device(dev[b].data_ptr(), w, h, b)
+        # the scale space shown is the one of the most recent detection
+        assert inst.octave_resolution(0) == (2 * shapes[3][0], 2 * shapes[3][1])
+        for b in (2, 0, 3, 1):
+            assert_features_equal(inst.download_features(b), exp[b], "rep %d buffer %d" % (rep, b))
+        # a lane is reused by a different image while the others still hold theirs
+        inst.detect(imgs[1], 0)
+        assert_features_equal(inst.download_features(0), exp[1], "reused lane")
+        assert_features_equal(inst.download_features(1), exp[1], "untouched buffer")
+    # matching waits for every lane
+    inst.detect(imgs[0], 0)
+    inst.detect(imgs[2], 2)
+    inst.match(0, 2)
+    m = inst.download_matches()
+    assert m.tobytes() == oracle_mod.match_features(exp[0], exp[2]).tobytes()
+    inst.close()
+
+
+def test_single_lane_override(api, oracle_mod, c1_image, monkeypatch):
+    monkeypatch.setenv("VKSIFT_LANES", "1")
+    inst = api.Instance()
+    assert inst.lane_count() == 1
+    inst.detect(c1_image, 0)
+    inst.detect(c1_image[::-1].copy(), 1)
+    a, b = inst.download_features(0), inst.download_features(1)
+    inst.close()
+    monkeypatch.delenv("VKSIFT_LANES")
+    inst = api.Instance()
+    assert inst.lane_count() == 2
+    inst.detect(c1_image, 0)
+    inst.detect(c1_image[::-1].copy(), 1)
+    assert_features_equal(inst.download_features(0), a, "lanes vs single lane, buffer 0")
+    assert_features_equal(inst.download_features(1), b, "lanes vs single lane, buffer 1")
+    inst.close()

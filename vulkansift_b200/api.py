@@ -93,6 +93,8 @@ def _load_library():
         "vksiftx_getStream": (C.c_void_p, [I]),
         "vksiftx_detectFeaturesDevice": (None, [I, C.c_void_p, u32, u32, u32]),
         "vksiftx_waitIdle": (None, [I]),
+        "vksiftx_getLaneCount": (u32, [I]),
+        "vksiftx_joinLanes": (None, [I]),
         "vksiftx_getBufferDeviceView": (None, [I, u32, P(u32), P(C.c_void_p), P(C.c_void_p)]),
         "vksiftx_uploadDescriptorsDevice": (None, [I, C.c_void_p, u32, u32]),
         "vksiftx_copyDescriptorsToDevice": (u32, [I, u32, C.c_void_p, u32]),
@@ -206,9 +208,15 @@ class Instance:
         self._check("vksift_getFeaturesNumber")
         return n
 
-    def download_features(self, buffer_id=0):
+    def download_features(self, buffer_id=0, out=None):
+        """vksift_getFeaturesNumber + vksift_downloadFeatures.  `out`: optional caller-owned FEATURE_DTYPE array (e.g. a view
+        of page-locked memory) with room for the features; the filled prefix is returned."""
         n = self.features_number(buffer_id)
-        out = np.zeros(n, FEATURE_DTYPE)
+        if out is None:
+            out = np.empty(n, FEATURE_DTYPE)
+        else:
+            assert out.dtype == FEATURE_DTYPE and len(out) >= n
+            out = out[:n]
         lib.vksift_downloadFeatures(self._h, out.ctypes.data, buffer_id)
         self._check("vksift_downloadFeatures")
         return out
@@ -278,6 +286,12 @@ class Instance:
 
     def wait_idle(self):
         lib.vksiftx_waitIdle(self._h)
+
+    def lane_count(self):
+        return int(lib.vksiftx_getLaneCount(self._h))
+
+    def join_lanes(self):
+        lib.vksiftx_joinLanes(self._h)
 
     def buffer_device_view(self, buffer_id=0):
         n, d, hd = C.c_uint32(0), C.c_void_p(None), C.c_void_p(None)

@@ -140,7 +140,21 @@ struct vksift_Instance_T
   std::vector<DetectGraph> graphs;
   bool use_graph = false;
 
-  std::vector<FeatureBuffer> buffers;
+  /* Detection lanes.  The reference owns one scale space and one command buffer, so a detection first waits for the
+   * previous one (vulkansift.c:326-327).  With 180 GB of HBM a second and third scale space cost nothing: the instance the
+   * caller holds (the primary, lane 0) owns `lanes.size() - 1` secondary instances, each with its own pyramid, scratch,
+   * streams and staging, all aliasing the primary's feature buffers.  A detection into buffer b runs on lane b % lanes and
+   * only waits for that lane, so detections into different buffers overlap on the GPU (the latency chain of the small
+   * octaves of one image hides behind the large octaves of the next) and the launch work of one overlaps the execution of
+   * the other.  Results are unchanged; only the blocking rule is relaxed. */
+  std::vector<vksift_Instance> lanes; /* primary: [0] = this; secondaries: empty */
+  vksift_Instance primary = nullptr;  /* secondaries: the owner */
+  uint32_t last_lane = 0;             /* lane of the most recent detection: the scale space the download functions show */
+  cudaEvent_t ev_h2d = nullptr;       /* image upload from caller-pinned memory complete */
+
+  std::vector<FeatureBuffer> own_buffers; /* primary only */
+  FeatureBuffer *buffers = nullptr;       /* own_buffers.data() of the primary */
+  uint32_t n_buffers = 0;
   Candidate *cand = nullptr;
   unsigned long long *raw = nullptr; /* queued extrema (s,y,x) per octave */
   uint32_t cand_cap = 0;
@@ -253,9 +267,9 @@ bool config_valid(const vksift_Config *c)
 bool buffer_idx_valid(vksift_Instance inst, uint32_t idx)
 {
   /* the reference tests '>' (vulkansift.c:588); its own example documents '>=' as the intent (SURVEY B-D5) */
-  if (idx >= inst->buffers.size())
+  if (idx >= inst->n_buffers)
   {
-    LOGE(TAG, "Provided target buffer index is (%u) but the number of reserved buffers is (%zu).", idx, inst->buffers.size());
+    LOGE(TAG, "Provided target buffer index is (%u) but the number of reserved buffers is (%u).", idx, inst->n_buffers);
     return false;
   }
   return true;
@@ -538,12 +552,26 @@ void fill_detect_params(vksift_Instance inst, const FeatureBuffer &fb, DetectPar
   P->max_feats = c.max_nb_sift_per_buffer;
 }
 
+void wait_lane(vksift_Instance lane)
+{
+  if (lane->detect_pending)
+  {
+    cudaEventSynchronize(lane->ev_detect_done);
+    lane->detect_pending = false;
+  }
+}
+
+vksift_Instance lane_of_buffer(vksift_Instance inst, uint32_t buf) { return inst->lanes.empty() ? inst : inst->lanes[buf % inst->lanes.size()]; }
+vksift_Instance last_lane(vksift_Instance inst) { return inst->lanes.empty() ? inst : inst->lanes[inst->last_lane]; }
+
+/* detect: every lane of the instance */
 void wait_pipelines(vksift_Instance inst, bool detect, bool match)
 {
-  if (detect && inst->detect_pending)
+  if (detect)
   {
-    cudaEventSynchronize(inst->ev_detect_done);
-    inst->detect_pending = false;
+    wait_lane(inst);
+    for (size_t k = 1; k < inst->lanes.size(); k++)
+      wait_lane(inst->lanes[k]);
   }
   if (match && inst->match_pending)
   {
@@ -575,7 +603,12 @@ void destroy_instance(vksift_Instance inst)
 {
   DeviceGuard g(inst->device);
   cudaDeviceSynchronize();
-  for (auto &fb : inst->buffers)
+  for (size_t k = 1; k < inst->lanes.size(); k++)
+    destroy_instance(inst->lanes[k]);
+  inst->lanes.clear();
+  if (inst->ev_h2d)
+    cudaEventDestroy(inst->ev_h2d);
+  for (auto &fb : inst->own_buffers)
   {
     cudaFree(fb.heads);
     cudaFree(fb.desc);
@@ -668,6 +701,7 @@ bool create_resources(vksift_Instance inst)
   }
   CU_TRY(cudaEventCreateWithFlags(&inst->ev_detect_done, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&inst->ev_match_done, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&inst->ev_h2d, cudaEventDisableTiming | cudaEventBlockingSync));
   for (int i = 0; i < EV_COUNT; i++)
     CU_TRY(cudaEventCreate(&inst->ev[i]));
 
@@ -706,14 +740,23 @@ bool create_resources(vksift_Instance inst)
   CU_TRY(cudaMalloc(&inst->desc_m_table, sizeof(float) * VKS_DESC_M_TABLE));
   CU_TRY(launch_descriptor_scale_table(inst->desc_m_table, inst->stream));
   CU_TRY(cudaMalloc(&inst->d_aos, sizeof(vksift_Feature) * maxf));
+  inst->graphs.resize(c.sift_buffer_count);
+  if (inst->primary)
+  {
+    /* a secondary lane: detection only, on the primary's feature buffers */
+    inst->buffers = inst->primary->buffers;
+    inst->n_buffers = inst->primary->n_buffers;
+    return set_resolution(inst, side, side);
+  }
   CU_TRY(cudaMalloc(&inst->d_matches, sizeof(vksift_Match_2NN) * maxf));
   CU_TRY(cudaMalloc(&inst->d_matches_rev, sizeof(vksift_Match_2NN) * maxf));
   CU_TRY(cudaMalloc(&inst->d_pairs, sizeof(uint32_t) * (2 * maxf + 1)));
   CU_TRY(match_workspace_create(&inst->match_ws, c.max_nb_sift_per_buffer));
 
-  inst->buffers.resize(c.sift_buffer_count);
-  inst->graphs.resize(c.sift_buffer_count);
-  for (auto &fb : inst->buffers)
+  inst->own_buffers.resize(c.sift_buffer_count);
+  inst->buffers = inst->own_buffers.data();
+  inst->n_buffers = c.sift_buffer_count;
+  for (auto &fb : inst->own_buffers)
   {
     /* +256 rows: the matcher's TMA boxes and |b|^2 loads may run past the last feature */
     CU_TRY(cudaMalloc(&fb.heads, sizeof(FeatHead) * (maxf + 256)));
@@ -728,8 +771,29 @@ bool create_resources(vksift_Instance inst)
   /* default resolution = square of the maximum size (sift_memory.c:637-640) */
   if (!set_resolution(inst, side, side))
     return false;
-  for (auto &fb : inst->buffers)
+  for (auto &fb : inst->own_buffers)
     update_buffer_sections(inst, fb);
+  /* detection lanes: VKSIFT_LANES overrides the default of one lane per feature buffer, at most 4 */
+  uint32_t n_lanes = c.sift_buffer_count < 4u ? c.sift_buffer_count : 4u;
+  if (const char *e = getenv("VKSIFT_LANES"))
+  {
+    const long v = strtol(e, nullptr, 10);
+    if (v >= 1)
+      n_lanes = (uint32_t)v < c.sift_buffer_count ? (uint32_t)v : c.sift_buffer_count;
+  }
+  if (inst->use_mega)
+    n_lanes = 1;
+  inst->lanes.push_back(inst);
+  for (uint32_t k = 1; k < n_lanes; k++)
+  {
+    vksift_Instance lane = new vksift_Instance_T();
+    lane->cfg = inst->cfg;
+    lane->device = inst->device;
+    lane->primary = inst;
+    inst->lanes.push_back(lane); /* owned from here on: destroy_instance(inst) frees it */
+    if (!create_resources(lane))
+      return false;
+  }
   return true;
 }
 
@@ -1037,25 +1101,54 @@ bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t bu
 
 bool detect_common(vksift_Instance inst, const uint8_t *host_image, const uint8_t *dev_image, uint32_t w, uint32_t h, uint32_t buf)
 {
-  /* a running detection or matching pipeline is waited for first (vulkansift.c:325-327) */
-  wait_pipelines(inst, true, true);
+  /* A running matching pipeline is waited for first (vulkansift.c:325-327), and so is the previous detection of the lane
+   * this buffer maps to (its scale space and scratch are about to be overwritten); detections on other lanes keep running. */
+  wait_pipelines(inst, false, true);
+  vksift_Instance lane = lane_of_buffer(inst, buf);
+  wait_lane(lane);
+  inst->last_lane = inst->lanes.empty() ? 0u : buf % (uint32_t)inst->lanes.size();
   /* vksift_prepareSiftMemoryForDetection (sift_memory.c:891-955) */
-  if (inst->cur_w != w || inst->cur_h != h)
+  if (lane->cur_w != w || lane->cur_h != h)
   {
-    if (!set_resolution(inst, w, h))
+    if (!set_resolution(lane, w, h))
       return false;
   }
-  FeatureBuffer &fb = inst->buffers[buf];
-  if (fb.cur_w != inst->cur_w || fb.cur_h != inst->cur_h)
-    update_buffer_sections(inst, fb);
+  FeatureBuffer &fb = lane->buffers[buf];
+  if (fb.cur_w != lane->cur_w || fb.cur_h != lane->cur_h)
+    update_buffer_sections(lane, fb);
   const uint8_t *src = dev_image;
+  bool direct = false;
   if (host_image)
   {
-    memcpy(inst->h_image, host_image, (size_t)w * h); /* the caller's buffer is free after return */
-    CU_TRY(cudaMemcpyAsync(inst->d_image, inst->h_image, (size_t)w * h, cudaMemcpyHostToDevice, inst->stream));
-    src = inst->d_image;
+    /* The caller's buffer is only borrowed for the duration of the call (sift_memory.c:943 copies it to a staging buffer).
+     * Page-locked caller memory is read by the copy engine directly and the call returns once that copy has completed,
+     * after the pipeline has been enqueued behind it; pageable memory goes through the lane's pinned staging buffer. */
+    cudaPointerAttributes attr;
+    direct = (cudaPointerGetAttributes(&attr, host_image) == cudaSuccess && attr.type == cudaMemoryTypeHost);
+    if (!direct)
+    {
+      cudaGetLastError();
+      memcpy(lane->h_image, host_image, (size_t)w * h);
+    }
+    CU_TRY(cudaMemcpyAsync(lane->d_image, direct ? host_image : lane->h_image, (size_t)w * h, cudaMemcpyHostToDevice, lane->stream));
+    if (direct)
+      CU_TRY(cudaEventRecord(lane->ev_h2d, lane->stream));
+    src = lane->d_image;
   }
-  return enqueue_detection(inst, src, buf);
+  const bool ok = enqueue_detection(lane, src, buf);
+  if (direct)
+    CU_TRY(cudaEventSynchronize(lane->ev_h2d));
+  return ok;
+}
+
+/* the lane whose pending detection writes this buffer is waited for; a pending match that reads the buffer too */
+void wait_buffer(vksift_Instance inst, uint32_t buf)
+{
+  vksift_Instance lane = lane_of_buffer(inst, buf);
+  if (lane->detect_pending && lane->detect_buffer == buf)
+    wait_lane(lane);
+  if (inst->match_pending && (buf == inst->match_a || buf == inst->match_b))
+    wait_pipelines(inst, false, true);
 }
 
 } // namespace
@@ -1230,11 +1323,12 @@ extern "C"
   {
     /* vulkansift.c:295-313 */
     DeviceGuard g(inst->device);
-    if (inst->detect_pending && gpu_buffer_id == inst->detect_buffer)
+    vksift_Instance lane = lane_of_buffer(inst, gpu_buffer_id);
+    if (lane->detect_pending && gpu_buffer_id == lane->detect_buffer)
     {
-      if (cudaEventQuery(inst->ev_detect_done) == cudaErrorNotReady)
+      if (cudaEventQuery(lane->ev_detect_done) == cudaErrorNotReady)
         return false;
-      inst->detect_pending = false;
+      lane->detect_pending = false;
     }
     if (inst->match_pending && (gpu_buffer_id == inst->match_a || gpu_buffer_id == inst->match_b))
     {
@@ -1296,8 +1390,7 @@ extern "C"
       return 0;
     }
     DeviceGuard g(inst->device);
-    if (!vksift_isBufferAvailable(inst, gpu_buffer_id))
-      wait_pipelines(inst, true, true);
+    wait_buffer(inst, gpu_buffer_id);
     return buffer_count(inst, gpu_buffer_id, true);
   }
 
@@ -1312,17 +1405,18 @@ extern "C"
     bool ok = true;
     {
       DeviceGuard g(inst->device);
-      if (!vksift_isBufferAvailable(inst, gpu_buffer_id))
-        wait_pipelines(inst, true, true);
+      wait_buffer(inst, gpu_buffer_id);
       FeatureBuffer &fb = inst->buffers[gpu_buffer_id];
       const uint32_t n = buffer_count(inst, gpu_buffer_id, false);
       if (n > 0)
       {
+        /* on the stream and staging area of the buffer's lane, so that the transfer does not queue behind another lane */
+        vksift_Instance lane = lane_of_buffer(inst, gpu_buffer_id);
         auto run = [&]() -> bool {
-          CU_TRY(launch_pack_aos(fb.heads, fb.desc, n, inst->d_aos, inst->stream));
+          CU_TRY(launch_pack_aos(fb.heads, fb.desc, n, lane->d_aos, lane->stream));
           inst->launches++;
-          CU_TRY(cudaMemcpyAsync(feats_ptr, inst->d_aos, sizeof(vksift_Feature) * (size_t)n, cudaMemcpyDeviceToHost, inst->stream));
-          CU_TRY(cudaStreamSynchronize(inst->stream));
+          CU_TRY(cudaMemcpyAsync(feats_ptr, lane->d_aos, sizeof(vksift_Feature) * (size_t)n, cudaMemcpyDeviceToHost, lane->stream));
+          CU_TRY(cudaStreamSynchronize(lane->stream));
           return true;
         };
         ok = run();
@@ -1497,28 +1591,31 @@ extern "C"
   }
 
   /* ---- scale-space access (vulkansift.c:463-519) --------------------------- */
-  uint8_t vksift_getScaleSpaceNbOctaves(vksift_Instance inst) { return (uint8_t)inst->pyr.n_oct; }
+  /* the scale space shown is the one of the most recent detection (every lane starts at the default resolution) */
+  uint8_t vksift_getScaleSpaceNbOctaves(vksift_Instance inst) { return (uint8_t)last_lane(inst)->pyr.n_oct; }
 
   void vksift_getScaleSpaceOctaveResolution(vksift_Instance inst, const uint8_t octave, uint32_t *octave_images_width, uint32_t *octave_images_height)
   {
-    if (octave >= inst->pyr.n_oct)
+    const Pyramid &pyr = last_lane(inst)->pyr;
+    if (octave >= pyr.n_oct)
     {
       LOGE(TAG, "vksift_getScaleSpaceOctaveResolution() error: invalid input. Requested octave idx is %d but the current number of octave is %d", octave,
-           inst->pyr.n_oct);
+           pyr.n_oct);
       inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
       return;
     }
-    *octave_images_width = inst->pyr.w[octave];
-    *octave_images_height = inst->pyr.h[octave];
+    *octave_images_width = pyr.w[octave];
+    *octave_images_height = pyr.h[octave];
   }
 
   static void download_layer(vksift_Instance inst, const uint8_t octave, const uint8_t scale, bool dog, float *out, const char *fn)
   {
     const uint32_t nscales = inst->cfg.nb_scales_per_octave + (dog ? 2u : 3u);
-    if (octave >= inst->pyr.n_oct || scale >= nscales)
+    const Pyramid &p = last_lane(inst)->pyr;
+    if (octave >= p.n_oct || scale >= nscales)
     {
-      if (octave >= inst->pyr.n_oct)
-        LOGE(TAG, "Requested octave idx is %d but the current number of octaves is %d", octave, inst->pyr.n_oct);
+      if (octave >= p.n_oct)
+        LOGE(TAG, "Requested octave idx is %d but the current number of octaves is %d", octave, p.n_oct);
       else
         LOGE(TAG, "Requested scale idx is %d but the number of %s scales is %d", scale, dog ? "DoG" : "blurred", nscales);
       LOGE(TAG, "%s() error: invalid input.", fn);
@@ -1529,7 +1626,6 @@ extern "C"
     {
       DeviceGuard g(inst->device);
       wait_pipelines(inst, true, false);
-      const Pyramid &p = inst->pyr;
       const size_t layer = (size_t)p.pitch[octave] * p.h[octave];
       const float *src = (dog ? p.D[octave] : p.G[octave]) + layer * scale;
       auto run = [&]() -> bool {
@@ -1572,6 +1668,17 @@ extern "C"
     DeviceGuard g(inst->device);
     wait_pipelines(inst, true, true);
     cudaStreamSynchronize(inst->stream);
+  }
+
+  uint32_t vksiftx_getLaneCount(vksift_Instance inst) { return (uint32_t)inst->lanes.size(); }
+
+  void vksiftx_joinLanes(vksift_Instance inst)
+  {
+    /* device-side join: work enqueued on the instance stream after this call starts after every enqueued detection */
+    DeviceGuard g(inst->device);
+    for (size_t k = 1; k < inst->lanes.size(); k++)
+      if (inst->lanes[k]->detect_pending)
+        cudaStreamWaitEvent(inst->stream, inst->lanes[k]->ev_detect_done, 0);
   }
 
   void vksiftx_getBufferDeviceView(vksift_Instance inst, const uint32_t gpu_buffer_id, uint32_t *nb_feats, void **d_descriptors, void **d_heads)
@@ -1642,11 +1749,14 @@ extern "C"
 
   void vksiftx_setProfiling(vksift_Instance inst, const bool enabled)
   {
-    inst->profiling = enabled;
     const char *t = getenv("VKSIFT_TRACE");
-    if (t && t[0] == '1')
-      inst->trace = enabled;
-    inst->trace_dump_stderr = (t && t[0] == '1');
+    for (vksift_Instance lane : inst->lanes)
+    {
+      lane->profiling = enabled;
+      if (t && t[0] == '1')
+        lane->trace = enabled;
+      lane->trace_dump_stderr = (t && t[0] == '1');
+    }
   }
 
   uint32_t vksiftx_matchFeaturesCrossChecked(vksift_Instance inst, const uint32_t gpu_buffer_id_A, const uint32_t gpu_buffer_id_B,
@@ -1710,21 +1820,28 @@ extern "C"
   void vksiftx_setSerialSchedule(vksift_Instance inst, const bool enabled)
   {
     wait_pipelines(inst, true, true);
-    inst->serial = enabled;
-    invalidate_graphs(inst);
+    for (vksift_Instance lane : inst->lanes)
+    {
+      lane->serial = enabled;
+      invalidate_graphs(lane);
+    }
   }
 
   void vksiftx_setLaunchTrace(vksift_Instance inst, const bool enabled)
   {
-    inst->trace = enabled;
-    if (enabled)
-      inst->profiling = true; /* the trace is relative to the detection's start event */
+    for (vksift_Instance lane : inst->lanes)
+    {
+      lane->trace = enabled;
+      if (enabled)
+        lane->profiling = true; /* the trace is relative to the detection's start event */
+    }
   }
 
   uint32_t vksiftx_getLaunchTrace(vksift_Instance inst, char (*names)[32], float *start_us, float *end_us, const uint32_t capacity)
   {
     DeviceGuard g(inst->device);
     wait_pipelines(inst, true, true);
+    inst = last_lane(inst); /* the most recent detection */
     if (!inst->ev_detect_valid)
       return 0;
     cudaEventSynchronize(inst->ev[EV_D4]);
@@ -1747,6 +1864,8 @@ extern "C"
     wait_pipelines(inst, true, true);
     for (int i = 0; i < VKSIFTX_NB_STAGES; i++)
       t[i] = 0.f;
+    vksift_Instance primary = inst;
+    inst = last_lane(inst); /* detection stages: the most recent detection */
     if (inst->ev_detect_valid)
     {
       cudaEventSynchronize(inst->ev[EV_D4]);
@@ -1767,6 +1886,7 @@ extern "C"
       cudaEventElapsedTime(&t[3], inst->ev[EV_D3], inst->ev[EV_D4]);
       cudaEventElapsedTime(&t[4], inst->ev[EV_D0], inst->ev[EV_D4]);
     }
+    inst = primary;
     if (inst->ev_match_valid)
     {
       cudaEventSynchronize(inst->ev[EV_M2]);
@@ -1776,7 +1896,13 @@ extern "C"
     }
   }
 
-  uint64_t vksiftx_getKernelLaunchCount(vksift_Instance inst) { return inst->launches; }
+  uint64_t vksiftx_getKernelLaunchCount(vksift_Instance inst)
+  {
+    uint64_t n = inst->launches;
+    for (size_t k = 1; k < inst->lanes.size(); k++)
+      n += inst->lanes[k]->launches;
+    return n;
+  }
 
   void vksiftx_getEffectiveTaps(vksift_Instance inst, uint32_t *radius, float *taps)
   {

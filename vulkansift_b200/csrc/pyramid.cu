@@ -937,6 +937,19 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) octave_fused_kernel(const __gri
   const int wi = tid >> 5, lane = tid & 31;
   const int t = (int)blockIdx.x;
   const int x0 = (t % P.tiles_x) * FZ_T, y0 = (t / P.tiles_x) * FZ_T;
+#ifdef VKS_FUSED_TIMING
+  unsigned long long tm[12];
+  int ntm = 0;
+#define FZ_MARK()                                                                                                                                    \
+  {                                                                                                                                                  \
+    unsigned long long t__;                                                                                                                          \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                                                                        \
+    tm[ntm++] = t__;                                                                                                                                 \
+  }
+#else
+#define FZ_MARK()
+#endif
+  FZ_MARK();
   int halo = 0;
   for (int k = 0; k < P.n_layers; k++)
     halo += P.radius[k];
@@ -965,6 +978,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) octave_fused_kernel(const __gri
     }
   }
   __syncthreads();
+  FZ_MARK();
   int lo = 0; /* the region of the current source is [lo, lo+n)^2 in buffer cells */
 #pragma unroll 1
   for (int k = 0; k < P.n_layers; k++)
@@ -987,6 +1001,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) octave_fused_kernel(const __gri
         mid[r * FZ_WB + c] = acc;
       }
     __syncthreads();
+    FZ_MARK();
     /* vertical over [lo+R, lo+R+n)^2, plus the global stores of the pixels that lie in the tile core and in the image */
     {
       float *gl = P.g0 + (size_t)k * P.layer_stride;
@@ -1026,11 +1041,21 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) octave_fused_kernel(const __gri
       }
     }
     __syncthreads();
+    FZ_MARK();
     float *tmp = cur;
     cur = nxt;
     nxt = tmp;
     lo += R;
   }
+#ifdef VKS_FUSED_TIMING
+  if (blockIdx.x == 0 && tid == 0 && P.w < 100)
+  {
+    printf("fused timing (ns) w=%d layers=%d:", P.w, P.n_layers);
+    for (int i = 1; i < ntm; i++)
+      printf(" %llu", tm[i] - tm[0]);
+    printf("\n");
+  }
+#endif
 }
 
 /* launch with programmatic stream serialization: the kernel may be scheduled before the previous kernel of the
