@@ -217,12 +217,13 @@ def test_c2_full_size_matches_oracle(api, oracle_mod):
     inst.close()
 
 
-@pytest.mark.parametrize("env", ["VKSIFT_MEGA", "VKSIFT_GRAPH", "VKSIFT_NO_SPLIT", "VKSIFT_NO_PDL"])
+@pytest.mark.parametrize("env", ["VKSIFT_MEGA=1", "VKSIFT_GRAPH=1", "VKSIFT_GRAPH=0", "VKSIFT_NO_SPLIT=1", "VKSIFT_NO_PDL=1"])
 def test_alternative_schedules_are_bit_exact(api, oracle_mod, env, monkeypatch):
     """The scale space can be scheduled four ways (per-layer launches = default, one persistent dataflow kernel, CUDA-graph
-    replay, no stage overlap / no programmatic dependent launch): same kernels, same bytes out."""
+    replay (the default with several lanes) or eager launches, no stage overlap / no programmatic dependent launch): same
+    kernels, same bytes out."""
     from vulkansift_b200.synth import blob_image
-    monkeypatch.setenv(env, "1")
+    monkeypatch.setenv(*env.split("="))
     imgs = [blob_image(640, 480, 400, seed=11), blob_image(1000, 700, 600, seed=12)]
     for img in imgs:
         with api.Instance() as inst:

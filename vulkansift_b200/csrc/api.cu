@@ -714,17 +714,31 @@ bool create_resources(vksift_Instance inst)
   CU_TRY(cudaMalloc(&inst->d_image, inst->max_image_size));
   CU_TRY(cudaHostAlloc(&inst->h_src_slot, sizeof(void *), cudaHostAllocDefault));
   CU_TRY(cudaMalloc(&inst->d_src_slot, sizeof(void *)));
+  /* detection lanes: VKSIFT_LANES overrides the default of one lane per feature buffer, at most 4 */
+  uint32_t n_lanes = c.sift_buffer_count < 4u ? c.sift_buffer_count : 4u;
+  if (const char *e = getenv("VKSIFT_LANES"))
   {
-    /* Two alternative schedules of the same kernels, off by default because they measured slower on B200:
-     * VKSIFT_MEGA=1: the whole scale space as one persistent dataflow launch instead of per-layer launches.
-     * VKSIFT_GRAPH=1: replay of the detection as a CUDA graph (per-layer path only: the persistent kernel takes a
-     * new epoch per launch). */
+    const long v = strtol(e, nullptr, 10);
+    if (v >= 1)
+      n_lanes = (uint32_t)v < c.sift_buffer_count ? (uint32_t)v : c.sift_buffer_count;
+  }
+  {
+    /* Alternative schedules of the same kernels (measurements in DESIGN.md):
+     * VKSIFT_MEGA=1: the whole scale space as one persistent dataflow launch instead of per-layer launches (slower).
+     * VKSIFT_GRAPH=0/1: replay of the detection as a CUDA graph, the analogue of the reference's pre-recorded command
+     * buffer.  A replay costs 8 us of CPU time instead of 210 us but loses the programmatic-dependent-launch edges and
+     * the stream priorities, so one detection alone is ~20 us slower; with several lanes the throughput is what counts
+     * and the replay wins (0.315 against 0.321 ms per 1920x1080 image), so it is the default exactly then. */
     const char *g = getenv("VKSIFT_GRAPH");
     const char *m = getenv("VKSIFT_MEGA");
     inst->use_mega = (m && m[0] == '1');
     const char *nsp = getenv("VKSIFT_NO_SPLIT");
     inst->no_split = (nsp && nsp[0] == '1');
-    inst->use_graph = (g && g[0] == '1') && !inst->use_mega;
+    if (inst->use_mega)
+      n_lanes = 1; /* the persistent kernel takes a new epoch per launch */
+    inst->use_graph = (g ? g[0] == '1' : n_lanes > 1) && !inst->use_mega;
+    if (inst->primary)
+      inst->use_graph = inst->primary->use_graph;
   }
 
   const size_t maxf = c.max_nb_sift_per_buffer;
@@ -773,16 +787,6 @@ bool create_resources(vksift_Instance inst)
     return false;
   for (auto &fb : inst->own_buffers)
     update_buffer_sections(inst, fb);
-  /* detection lanes: VKSIFT_LANES overrides the default of one lane per feature buffer, at most 4 */
-  uint32_t n_lanes = c.sift_buffer_count < 4u ? c.sift_buffer_count : 4u;
-  if (const char *e = getenv("VKSIFT_LANES"))
-  {
-    const long v = strtol(e, nullptr, 10);
-    if (v >= 1)
-      n_lanes = (uint32_t)v < c.sift_buffer_count ? (uint32_t)v : c.sift_buffer_count;
-  }
-  if (inst->use_mega)
-    n_lanes = 1;
   inst->lanes.push_back(inst);
   for (uint32_t k = 1; k < n_lanes; k++)
   {
