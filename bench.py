@@ -344,39 +344,31 @@ def main():
     clocks = sampler.stop()
 
     # ---------------- small images (configs[2] pattern: 640x480, 8 images per GPU) ----------------
-    # One vksift instance keeps one pipeline in flight (reference semantics), which leaves a B200 mostly idle on a
-    # 640x480 image; several instances on one GPU overlap their pipelines.  Reported, not the headline.
+    # One 640x480 detection leaves a B200 mostly idle; an instance with 8 feature buffers runs 8 detection lanes, so the 8
+    # images of a GPU's share overlap.  Reported, not the headline.
     from vulkansift_b200.synth import C1
     small = [blob_image(**dict(C1, seed=C1["seed"] + i)) for i in range(8)]
     d_small = [torch.from_numpy(im).cuda() for im in small]
     sh_, sw_ = small[0].shape
     small_res = {}
-    for n_inst in (1, 4):
-        insts = [api.Instance(gpu_device_index=local_rank, input_image_max_size=sw_ * sh_, max_nb_sift_per_buffer=20000) for _ in range(n_inst)]
+    for n_buf in (1, 8):
+        sinst = api.Instance(gpu_device_index=local_rank, input_image_max_size=sw_ * sh_, max_nb_sift_per_buffer=20000, sift_buffer_count=n_buf)
         for rep in range(3):
             for i in range(8):
-                insts[i % n_inst].detect_device(d_small[i].data_ptr(), sw_, sh_, 0)
-        for it in insts:
-            it.wait_idle()
-        nf_small = 0
+                sinst.detect_device(d_small[i].data_ptr(), sw_, sh_, i % n_buf)
+        sinst.wait_idle()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        reps = 10
+        reps = 20
         for rep in range(reps):
             for i in range(8):
-                insts[i % n_inst].detect_device(d_small[i].data_ptr(), sw_, sh_, 0)
-        for it in insts:
-            it.wait_idle()
-        torch.cuda.synchronize()
+                sinst.detect_device(d_small[i].data_ptr(), sw_, sh_, i % n_buf)
+        sinst.wait_idle()
         dt = time.perf_counter() - t0
-        if n_inst == 1:
-            for i in range(8):
-                insts[0].detect_device(d_small[i].data_ptr(), sw_, sh_, 0)
-                nf_small += insts[0].features_number(0)
-            small_res["features_per_8_images"] = nf_small
-        small_res["images_per_s_%d_instance%s" % (n_inst, "" if n_inst == 1 else "s")] = 8 * reps / dt
-        for it in insts:
-            it.close()
+        if n_buf == 8:
+            small_res["features_per_8_images"] = sum(sinst.features_number(i) for i in range(8))
+        small_res["images_per_s_%d_lane%s" % (sinst.lane_count(), "" if n_buf == 1 else "s")] = 8 * reps / dt
+        sinst.close()
 
     # ---------------- matcher (configs[3]) ----------------
     da, db = random_descriptors(MATCH_N, 1234), random_descriptors(MATCH_N, 1235)
@@ -480,7 +472,7 @@ def main():
                                    "flops": flops, "peak_source": peak_src + " bf16 dense burst (i8 operands run at 2x this rate)"}},
             "clocks": clocks,
             "small_images": dict(small_res, workload="configs[2] pattern on one GPU: 8 x 640x480 (upsampled, default config), images resident in "
-                                                     "HBM, wall clock over 10 rounds; N > 1: every rank does the same (weak scaling)"),
+                                                     "HBM, wall clock over 20 rounds; N > 1: every rank does the same (weak scaling)"),
         }
         line["config"]["schedule"] = ("%d feature buffers = %d detection lanes (own scale space each, 0.5 GB): a detection waits for the "
                                       "previous one of its lane only, consecutive images overlap on the GPU" % (NBUF, inst.lane_count()))

@@ -37,7 +37,7 @@ extern "C"
   VKSIFT_EXPORT void vksiftx_waitIdle(vksift_Instance instance);
 
   /* Detection lanes.  The reference makes vksift_detectFeatures wait for the previous detection because the instance owns
-   * one scale space and one command buffer (vulkansift.c:326-327).  This build gives the instance min(sift_buffer_count, 4)
+   * one scale space and one command buffer (vulkansift.c:326-327).  This build gives the instance min(sift_buffer_count, 8)
    * lanes (environment override VKSIFT_LANES=n), each with its own scale space, scratch memory and streams; a detection
    * into buffer b runs on lane b % lanes and waits for that lane only, so detections into different buffers overlap on the
    * GPU.  Results are identical to the one-lane schedule.  vksift_getScaleSpace* / vksift_download*Image show the scale

@@ -714,8 +714,9 @@ bool create_resources(vksift_Instance inst)
   CU_TRY(cudaMalloc(&inst->d_image, inst->max_image_size));
   CU_TRY(cudaHostAlloc(&inst->h_src_slot, sizeof(void *), cudaHostAllocDefault));
   CU_TRY(cudaMalloc(&inst->d_src_slot, sizeof(void *)));
-  /* detection lanes: VKSIFT_LANES overrides the default of one lane per feature buffer, at most 4 */
-  uint32_t n_lanes = c.sift_buffer_count < 4u ? c.sift_buffer_count : 4u;
+  /* detection lanes: VKSIFT_LANES overrides the default of one lane per feature buffer, at most 8
+   * (1920x1080: 0.45 / 0.35 / 0.315 / 0.309 ms per image with 1 / 2 / 4 / 8 lanes; 640x480: 0.224 / 0.119 / 0.080 / 0.070) */
+  uint32_t n_lanes = c.sift_buffer_count < 8u ? c.sift_buffer_count : 8u;
   if (const char *e = getenv("VKSIFT_LANES"))
   {
     const long v = strtol(e, nullptr, 10);

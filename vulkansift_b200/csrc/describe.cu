@@ -185,7 +185,15 @@ __global__ void __launch_bounds__(ORI_THREADS) orientation_kernel(const __grid_c
 
 cudaError_t launch_orientation(const DetectParams &P, DetectCounters *cnt, const FeatHead *prim, float *ori, uint32_t *n_ori, cudaStream_t st)
 {
-  orientation_kernel<<<148 * 8, ORI_THREADS, 0, st>>>(P, cnt, prim, ori, n_ori);
+  static int per_sm = 0;
+  if (per_sm == 0)
+  {
+    const char *e = getenv("VKSIFT_ORI_CTAS");
+    per_sm = e ? atoi(e) : 8;
+    if (per_sm < 1 || per_sm > 16)
+      per_sm = 8;
+  }
+  orientation_kernel<<<148 * per_sm, ORI_THREADS, 0, st>>>(P, cnt, prim, ori, n_ori);
   return cudaGetLastError();
 }
 
@@ -569,7 +577,15 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
 cudaError_t launch_descriptors(const DetectParams &P, DetectCounters *cnt, const float *m_table, const FeatHead *prim, const float *ori,
                                const uint32_t *feat_src, FeatHead *out_heads, uint8_t *out_desc, cudaStream_t st)
 {
-  descriptor_kernel<<<148 * 8, DESC_THREADS, 0, st>>>(P, cnt, m_table, prim, ori, feat_src, out_heads, out_desc);
+  static int per_sm = 0;
+  if (per_sm == 0)
+  {
+    const char *e = getenv("VKSIFT_DESC_CTAS");
+    per_sm = e ? atoi(e) : 8;
+    if (per_sm < 1 || per_sm > 16)
+      per_sm = 8;
+  }
+  descriptor_kernel<<<148 * per_sm, DESC_THREADS, 0, st>>>(P, cnt, m_table, prim, ori, feat_src, out_heads, out_desc);
   return cudaGetLastError();
 }
 

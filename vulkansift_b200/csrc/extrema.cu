@@ -117,6 +117,7 @@ __device__ bool refine_keypoint(const DetectParams &P, const OctaveView &ov, int
 #define EX_SW 256 /* smem row: columns x0-4 .. x0+251.  TMA moves a box row by row at a fixed cost per row, so rows
                      are made as long as a box allows (256 elements = 1 KB): 72-float rows measured 6 B/clk/SM */
 #define EX_SH (EX_TH + 2)
+#define EX_THREADS_DEFAULT 512 /* 256 columns x 2 row groups (VKSIFT_EX_THREADS=256: one thread per column of 8 rows) */
 
 struct ExtremaMaps
 {
@@ -141,9 +142,11 @@ __device__ __forceinline__ bool extrema_tile_coords(const DetectParams &P, int t
   return false;
 }
 
-__global__ void __launch_bounds__(256) extrema_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ ExtremaMaps maps, int t_begin,
+template <int EX_THREADS>
+__global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ ExtremaMaps maps, int t_begin,
                                                       int n_tiles, unsigned long long *__restrict__ raw, DetectCounters *__restrict__ cnt)
 {
+  constexpr int EX_RPT = EX_TH / (EX_THREADS / 256); /* rows per thread */
   extern __shared__ __align__(128) float ex_smem[];
   __shared__ __align__(8) uint64_t s_bar[2];
   const int ns = P.ns, nl = P.ns + 2;
@@ -190,24 +193,24 @@ __global__ void __launch_bounds__(256) extrema_kernel(const __grid_constant__ De
 
     const OctaveView &ov = P.oct[o];
     const float *tile = ex_smem + cur * buf_floats;
-    const int lx = tid, ly = 0; /* one column of 8 rows per thread */
+    const int lx = tid & 255, ly = (tid >> 8) * EX_RPT; /* one column of EX_RPT rows per thread */
     const int x = x0 + lx;
     const int ow = ov.w, oh = ov.h;
     if (lx < EX_TW && x >= 1 && x < ow - 1)
     {
       /* rows of this thread that are inside [1, h-2] */
-      const int r_lo = max(0, 1 - (y0 + ly)), r_hi = min(8, (oh - 1) - (y0 + ly));
+      const int r_lo = max(0, 1 - (y0 + ly)), r_hi = min(EX_RPT, (oh - 1) - (y0 + ly));
       for (int s = 1; s <= ns; s++)
       {
         const float *col = tile + (s * EX_SH + ly + 1) * EX_SW + (lx + 4);
-        /* prefilter all 8 centre values first (independent loads), then visit only the survivors */
-        float cv[8];
+        /* prefilter all centre values first (independent loads), then visit only the survivors */
+        float cv[EX_RPT];
 #pragma unroll
-        for (int r = 0; r < 8; r++)
+        for (int r = 0; r < EX_RPT; r++)
           cv[r] = col[r * EX_SW];
         uint32_t mask = 0;
 #pragma unroll
-        for (int r = 0; r < 8; r++)
+        for (int r = 0; r < EX_RPT; r++)
           mask |= (fabsf(cv[r]) > prefilter && r >= r_lo && r < r_hi) ? (1u << r) : 0u;
         while (mask)
         {
@@ -331,11 +334,19 @@ cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, unsigne
   if (smem > 220 * 1024)
     return cudaErrorInvalidConfiguration; /* nb_scales_per_octave too large for the double-buffered tile */
   static bool attr_done[64] = {false};
+  static int threads = 0;
+  if (threads == 0)
+  {
+    const char *e = getenv("VKSIFT_EX_THREADS");
+    threads = (e && atoi(e) == 256) ? 256 : EX_THREADS_DEFAULT;
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_done[dev])
   {
-    cudaError_t e = cudaFuncSetAttribute(extrema_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(extrema_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(extrema_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess)
       return e;
     attr_done[dev] = true;
@@ -345,7 +356,10 @@ cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, unsigne
   int grid = sms * (per_sm > 2 ? 2 : per_sm);
   if (grid > t_end - t_begin)
     grid = t_end - t_begin;
-  extrema_kernel<<<grid, 256, smem, st>>>(P, pl->maps, t_begin, t_end, raw, cnt);
+  if (threads == 256)
+    extrema_kernel<256><<<grid, 256, smem, st>>>(P, pl->maps, t_begin, t_end, raw, cnt);
+  else
+    extrema_kernel<512><<<grid, 512, smem, st>>>(P, pl->maps, t_begin, t_end, raw, cnt);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
