@@ -248,7 +248,7 @@ def main():
     K, W = args.steps, max(3, args.warmup)
     images = workload_images()
     h, w = images[0].shape
-    NBUF = int(os.environ.get("VKSIFT_BENCH_BUFFERS", "4"))  # feature buffers = detection lanes (the default config has 2)
+    NBUF = int(os.environ.get("VKSIFT_BENCH_BUFFERS", "8"))  # feature buffers = detection lanes (the default config has 2)
     inst = api.Instance(gpu_device_index=local_rank, input_image_max_size=w * h, sift_buffer_count=NBUF)
     stream = torch.cuda.ExternalStream(inst.stream, device=local_rank)
     d_images = [torch.from_numpy(im).cuda() for im in images]
@@ -261,7 +261,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident detection (value) ----------------
-    for i in range(W):
+    for i in range(max(W, 3 * NBUF)):  # every lane captures its CUDA graph on the second use of a buffer
         inst.detect_device(d_images[i % N_IMAGES].data_ptr(), w, h, i % NBUF)
     inst.wait_idle()
     counts = {}
@@ -335,7 +335,7 @@ def main():
                 nbytes += f.nbytes + 4
         return feats, nbytes
 
-    e2e_loop(max(3, NBUF))
+    e2e_loop(3 * NBUF)
     barrier()
     t0 = time.perf_counter()
     e2e_feat, d2h = e2e_loop(K)
@@ -416,7 +416,7 @@ def main():
         for rep in range(reps + 1):
             barrier()
             t0 = time.perf_counter()
-            counts_g, blocks_g = vdist.gather_instance_descriptors(inst, 0)
+            counts_g, blocks_g = vdist.gather_instance_descriptors(inst, 0, capacity=8191)  # 8192-row slots: 1 MB per rank
             torch.cuda.synchronize()
             t1 = time.perf_counter()
             vdist.match_against_peers(inst, 0, 1, counts_g, blocks_g, rank, world, download=True)

@@ -49,7 +49,7 @@ extern "C"
 
   /* Packed device view of a feature buffer: n descriptors [n][128] u8 (row
    * pitch 128 B) and n 36-byte feature heads (the vksift_Feature fields before
-   * `descriptor`).  Waits for the buffer; pointers stay valid until the next
+   * `descriptor`).  Read-only (the matcher caches per-buffer norms).  Waits for the buffer; pointers stay valid until the next
    * detect/upload on it.  Any out pointer may be NULL. */
   VKSIFT_EXPORT void vksiftx_getBufferDeviceView(vksift_Instance instance, const uint32_t gpu_buffer_id, uint32_t *nb_feats, void **d_descriptors,
                                                  void **d_heads);
@@ -65,6 +65,13 @@ extern "C"
    * e.g. the send slot of an NCCL all-gather); rows past the feature count are zero-filled up to
    * `capacity`.  Returns the feature count.  Blocking like the other transfer functions. */
   VKSIFT_EXPORT uint32_t vksiftx_copyDescriptorsToDevice(vksift_Instance instance, const uint32_t gpu_buffer_id, void *d_dst, const uint32_t capacity);
+
+  /* vksift_matchFeatures with the B side read in place from caller-owned device memory ([nb_feats_B][128] u8, 128-byte
+   * aligned, e.g. a peer's block inside the receive buffer of the NCCL descriptor all-gather): no copy into a feature
+   * buffer.  Same result records, tie rule, asynchrony and error behaviour as vksift_matchFeatures; the memory must stay
+   * valid until the match has been downloaded. */
+  VKSIFT_EXPORT void vksiftx_matchFeaturesAgainstDevice(vksift_Instance instance, const uint32_t gpu_buffer_id_A, const void *d_descriptors_B,
+                                                        const uint32_t nb_feats_B);
 
   /* Device pointer of the last match result: vksift_getMatchesNumber() rows of vksift_Match_2NN. */
   VKSIFT_EXPORT void *vksiftx_getMatchesDevice(vksift_Instance instance);

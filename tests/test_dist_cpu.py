@@ -35,6 +35,12 @@ def _worker(rank, world, port, out_dir):
     assert counts == [37, 101] and tuple(blocks.shape) == (2, 101, 128)
     assert np.array_equal(blocks[rank, :n].numpy(), desc)
     assert int(blocks[0, 37:].sum()) == 0  # padding rows are zero
+    # single-collective form: fixed-capacity slots with the count in the last row
+    counts1, blocks1 = exchange_descriptor_blocks(torch.from_numpy(desc), capacity=128)
+    assert counts1 == [37, 101] and tuple(blocks1.shape) == (2, 129, 128)
+    for j in range(2):
+        assert torch.equal(blocks1[j, :counts1[j]], blocks[j, :counts[j]])
+        assert int(blocks1[j, counts1[j]:128].sum()) == 0
     res = {}
     for j in all_pairs_schedule(rank, world):
         peer = blocks[j, :counts[j]].numpy()

@@ -167,3 +167,29 @@ def test_cross_checked_matcher_equals_the_reference_callers_loop(api):
         assert [tuple(int(v) for v in r) for r in got] == exp
         # the retained match list is the A->B one
         assert inst.download_matches().tobytes() == m12.tobytes()
+
+
+@pytest.mark.parametrize("shape", [(700, 2), (1000, 777), (3000, 3100)])
+def test_match_against_device_descriptors_in_place(api, oracle_mod, shape):
+    """vksiftx_matchFeaturesAgainstDevice: B read in place from caller-owned device memory (a peer's block of the NCCL
+    all-gather) gives the records vksift_matchFeatures gives for the same B in a feature buffer."""
+    import torch
+    from vulkansift_b200.synth import random_descriptors
+    na, nb = shape
+    da, db = random_descriptors(na, 300 + na), random_descriptors(nb, 400 + nb)
+    inst = api.Instance(max_nb_sift_per_buffer=4096)
+    inst.upload_features(_feats(api, da), 0)
+    slot = torch.zeros((2, 4096, 128), dtype=torch.uint8, device="cuda")  # B sits in the second slot, exactly nb rows used
+    slot[1, :nb] = torch.from_numpy(db).cuda()
+    slot[1, nb:] = 255  # rows past nb must never be read as candidates
+    torch.cuda.synchronize()
+    inst.match_against_device(0, slot[1].data_ptr(), nb)
+    got = inst.download_matches()
+    _check(got, oracle_mod.match_descriptors(da, db), "in place %s" % (shape,))
+    with pytest.raises(api.VksiftError) as e:
+        inst.match_against_device(0, slot[1].data_ptr() + 64, nb)
+    assert e.value.code == api.VKSIFT_INVALID_INPUT_ERROR
+    with pytest.raises(api.VksiftError) as e:
+        inst.match_against_device(0, slot[1].data_ptr(), 1)
+    assert e.value.code == api.VKSIFT_INVALID_INPUT_ERROR
+    inst.close()

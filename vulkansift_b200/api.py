@@ -99,6 +99,7 @@ def _load_library():
         "vksiftx_uploadDescriptorsDevice": (None, [I, C.c_void_p, u32, u32]),
         "vksiftx_copyDescriptorsToDevice": (u32, [I, u32, C.c_void_p, u32]),
         "vksiftx_getMatchesDevice": (C.c_void_p, [I]),
+        "vksiftx_matchFeaturesAgainstDevice": (None, [I, u32, C.c_void_p, u32]),
         "vksiftx_setProfiling": (None, [I, C.c_bool]),
         "vksiftx_getStageTimesMs": (None, [I, P(C.c_float)]),
         "vksiftx_matchFeaturesCrossChecked": (C.c_uint32, [I, C.c_uint32, C.c_uint32, C.c_float, P(C.c_uint32), C.c_uint32]),
@@ -307,6 +308,11 @@ class Instance:
         n = lib.vksiftx_copyDescriptorsToDevice(self._h, buffer_id, dev_ptr, capacity)
         self._check("vksiftx_copyDescriptorsToDevice")
         return n
+
+    def match_against_device(self, buffer_a, dev_ptr, n_b):
+        """2-NN of buffer_a's features against n_b descriptors read in place from device memory."""
+        lib.vksiftx_matchFeaturesAgainstDevice(self._h, buffer_a, dev_ptr, n_b)
+        self._check("vksiftx_matchFeaturesAgainstDevice")
 
     def matches_device(self):
         return lib.vksiftx_getMatchesDevice(self._h)

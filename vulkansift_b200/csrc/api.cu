@@ -55,6 +55,12 @@ struct FeatureBuffer
   uint32_t cur_w = 0, cur_h = 0;
   bool uploaded = false; /* content came from vksift_uploadFeatures (is_packed in the reference) */
   uint32_t n_uploaded = 0;
+  /* |d|^2 of the descriptors in the two forms the matcher reads (A side plain, B side packed), computed by the first match
+   * that uses the buffer and kept until its content changes: matching one image against many (all-pairs) or the same pair
+   * repeatedly does not recompute them */
+  uint32_t *norm_plain = nullptr, *norm_packed = nullptr;
+  bool norms_valid = false;
+  uint32_t norms_n = 0;
 };
 
 struct Pyramid
@@ -613,6 +619,8 @@ void destroy_instance(vksift_Instance inst)
     cudaFree(fb.heads);
     cudaFree(fb.desc);
     cudaFree(fb.cnt);
+    cudaFree(fb.norm_plain);
+    cudaFree(fb.norm_packed);
     if (fb.host_counts)
       cudaFreeHost(fb.host_counts);
   }
@@ -779,6 +787,8 @@ bool create_resources(vksift_Instance inst)
     CU_TRY(cudaMemset(fb.desc, 0, 128 * (maxf + 256)));
     CU_TRY(cudaMalloc(&fb.cnt, sizeof(DetectCounters)));
     CU_TRY(cudaMemset(fb.cnt, 0, sizeof(DetectCounters)));
+    CU_TRY(cudaMalloc(&fb.norm_plain, sizeof(uint32_t) * (maxf + 256)));
+    CU_TRY(cudaMalloc(&fb.norm_packed, sizeof(uint32_t) * (maxf + 256)));
     CU_TRY(cudaHostAlloc(&fb.host_counts, sizeof(uint32_t) * (1 + 2 * VKS_MAX_OCT), cudaHostAllocMapped));
     memset(fb.host_counts, 0, sizeof(uint32_t) * (1 + 2 * VKS_MAX_OCT));
     CU_TRY(cudaHostGetDevicePointer(&fb.host_counts_dev, fb.host_counts, 0));
@@ -1054,7 +1064,8 @@ bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t bu
   cudaStream_t st = inst->stream;
   *inst->h_src_slot = d_image;
   auto &g = inst->graphs[buf];
-  const bool want_graph = inst->use_graph && !inst->trace;
+  /* stage profiling and launch tracing are analysis modes of the eager schedule (the one a single-lane instance runs) */
+  const bool want_graph = inst->use_graph && !inst->trace && !inst->profiling;
   if (g.exec && (g.prof != inst->profiling || !want_graph))
   {
     cudaGraphExecDestroy(g.exec);
@@ -1101,6 +1112,7 @@ bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t bu
   inst->detect_pending = true;
   inst->detect_buffer = buf;
   fb.uploaded = false;
+  fb.norms_valid = false;
   return true;
 }
 
@@ -1467,6 +1479,7 @@ extern "C"
         fb.uploaded = true;
         fb.n_uploaded = nb_feats;
       }
+      fb.norms_valid = false;
     }
     if (!ok)
     {
@@ -1504,6 +1517,7 @@ extern "C"
         fb.uploaded = true;
         fb.n_uploaded = nb_feats;
       }
+      fb.norms_valid = false;
     }
     if (!ok)
     {
@@ -1512,35 +1526,53 @@ extern "C"
     }
   }
 
-  void vksift_matchFeatures(vksift_Instance inst, const uint32_t gpu_buffer_id_A, const uint32_t gpu_buffer_id_B)
+  static bool ensure_norms(vksift_Instance inst, FeatureBuffer &fb, uint32_t n)
   {
-    if (!buffer_idx_valid(inst, gpu_buffer_id_A) || !buffer_idx_valid(inst, gpu_buffer_id_B))
-    {
-      LOGE(TAG, "vksift_matchFeatures() error: invalid input.");
-      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
-      return;
-    }
+    if (fb.norms_valid && fb.norms_n == n)
+      return true;
+    CU_TRY(launch_norms(fb.desc, n, fb.norm_plain, fb.norm_packed, inst->stream));
+    inst->launches++;
+    fb.norms_valid = true;
+    fb.norms_n = n;
+    return true;
+  }
+
+  /* shared by vksift_matchFeatures and vksiftx_matchFeaturesAgainstDevice: B is a feature buffer or caller-owned descriptors */
+  static void match_common(vksift_Instance inst, const uint32_t gpu_buffer_id_A, const uint32_t gpu_buffer_id_B, const uint8_t *d_desc_b,
+                           const uint32_t nb_ext, const char *fn)
+  {
     bool ok = true, invalid = false;
     {
       DeviceGuard g(inst->device);
       wait_pipelines(inst, true, true); /* vulkansift.c:427-428 */
       const uint32_t na = buffer_count(inst, gpu_buffer_id_A, false);
-      const uint32_t nb = buffer_count(inst, gpu_buffer_id_B, false);
+      const uint32_t nb = d_desc_b ? nb_ext : buffer_count(inst, gpu_buffer_id_B, false);
       if (nb < 2 && na > 0)
       {
         /* the shader reads B[0] and B[1] unconditionally (Get2NearestNeighbors.comp:66-67), SURVEY B-D13 */
-        LOGE(TAG, "vksift_matchFeatures() error: buffer B holds %u feature(s), the 2-nearest-neighbour search needs at least 2.", nb);
+        LOGE(TAG, "%s() error: buffer B holds %u feature(s), the 2-nearest-neighbour search needs at least 2.", fn, nb);
         invalid = true;
       }
       else
       {
         inst->nb_matches = na; /* sift_memory.c:1056 */
-        FeatureBuffer &A = inst->buffers[gpu_buffer_id_A], &B = inst->buffers[gpu_buffer_id_B];
+        FeatureBuffer &A = inst->buffers[gpu_buffer_id_A];
+        const uint8_t *b_desc = d_desc_b ? d_desc_b : inst->buffers[gpu_buffer_id_B].desc;
         auto run = [&]() -> bool {
           const bool prof = inst->profiling;
           if (prof)
             CU_TRY(cudaEventRecord(inst->ev[EV_M0], inst->stream));
-          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, B.desc, nb, inst->d_matches, inst->stream,
+          if (na > 0 && !ensure_norms(inst, A, na))
+            return false;
+          const uint32_t *nb_cached = nullptr;
+          if (na > 0 && !d_desc_b)
+          {
+            FeatureBuffer &B = inst->buffers[gpu_buffer_id_B];
+            if (!ensure_norms(inst, B, nb))
+              return false;
+            nb_cached = B.norm_packed;
+          }
+          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, A.norm_plain, b_desc, nb, nb_cached, inst->d_matches, inst->stream,
                               prof ? inst->ev[EV_M1] : nullptr, &inst->launches));
           if (prof)
           {
@@ -1555,7 +1587,7 @@ extern "C"
         ok = run();
         inst->match_pending = ok;
         inst->match_a = gpu_buffer_id_A;
-        inst->match_b = gpu_buffer_id_B;
+        inst->match_b = d_desc_b ? gpu_buffer_id_A : gpu_buffer_id_B;
       }
     }
     if (invalid)
@@ -1565,9 +1597,33 @@ extern "C"
     }
     if (!ok)
     {
-      LOGE(TAG, "vksift_matchFeatures() error: Failed to start the matching pipeline.");
+      LOGE(TAG, "%s() error: Failed to start the matching pipeline.", fn);
       inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
     }
+  }
+
+  void vksift_matchFeatures(vksift_Instance inst, const uint32_t gpu_buffer_id_A, const uint32_t gpu_buffer_id_B)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id_A) || !buffer_idx_valid(inst, gpu_buffer_id_B))
+    {
+      LOGE(TAG, "vksift_matchFeatures() error: invalid input.");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    match_common(inst, gpu_buffer_id_A, gpu_buffer_id_B, nullptr, 0, "vksift_matchFeatures");
+  }
+
+  void vksiftx_matchFeaturesAgainstDevice(vksift_Instance inst, const uint32_t gpu_buffer_id_A, const void *d_descriptors_B, const uint32_t nb_feats_B)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id_A) || d_descriptors_B == NULL || ((uintptr_t)d_descriptors_B & 127u) != 0 ||
+        nb_feats_B > inst->cfg.max_nb_sift_per_buffer)
+    {
+      LOGE(TAG, "vksiftx_matchFeaturesAgainstDevice() error: invalid input (B must be a 128-byte aligned device pointer holding at most "
+                "max_nb_sift_per_buffer descriptors).");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    match_common(inst, gpu_buffer_id_A, 0, (const uint8_t *)d_descriptors_B, nb_feats_B, "vksiftx_matchFeaturesAgainstDevice");
   }
 
   uint32_t vksift_getMatchesNumber(vksift_Instance inst) { return inst->nb_matches; }
@@ -1790,8 +1846,12 @@ extern "C"
         FeatureBuffer &A = inst->buffers[gpu_buffer_id_A], &B = inst->buffers[gpu_buffer_id_B];
         const size_t maxf = inst->cfg.max_nb_sift_per_buffer;
         auto run = [&]() -> bool {
-          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, B.desc, nb, A.desc, na, inst->d_matches_rev, inst->stream, nullptr, &inst->launches));
-          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, B.desc, nb, inst->d_matches, inst->stream, nullptr, &inst->launches));
+          if (!ensure_norms(inst, A, na) || !ensure_norms(inst, B, nb))
+            return false;
+          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, B.desc, nb, B.norm_plain, A.desc, na, A.norm_packed, inst->d_matches_rev, inst->stream,
+                              nullptr, &inst->launches));
+          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, A.norm_plain, B.desc, nb, B.norm_packed, inst->d_matches, inst->stream,
+                              nullptr, &inst->launches));
           CU_TRY(launch_match_filter(inst->d_matches, na, inst->d_matches_rev, nb, lowe_ratio, inst->d_pairs, (uint32_t)maxf, inst->d_pairs + 2 * maxf,
                                      inst->stream));
           inst->launches++;

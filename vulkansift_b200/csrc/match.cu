@@ -216,15 +216,56 @@ cudaError_t launch_match_filter(const vksift_Match_2NN *m12, uint32_t na, const 
   return cudaGetLastError();
 }
 
-cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *da, uint32_t na, const uint8_t *db, uint32_t nb, vksift_Match_2NN *out,
-                         cudaStream_t st, cudaEvent_t ev_after_prepare, uint64_t *launch_count)
+__global__ void norms_both_kernel(const uint8_t *__restrict__ desc, uint32_t n, uint32_t n_padded, uint32_t *__restrict__ out_plain,
+                                  uint32_t *__restrict__ out_packed)
+{
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n)
+  {
+    if (row < n_padded && lane == 0)
+      out_packed[row] = NORM_PAD_VALUE;
+    return;
+  }
+  const uint32_t v = __ldg((const uint32_t *)(desc + (size_t)row * 128) + lane);
+  uint32_t s = __dp4a(v, v, 0u);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, d);
+  if (lane == 0)
+  {
+    out_plain[row] = s;
+    out_packed[row] = s * 256u + (match_pos_host_device(row) & 255u);
+  }
+}
+
+cudaError_t launch_norms(const uint8_t *desc, uint32_t n, uint32_t *out_plain, uint32_t *out_packed, cudaStream_t st)
+{
+  const uint32_t n_pad = (n + 127u) & ~127u;
+  if (n_pad == 0)
+    return cudaSuccess;
+  norms_both_kernel<<<(n_pad * 32 + 255) / 256, 256, 0, st>>>(desc, n, n_pad, out_plain, out_packed);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *da, uint32_t na, const uint32_t *norm_a, const uint8_t *db, uint32_t nb,
+                         const uint32_t *norm_b, vksift_Match_2NN *out, cudaStream_t st, cudaEvent_t ev_after_prepare, uint64_t *launch_count)
 {
   if (na == 0)
     return cudaSuccess;
   const uint32_t nb_pad = (nb + 127u) & ~127u; /* the tensor-core path reads |b|^2 in tiles of 128 */
-  norms_kernel<<<(na * 32 + 255) / 256, 256, 0, st>>>(da, na, na, ws->norm_a, 0);
-  norms_kernel<<<(nb_pad * 32 + 255) / 256, 256, 0, st>>>(db, nb, nb_pad, ws->norm_b, 1);
-  *launch_count += 2;
+  if (!norm_a)
+  {
+    norms_kernel<<<(na * 32 + 255) / 256, 256, 0, st>>>(da, na, na, ws->norm_a, 0);
+    *launch_count += 1;
+    norm_a = ws->norm_a;
+  }
+  if (!norm_b)
+  {
+    norms_kernel<<<(nb_pad * 32 + 255) / 256, 256, 0, st>>>(db, nb, nb_pad, ws->norm_b, 1);
+    *launch_count += 1;
+    norm_b = ws->norm_b;
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
@@ -232,11 +273,11 @@ cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *da, uint32
     cudaEventRecord(ev_after_prepare, st);
   if (impl == 1)
   {
-    match_simt_kernel<<<(na + MS_ROWS - 1) / MS_ROWS, MS_ROWS, 0, st>>>(da, na, ws->norm_a, db, nb, ws->norm_b, out);
+    match_simt_kernel<<<(na + MS_ROWS - 1) / MS_ROWS, MS_ROWS, 0, st>>>(da, na, norm_a, db, nb, norm_b, out);
     *launch_count += 1;
     return cudaGetLastError();
   }
-  return match_tc_launch(ws->tc, da, na, ws->norm_a, db, nb, ws->norm_b, out, st, launch_count);
+  return match_tc_launch(ws->tc, da, na, norm_a, db, nb, norm_b, out, st, launch_count);
 }
 
 } // namespace vks

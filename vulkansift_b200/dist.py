@@ -17,17 +17,30 @@ def shard_range(n_items, rank, world):
     return begin, begin + base + (1 if rank < extra else 0)
 
 
-def exchange_descriptor_blocks(local_desc, group=None):
+def exchange_descriptor_blocks(local_desc, group=None, capacity=None):
     """All-gather of per-rank descriptor blocks of different lengths.
 
     local_desc: (n_local, 128) uint8 tensor on the backend's device.
-    Returns (counts, blocks): counts[j] = rows contributed by rank j; blocks is (world, max_n, 128),
+    Returns (counts, blocks): counts[j] = rows contributed by rank j; blocks is (world, rows, 128),
     rank j's descriptors are blocks[j, :counts[j]] and the padding rows are zero.
-    Two collectives: 4-byte counts, then blocks padded to the largest count (0.4 MB/rank at ~3k features).
+    capacity=None: two collectives, 8-byte counts, then blocks padded to the largest count (0.4 MB/rank at ~3k features).
+    capacity=c (every rank holds at most c rows and passes the same c): ONE collective of (c+1)-row slots whose last row
+    carries the count, so the exchange costs one launch and one host read instead of two of each; the step is latency
+    bound (0.4 MB per rank against 900 GB/s per direction of NVLink), so the extra padding rows are free.
     """
     world = dist.get_world_size(group)
     dev = local_desc.device
     assert local_desc.dtype == torch.uint8 and local_desc.dim() == 2 and local_desc.shape[1] == 128
+    if capacity is not None:
+        n = local_desc.shape[0]
+        assert n <= capacity, "descriptor block of %d rows exceeds the exchange capacity %d" % (n, capacity)
+        send = torch.zeros((capacity + 1, 128), dtype=torch.uint8, device=dev)
+        send[:n] = local_desc
+        send[capacity, :8] = torch.tensor([n], dtype=torch.int64).view(torch.uint8).to(dev)
+        blocks = torch.empty((world, capacity + 1, 128), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(blocks.view(world * (capacity + 1), 128), send, group=group)
+        counts = [int(c) for c in blocks[:, capacity, :8].contiguous().view(torch.int64).flatten().tolist()]
+        return counts, blocks
     n_local = torch.tensor([local_desc.shape[0]], dtype=torch.int64, device=dev)
     counts_t = torch.zeros(world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(counts_t, n_local, group=group)
@@ -46,7 +59,7 @@ def all_pairs_schedule(rank, world):
     return [(rank + d) % world for d in range(1, world)]
 
 
-def gather_instance_descriptors(inst, buffer_id, group=None):
+def gather_instance_descriptors(inst, buffer_id, group=None, capacity=None):
     """CUDA glue: all-gather the descriptors of one feature buffer of a vulkansift_b200.api.Instance.
 
     The local block is copied device-to-device into a torch tensor (the NCCL send buffer) by
@@ -56,17 +69,23 @@ def gather_instance_descriptors(inst, buffer_id, group=None):
     dev = torch.device("cuda", inst.device_index)
     local = torch.empty((max(n, 1), 128), dtype=torch.uint8, device=dev)
     inst.copy_descriptors_to_device(buffer_id, local.data_ptr(), max(n, 1))
-    return exchange_descriptor_blocks(local[:n], group)
+    return exchange_descriptor_blocks(local[:n], group, capacity)
 
 
 def match_against_peers(inst, buffer_a, scratch_buffer, counts, blocks, rank, world, download=True):
-    """Match the local features (buffer_a) against every peer block.  Returns {peer: matches or None}."""
+    """Match the local features (buffer_a) against every peer block, read in place from the gathered tensor
+    (vksiftx_matchFeaturesAgainstDevice; a block whose address is not 128-byte aligned goes through `scratch_buffer`).
+    Returns {peer: matches or None}."""
     out = {}
     for j in all_pairs_schedule(rank, world):
         if counts[j] < 2:
             out[j] = None
             continue
-        inst.upload_descriptors_device(blocks[j].data_ptr(), counts[j], scratch_buffer)
-        inst.match(buffer_a, scratch_buffer)
+        ptr = blocks[j].data_ptr()
+        if ptr % 128 == 0:
+            inst.match_against_device(buffer_a, ptr, counts[j])
+        else:
+            inst.upload_descriptors_device(ptr, counts[j], scratch_buffer)
+            inst.match(buffer_a, scratch_buffer)
         out[j] = inst.download_matches() if download else None
     return out
