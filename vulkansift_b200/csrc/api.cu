@@ -642,7 +642,8 @@ void destroy_instance(vksift_Instance inst)
   cudaFree(inst->ori);
   cudaFree(inst->n_ori);
   cudaFree(inst->feat_src);
-  cudaFree(inst->desc_m_table);
+  if (!inst->primary)
+    cudaFree(inst->desc_m_table);
   cudaFree(inst->d_aos);
   cudaFree(inst->d_matches);
   cudaFree(inst->d_matches_rev);
@@ -760,8 +761,14 @@ bool create_resources(vksift_Instance inst)
   CU_TRY(cudaMalloc(&inst->ori, sizeof(float) * (maxf + 1) * inst->ori_stride));
   CU_TRY(cudaMalloc(&inst->n_ori, sizeof(uint32_t) * (maxf + 1)));
   CU_TRY(cudaMalloc(&inst->feat_src, sizeof(uint32_t) * (maxf + 1)));
-  CU_TRY(cudaMalloc(&inst->desc_m_table, sizeof(float) * VKS_DESC_M_TABLE));
-  CU_TRY(launch_descriptor_scale_table(inst->desc_m_table, inst->stream));
+  if (inst->primary)
+    inst->desc_m_table = inst->primary->desc_m_table; /* read-only table, built once per instance */
+  else
+  {
+    CU_TRY(cudaMalloc(&inst->desc_m_table, sizeof(float) * VKS_DESC_M_TABLE));
+    CU_TRY(launch_descriptor_scale_table(inst->desc_m_table, inst->stream));
+    CU_TRY(cudaStreamSynchronize(inst->stream)); /* the other lanes read it from their own streams */
+  }
   CU_TRY(cudaMalloc(&inst->d_aos, sizeof(vksift_Feature) * maxf));
   inst->graphs.resize(c.sift_buffer_count);
   if (inst->primary)

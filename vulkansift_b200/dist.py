@@ -59,17 +59,46 @@ def all_pairs_schedule(rank, world):
     return [(rank + d) % world for d in range(1, world)]
 
 
+class _ExchangeBuffers:
+    """Persistent send slot / receive buffer of the single-collective exchange (allocated once per (device, world, capacity))."""
+
+    def __init__(self, dev, world, capacity):
+        self.capacity = capacity
+        self.send = torch.zeros((capacity + 1, 128), dtype=torch.uint8, device=dev)
+        self.recv = torch.empty((world, capacity + 1, 128), dtype=torch.uint8, device=dev)
+        self.count_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+
+
+_exchange_buffers = {}
+
+
 def gather_instance_descriptors(inst, buffer_id, group=None, capacity=None):
     """CUDA glue: all-gather the descriptors of one feature buffer of a vulkansift_b200.api.Instance.
 
-    The local block is copied device-to-device into a torch tensor (the NCCL send buffer) by
-    vksiftx_copyDescriptorsToDevice; nothing touches the host except the 8-byte counts.
+    capacity=None: the local block is copied device-to-device into a torch tensor by vksiftx_copyDescriptorsToDevice and
+    exchanged with two collectives (counts, then blocks padded to the largest count).
+    capacity=c: vksiftx_copyDescriptorsToDevice writes the block (zero padded) straight into a persistent (c+1)-row send
+    slot, the count goes into the slot's last row, and ONE all-gather moves everything; the host then reads the world's
+    counts back.  Nothing else touches the host.  The returned blocks alias the persistent receive buffer: they are valid
+    until the next gather with the same capacity.
     """
-    n = inst.features_number(buffer_id)
     dev = torch.device("cuda", inst.device_index)
-    local = torch.empty((max(n, 1), 128), dtype=torch.uint8, device=dev)
-    inst.copy_descriptors_to_device(buffer_id, local.data_ptr(), max(n, 1))
-    return exchange_descriptor_blocks(local[:n], group, capacity)
+    if capacity is None:
+        n = inst.features_number(buffer_id)
+        local = torch.empty((max(n, 1), 128), dtype=torch.uint8, device=dev)
+        inst.copy_descriptors_to_device(buffer_id, local.data_ptr(), max(n, 1))
+        return exchange_descriptor_blocks(local[:n], group)
+    world = dist.get_world_size(group)
+    key = (inst.device_index, world, capacity)
+    xb = _exchange_buffers.get(key)
+    if xb is None:
+        xb = _exchange_buffers[key] = _ExchangeBuffers(dev, world, capacity)
+    n = inst.copy_descriptors_to_device(buffer_id, xb.send.data_ptr(), capacity)  # rows [n, capacity) are zero filled
+    xb.count_host[0] = n
+    xb.send[capacity].view(torch.int64)[:1].copy_(xb.count_host, non_blocking=True)
+    dist.all_gather_into_tensor(xb.recv.view(world * (capacity + 1), 128), xb.send, group=group)
+    counts = [int(c) for c in xb.recv[:, capacity, :8].contiguous().view(torch.int64).flatten().tolist()]
+    return counts, xb.recv
 
 
 def match_against_peers(inst, buffer_a, scratch_buffer, counts, blocks, rank, world, download=True):
