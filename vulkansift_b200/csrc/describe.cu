@@ -419,6 +419,8 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
     const float rsx = vks_rint(kp.scale_x), rsy = vks_rint(kp.scale_y);
     const int cx = (int)rsx, cy = (int)rsy;
     const int box = 2 * R + 1;
+    const uint32_t s_desc_addr = (uint32_t)__cvta_generic_to_shared(s_desc);
+    const int pitch = ov.pitch;
     auto add_pixel = [&](int dx, int dy) {
       const int ix = cx + dx, iy = cy + dy;
       if (ix < 1 || ix >= (ov.w - 1) || iy < 1 || iy >= (ov.h - 1))
@@ -429,12 +431,13 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
       const float oy = kc * sdy - ks * sdx;
       /* pixels whose both spatial cells fall outside the 4x4 grid contribute to no bin (:187):
        * skip them before the transcendental work (about half of the box after rotation) */
-      const int hx0 = (int)floorf((ox + 2.f) - 0.5f), hy0 = (int)floorf((oy + 2.f) - 0.5f);
-      if (hx0 < -1 || hx0 > 3 || hy0 < -1 || hy0 > 3)
+      const float fx = ox + 2.f, fy = oy + 2.f;
+      const int hx = (int)floorf(fx - 0.5f), hy = (int)floorf(fy - 0.5f);
+      if (hx < -1 || hx > 3 || hy < -1 || hy > 3)
         return;
-      const float *__restrict__ c = L + (size_t)iy * ov.pitch + ix;
-      const float gX = 0.5f * (__ldg(c + 1) - __ldg(c - 1));
-      const float gY = 0.5f * (__ldg(c + ov.pitch) - __ldg(c - ov.pitch));
+      const int off = iy * pitch + ix; /* 32-bit index: a layer has fewer than 2^31 cells */
+      const float gX = 0.5f * (__ldg(L + (off + 1)) - __ldg(L + (off - 1)));
+      const float gY = 0.5f * (__ldg(L + (off + pitch)) - __ldg(L + (off - pitch)));
       float th = vks_atan2f(gY, gX);
       if (th < 0.f)
         th += VKS_TWO_PI_F;
@@ -446,23 +449,28 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
       else if (th > VKS_TWO_PI_F)
         th -= VKS_TWO_PI_F;
       const float mag = vks_expf(es * ((ox * ox) + (oy * oy))) * vks_sqrt((gX * gX) + (gY * gY));
-      const float fx = ox + 2.f, fy = oy + 2.f;
       const float fb = P.vlfeat ? ((th * 8.f) / VKS_TWO_PI_F) : ((-th * 8.f) / VKS_TWO_PI_F);
-      const int hx = (int)floorf(fx - 0.5f), hy = (int)floorf(fy - 0.5f), hb = (int)floorf(fb);
+      const int hb = (int)floorf(fb);
       const float rx = fx - ((float)hx + 0.5f), ry = fy - ((float)hy + 0.5f), rb = fb - (float)hb;
+      /* trilinear weights |1 - i - r| for i = 0, 1 (the second one is |0 - r| = |r| exactly); the eight contributions are
+       * computed unconditionally in the shader's order ((wx*wy)*wb)*mag, then *fp, and added by predicated shared-memory
+       * reductions: integer adds commute, so the histogram does not depend on the order of the lanes */
+      const float wx[2] = {fabsf(1.f - rx), fabsf(rx)}, wy[2] = {fabsf(1.f - ry), fabsf(ry)}, wb[2] = {fabsf(1.f - rb), fabsf(rb)};
+      const uint32_t b0 = (uint32_t)hb & 7u, b1 = (uint32_t)(hb + 1) & 7u; /* non-negative modulo (SURVEY B-D7) */
 #pragma unroll
-      for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 2; j++)
 #pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-          for (int q = 0; q < 2; q++)
-            if ((i + hx) >= 0 && (i + hx) < 4 && (j + hy) >= 0 && (j + hy) < 4)
-            {
-              const int b = (q + hb) & 7; /* non-negative modulo (SURVEY B-D7) */
-              const int idx = (j + hy) * 32 + (i + hx) * 8 + b;
-              const float val = fabsf(1.f - (float)i - rx) * fabsf(1.f - (float)j - ry) * fabsf(1.f - (float)q - rb) * mag;
-              atomicAdd(&s_desc[idx], (uint32_t)(val * fp));
-            }
+        for (int i = 0; i < 2; i++)
+        {
+          const uint32_t ok = ((uint32_t)(i + hx) < 4u && (uint32_t)(j + hy) < 4u) ? 1u : 0u;
+          const float wxy = wx[i] * wy[j];
+          const uint32_t v0 = (uint32_t)(((wxy * wb[0]) * mag) * fp), v1 = (uint32_t)(((wxy * wb[1]) * mag) * fp);
+          const uint32_t cell = s_desc_addr + (uint32_t)(((j + hy) * 32 + (i + hx) * 8) * 4);
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t@p red.shared.add.u32 [%2], %4;\n\t}" ::"r"(
+                           cell + b0 * 4u),
+                       "r"(v0), "r"(cell + b1 * 4u), "r"(ok), "r"(v1)
+                       : "memory");
+        }
     };
     if (box <= DESC_MAXBOX)
     {
@@ -529,12 +537,34 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
       }
       __syncthreads();
       const int n_px = s_row_start[box];
+      /* Each warp takes one contiguous quarter of the concatenated intervals and walks it 32 pixels at a time, so a lane
+       * moves on by about one row per step (the search for its row is a short loop; with a stride of the whole CTA it cost
+       * five iterations per pixel).  First row of the warp by bisection. */
+      const int per_warp = (((n_px + (DESC_THREADS / 32) - 1) / (DESC_THREADS / 32)) + 31) & ~31;
+      const int w_begin = (tid >> 5) * per_warp, w_end = min(n_px, w_begin + per_warp);
       int row = 0;
-      for (int idx = tid; idx < n_px; idx += DESC_THREADS)
       {
-        while (idx >= s_row_start[row + 1])
+        int lo = 0, hi = box; /* largest row with s_row_start[row] <= w_begin */
+        while (hi - lo > 1)
+        {
+          const int mid = (lo + hi) >> 1;
+          if (s_row_start[mid] <= w_begin)
+            lo = mid;
+          else
+            hi = mid;
+        }
+        row = lo;
+      }
+      int row_begin = s_row_start[row], row_end = s_row_start[row + 1];
+      for (int idx = w_begin + (tid & 31); idx < w_end; idx += 32)
+      {
+        while (idx >= row_end)
+        {
           row++;
-        add_pixel(s_row_lo[row] + (idx - s_row_start[row]), row - R);
+          row_begin = row_end;
+          row_end = s_row_start[row + 1];
+        }
+        add_pixel(s_row_lo[row] + (idx - row_begin), row - R);
       }
     }
     else
