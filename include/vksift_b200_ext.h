@@ -119,6 +119,11 @@ extern "C"
    * kernel (default, the product path), 1 = SIMT dp4a cross-check kernel. */
   VKSIFT_EXPORT void vksiftx_setMatcherImpl(vksift_Instance instance, const int32_t impl);
 
+  /* Ablation timing (analysis only, the results of later detections are INVALID while a bit is set): leave stages of the
+   * detection out to measure what each one costs in the pipelined schedule.  Bits: 1 descriptors, 2 orientation,
+   * 4 extrema scan + refinement + ordering, 8 scale space (the layers keep the content of the previous detection). */
+  VKSIFT_EXPORT void vksiftx_setDebugSkip(vksift_Instance instance, const int32_t mask);
+
 #ifdef __cplusplus
 }
 #endif

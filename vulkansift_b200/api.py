@@ -110,6 +110,7 @@ def _load_library():
         "vksiftx_getEffectiveTaps": (None, [I, C.c_void_p, C.c_void_p]),
         "vksiftx_getSectionCapacities": (None, [I, u32, C.c_void_p]),
         "vksiftx_setMatcherImpl": (None, [I, C.c_int32]),
+        "vksiftx_setDebugSkip": (None, [I, C.c_int32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
@@ -362,6 +363,9 @@ class Instance:
         lib.vksiftx_getSectionCapacities(self._h, buffer_id, caps.ctypes.data)
         self._check("vksiftx_getSectionCapacities")
         return caps
+
+    def set_debug_skip(self, mask):
+        lib.vksiftx_setDebugSkip(self._h, int(mask))
 
     def set_matcher_impl(self, impl):
         lib.vksiftx_setMatcherImpl(self._h, int(impl))

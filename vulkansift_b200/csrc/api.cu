@@ -119,6 +119,7 @@ struct vksift_Instance_T
   MegaPlan *mega = nullptr;                    /* whole scale space as one persistent launch, when the configuration allows it */
   bool use_mega = false;
   bool serial = false;   /* vksiftx_setSerialSchedule */
+  int debug_skip = 0;    /* VKSIFT_DEBUG_SKIP bit mask (ablation timing only, results invalid): 1 descriptors, 2 orientation, 4 extrema+order, 8 scale space */
   bool no_split = false; /* VKSIFT_NO_SPLIT=1: extrema/orientation of all octaves after the whole pyramid (debug) */
   cudaStream_t side_stream = nullptr, side2_stream = nullptr;
   cudaEvent_t ev_chain[VKS_MAX_OCT] = {nullptr}; /* chain launches of octave o enqueued on the side stream */
@@ -744,6 +745,8 @@ bool create_resources(vksift_Instance inst)
     inst->use_mega = (m && m[0] == '1');
     const char *nsp = getenv("VKSIFT_NO_SPLIT");
     inst->no_split = (nsp && nsp[0] == '1');
+    if (const char *ds = getenv("VKSIFT_DEBUG_SKIP"))
+      inst->debug_skip = atoi(ds);
     if (inst->use_mega)
       n_lanes = 1; /* the persistent kernel takes a new epoch per launch */
     inst->use_graph = (g ? g[0] == '1' : n_lanes > 1) && !inst->use_mega;
@@ -905,9 +908,13 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
     DetectParams Q = P;
     Q.ob = ob;
     Q.oe = oe;
-    CU_TRY(launch_extrema(Q, inst->extrema_plan, inst->raw, inst->cand, fb.cnt, s));
-    CU_TRY(launch_order_primaries(Q, inst->cand, fb.cnt, inst->prim, s));
-    CU_TRY(launch_orientation(Q, fb.cnt, inst->prim, inst->ori, inst->n_ori, s));
+    if (!(inst->debug_skip & 4))
+    {
+      CU_TRY(launch_extrema(Q, inst->extrema_plan, inst->raw, inst->cand, fb.cnt, s));
+      CU_TRY(launch_order_primaries(Q, inst->cand, fb.cnt, inst->prim, s));
+    }
+    if (!(inst->debug_skip & 2))
+      CU_TRY(launch_orientation(Q, fb.cnt, inst->prim, inst->ori, inst->n_ori, s));
     inst->launches += 4;
     return true;
   };
@@ -918,6 +925,7 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
       CU_TRY(cudaStreamWaitEvent(so, inst->ev_seed[o], 0));
     for (BlurPass &bp : inst->fast_oct[o])
     {
+      if (!(inst->debug_skip & 8))
       {
         TraceScope ts(inst, so, "fast o%d r%d", o, bp.radius);
         CU_TRY(launch_blur_pass_fast(bp, so));
@@ -956,7 +964,8 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
       for (const FusedLaunch &F : fo.chain)
       {
         TraceScope ts(inst, ss, "fused chain o%d n%d", n_fast + (int)j, F.n_layers);
-        CU_TRY(launch_fused(F, ss));
+        if (!(inst->debug_skip & 8))
+          CU_TRY(launch_fused(F, ss));
         inst->launches++;
       }
       if (!fo.rest.empty())
@@ -966,7 +975,8 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
         for (const FusedLaunch &F : fo.rest)
         {
           TraceScope ts(inst, side2, "fused rest o%d n%d", n_fast + (int)j, F.n_layers);
-          CU_TRY(launch_fused(F, side2));
+          if (!(inst->debug_skip & 8))
+            CU_TRY(launch_fused(F, side2));
           inst->launches++;
         }
         used2 = true;
@@ -1028,13 +1038,16 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   DetectParams PA = P;
   if (split)
     PA.oe = 1; /* octave 0 (its layers are complete on this stream); the other octaves follow on the side stream */
-  CU_TRY(launch_extrema(PA, inst->extrema_plan, inst->raw, inst->cand, fb.cnt, st));
-  inst->launches += 2;
-  CU_TRY(launch_order_primaries(PA, inst->cand, fb.cnt, inst->prim, st));
-  inst->launches++;
+  if (!(inst->debug_skip & 4))
+  {
+    CU_TRY(launch_extrema(PA, inst->extrema_plan, inst->raw, inst->cand, fb.cnt, st));
+    CU_TRY(launch_order_primaries(PA, inst->cand, fb.cnt, inst->prim, st));
+  }
+  inst->launches += 3;
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D2], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
-  CU_TRY(launch_orientation(PA, fb.cnt, inst->prim, inst->ori, inst->n_ori, st));
+  if (!(inst->debug_skip & 2))
+    CU_TRY(launch_orientation(PA, fb.cnt, inst->prim, inst->ori, inst->n_ori, st));
   inst->launches++;
   if (split)
   {
@@ -1046,7 +1059,8 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D3], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   CU_TRY(launch_assemble(P, fb.cnt, inst->n_ori, inst->feat_src, fb.host_counts_dev, st));
-  CU_TRY(launch_descriptors(P, fb.cnt, inst->desc_m_table, inst->prim, inst->ori, inst->feat_src, fb.heads, fb.desc, st));
+  if (!(inst->debug_skip & 1))
+    CU_TRY(launch_descriptors(P, fb.cnt, inst->desc_m_table, inst->prim, inst->ori, inst->feat_src, fb.heads, fb.desc, st));
   inst->launches += 2;
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D4], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
@@ -1999,5 +2013,15 @@ extern "C"
   }
 
   void vksiftx_setMatcherImpl(vksift_Instance inst, const int32_t impl) { inst->matcher_impl = impl; }
+
+  void vksiftx_setDebugSkip(vksift_Instance inst, const int32_t mask)
+  {
+    wait_pipelines(inst, true, true);
+    for (vksift_Instance lane : inst->lanes)
+    {
+      lane->debug_skip = mask;
+      invalidate_graphs(lane);
+    }
+  }
 
 } /* extern "C" */
