@@ -288,6 +288,28 @@ def main():
     dev_ms = ev0.elapsed_time(ev1)
     launches = inst.kernel_launch_count() - launches0
 
+    # what the scale space costs per image in the pipelined schedule: the same timed loop with the blur launches left out
+    # (vksiftx_setDebugSkip: analysis mode, the detections made while it is set are not used for anything else)
+    def timed_loop(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(3 * NBUF):
+            inst.detect_device(d_images[i % N_IMAGES].data_ptr(), w, h, i % NBUF)
+        inst.wait_idle()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for i in range(n):
+            inst.detect_device(d_images[i % N_IMAGES].data_ptr(), w, h, i % NBUF)
+        inst.join_lanes()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    t_all = timed_loop(K)
+    inst.set_debug_skip(8)
+    t_no_pyr = timed_loop(K)
+    inst.set_debug_skip(0)
+    pyr_marginal_ms = max(t_all - t_no_pyr, 1e-6)
+
     # stage times: CUDA events of the library on its own stream, one synchronised detection at a time
     inst.set_profiling(True)
     stage_acc = {}
@@ -464,6 +486,12 @@ def main():
             "roofline_stage": {"bound": "hbm", "kernel": "whole pyramid+DoG stage (all blur launches of all octaves, CUDA events of the library)",
                                "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "algorithmic_bytes": alg, "stage_ms": pyr_ms,
                                "peak_source": peak_src},
+            "roofline_stage_pipelined": {"bound": "hbm", "kernel": "whole pyramid+DoG stage, marginal cost per image with all lanes busy: ms per "
+                                         "image of the timed loop minus the same loop with the blur launches left out "
+                                         "(vksiftx_setDebugSkip)", "achieved": alg / (pyr_marginal_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                         "frac": alg / (pyr_marginal_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": alg,
+                                         "marginal_ms": pyr_marginal_ms, "ms_per_image_all_stages": t_all,
+                                         "ms_per_image_without_scale_space": t_no_pyr, "peak_source": peak_src},
             "scale_space_launches_us": {k: round(v, 2) for k, v in trace_acc.items()},
             "match": {"metric": "2nn_matches_per_sec", "value": world * MATCH_N / (match_ms * 1e-3), "unit": "matches/s",
                       "workload": "configs[3]: 10000 x 10000 x 128-D u8, tcgen05 kind::i8 path", "ms_per_match_call": match_ms,
