@@ -611,9 +611,9 @@ cudaError_t launch_descriptors(const DetectParams &P, DetectCounters *cnt, const
   if (per_sm == 0)
   {
     const char *e = getenv("VKSIFT_DESC_CTAS");
-    per_sm = e ? atoi(e) : 8;
+    per_sm = e ? atoi(e) : 12; /* 44 registers x 128 threads: up to 11 resident; 12 measured 5 us faster than 8 for 3.4 k features */
     if (per_sm < 1 || per_sm > 16)
-      per_sm = 8;
+      per_sm = 12;
   }
   descriptor_kernel<<<148 * per_sm, DESC_THREADS, 0, st>>>(P, cnt, m_table, prim, ori, feat_src, out_heads, out_desc);
   return cudaGetLastError();
