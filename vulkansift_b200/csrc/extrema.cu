@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
   constexpr int EX_RPT = EX_TH / (EX_THREADS / 256); /* rows per thread */
   extern __shared__ __align__(128) float ex_smem[];
   __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ int s_tile[2][4]; /* (octave, x0, y0) of the tile in each buffer: computed once by the thread that requests it */
   const int ns = P.ns, nl = P.ns + 2;
   const float prefilter = P.prefilter;
   const uint32_t tile_bytes = (uint32_t)(nl * EX_SH * EX_SW) * 4u;
@@ -164,6 +165,9 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
     int o, x0, y0;
     if (t_begin + (int)blockIdx.x < n_tiles && extrema_tile_coords(P, t_begin + (int)blockIdx.x, &o, &x0, &y0))
     {
+      s_tile[0][0] = o;
+      s_tile[0][1] = x0;
+      s_tile[0][2] = y0;
       tma_mbar_expect_tx(bar0, tile_bytes);
       for (int l = 0; l < nl; l++) /* one request per layer: the TMA unit pipelines independent requests */
         tma_load_3d(tma_smem_u32(ex_smem + l * EX_SH * EX_SW), &maps.m[o], x0 - 4, y0 - 1, l, bar0);
@@ -175,14 +179,17 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
   for (int t = t_begin + (int)blockIdx.x; t < n_tiles; t += gridDim.x, it++) /* tiles [t_begin, n_tiles) = the octaves [P.ob, P.oe) */
   {
     const int cur = it & 1;
-    int o, x0, y0;
-    extrema_tile_coords(P, t, &o, &x0, &y0);
+    /* written by thread 0 before the barrier that ended the previous iteration (or the one after the prologue) */
+    const int o = s_tile[cur][0], x0 = s_tile[cur][1], y0 = s_tile[cur][2];
     if (tid == 0)
     {
       /* prefetch the next tile into the other buffer (its previous readers passed the barrier below) */
       int on, xn, yn;
       if (t + (int)gridDim.x < n_tiles && extrema_tile_coords(P, t + (int)gridDim.x, &on, &xn, &yn))
       {
+        s_tile[cur ^ 1][0] = on;
+        s_tile[cur ^ 1][1] = xn;
+        s_tile[cur ^ 1][2] = yn;
         tma_fence_proxy_async();
         tma_mbar_expect_tx(bar0 + 8 * (cur ^ 1), tile_bytes);
         for (int l = 0; l < nl; l++)
@@ -200,6 +207,7 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
     {
       /* rows of this thread that are inside [1, h-2] */
       const int r_lo = max(0, 1 - (y0 + ly)), r_hi = min(EX_RPT, (oh - 1) - (y0 + ly));
+      const uint32_t row_ok = (r_hi > r_lo) ? (((1u << r_hi) - 1u) & ~((1u << r_lo) - 1u)) : 0u;
       for (int s = 1; s <= ns; s++)
       {
         const float *col = tile + (s * EX_SH + ly + 1) * EX_SW + (lx + 4);
@@ -211,7 +219,8 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
         uint32_t mask = 0;
 #pragma unroll
         for (int r = 0; r < EX_RPT; r++)
-          mask |= (fabsf(cv[r]) > prefilter && r >= r_lo && r < r_hi) ? (1u << r) : 0u;
+          mask |= (fabsf(cv[r]) > prefilter) ? (1u << r) : 0u;
+        mask &= row_ok;
         while (mask)
         {
           const int r = __ffs(mask) - 1;
