@@ -423,10 +423,12 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
       float *lut = ft_smem + BAR_OFF + 2 * FT_NB;
       lut[tid] = vks_unorm8((uint8_t)tid);
       __syncthreads();
-      for (int i = tid; i < sw * sh; i += FT_THREADS)
+      /* one warp per staged row, lanes along the row: no integer division in the loop */
+      for (int yy = wi; yy < sh; yy += FT_THREADS / 32)
       {
-        const int yy = i / sw, xx = i - yy * sw;
-        s_mid[i] = lut[__ldg(img + (size_t)(sy_lo + yy) * p.src_w + sx_lo + xx)];
+        const uint8_t *__restrict__ srow = img + (size_t)(sy_lo + yy) * p.src_w + sx_lo;
+        for (int xx = lane; xx < sw; xx += 32)
+          s_mid[yy * sw + xx] = lut[__ldg(srow + xx)];
       }
       __syncthreads();
       const int cx = x0 - RX, cy = y0 - R; /* both even */
