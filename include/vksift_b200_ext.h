@@ -119,10 +119,13 @@ extern "C"
    * kernel (default, the product path), 1 = SIMT dp4a cross-check kernel. */
   VKSIFT_EXPORT void vksiftx_setMatcherImpl(vksift_Instance instance, const int32_t impl);
 
-  /* Ablation timing (analysis only, the results of later detections are INVALID while a bit is set): leave stages of the
-   * detection out to measure what each one costs in the pipelined schedule.  Bits: 1 descriptors, 2 orientation,
-   * 4 extrema scan + refinement + ordering, 8 scale space (the layers keep the content of the previous detection). */
+#ifdef VKS_ANALYSIS
+  /* ANALYSIS BUILD ONLY (vulkansift_b200/lib/libvulkansift_analysis.so, compiled with -DVKS_ANALYSIS; the product library
+   * does not contain this entry point nor the code behind it).  Ablation timing: leave stages of the detection out to
+   * measure what each one costs in the pipelined schedule; the results of detections made while a bit is set are INVALID.
+   * Bits: 1 descriptors, 2 orientation, 4 extrema scan + refinement + ordering, 8 scale space. */
   VKSIFT_EXPORT void vksiftx_setDebugSkip(vksift_Instance instance, const int32_t mask);
+#endif
 
 #ifdef __cplusplus
 }

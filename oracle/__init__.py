@@ -4,4 +4,4 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 legs may import this package; the product (vulkansift_b200) never does.
 """
 from .oracle import (Oracle, OracleConfig, FEATURE_DTYPE, MATCH_DTYPE, build, lib_path, match_descriptors,
-                     match_features, arith)  # noqa: F401
+                     match_features, arith, seed_image, downsample_nearest)  # noqa: F401

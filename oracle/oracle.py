@@ -67,6 +67,8 @@ def _load():
     lib.vkso_stage_seconds.argtypes = [C.c_void_p, C.c_void_p]
     lib.vkso_match.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
     lib.vkso_match_features.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
+    lib.vkso_seed_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    lib.vkso_downsample_nearest.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
     lib.vkso_expf.argtypes = [C.c_float]
     lib.vkso_expf.restype = C.c_float
     lib.vkso_exp2f.argtypes = [C.c_float]
@@ -224,4 +226,20 @@ def match_features(fa, fb, nb_threads=0):
     assert fa.dtype == FEATURE_DTYPE and fb.dtype == FEATURE_DTYPE and len(fb) >= 2
     out = np.zeros(len(fa), MATCH_DTYPE)
     _load().vkso_match_features(fa.ctypes.data, len(fa), fb.ctypes.data, len(fb), out.ctypes.data, nb_threads)
+    return out
+
+
+def seed_image(image, dw, dh):
+    """u8 UNORM upload + LINEAR blit to (dh, dw) (or the 1:1 conversion): the Vulkan fixed-function step in front of the first blur."""
+    image = np.ascontiguousarray(image, np.uint8)
+    out = np.zeros((dh, dw), np.float32)
+    _load().vkso_seed_image(image.ctypes.data, image.shape[1], image.shape[0], out.ctypes.data, dw, dh)
+    return out
+
+
+def downsample_nearest(layer, dw, dh):
+    """NEAREST blit of a Gaussian layer into the next octave's layer 0."""
+    layer = np.ascontiguousarray(layer, np.float32)
+    out = np.zeros((dh, dw), np.float32)
+    _load().vkso_downsample_nearest(layer.ctypes.data, layer.shape[1], layer.shape[0], out.ctypes.data, dw, dh)
     return out

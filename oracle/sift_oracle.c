@@ -904,6 +904,11 @@ void vkso_match_features(const vkso_Feature *a, uint32_t na, const vkso_Feature 
 }
 
 /* ---- arithmetic probes -------------------------------------------------- */
+/* the two Vulkan fixed-function steps of the path (restated from the Vulkan specification, not in the reference sources),
+ * exposed so that a test can chain the reference's own shaders between them (tests/test_ref_chain.py) */
+void vkso_seed_image(const uint8_t *img, int sw, int sh, float *dst, int dw, int dh) { seed_image(img, sw, sh, dst, dw, dh); }
+void vkso_downsample_nearest(const float *src, int sw, int sh, float *dst, int dw, int dh) { downsample_nearest(src, sw, sh, dst, dw, dh); }
+
 float vkso_expf(float x) { return vks_expf(x); }
 float vkso_exp2f(float x) { return vks_exp2f(x); }
 float vkso_atan2f(float y, float x) { return vks_atan2f(y, x); }

@@ -97,6 +97,10 @@ extern "C"
   void vkso_match(const uint8_t *desc_a, uint32_t na, const uint8_t *desc_b, uint32_t nb, vkso_Match *out, int nb_threads);
   void vkso_match_features(const vkso_Feature *a, uint32_t na, const vkso_Feature *b, uint32_t nb, vkso_Match *out, int nb_threads);
 
+  /* the Vulkan fixed-function steps (u8 UNORM upload + LINEAR blit, NEAREST blit), sift_detector.c:860-916, 1003-1034 */
+  void vkso_seed_image(const uint8_t *img, int sw, int sh, float *dst, int dw, int dh);
+  void vkso_downsample_nearest(const float *src, int sw, int sh, float *dst, int dw, int dh);
+
   /* arithmetic probes for tests (include/vksift_arith.h) */
   float vkso_expf(float x);
   float vkso_exp2f(float x);

@@ -18,6 +18,7 @@ def _declared_symbols():
     for hdr in ("vulkansift/vulkansift.h", "vksift_b200_ext.h"):
         txt = open(os.path.join(INC, hdr)).read()
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        txt = re.sub(r"#ifdef VKS_ANALYSIS.*?#endif", "", txt, flags=re.S)  # entry points of the analysis build only
         names += re.findall(r"VKSIFT_EXPORT[^;(]*?\b(vksiftx?_\w+)\s*\(", txt)
     return sorted(set(names))
 
@@ -32,6 +33,20 @@ def test_library_builds_loads_and_exports_everything():
         assert hasattr(lib, name), "library does not export %s" % name
     from vulkansift_b200 import api
     assert set(api.EXPORTED_SYMBOLS) == set(declared)
+
+
+def test_product_library_has_no_stage_skipping_switches():
+    """The ablation switch (vksiftx_setDebugSkip, stages left out, invalid results) only exists in the analysis build;
+    the library that is benchmarked and shipped neither exports it nor reads any debug environment variable for it."""
+    from vulkansift_b200 import build
+    build.build()
+    prod = ctypes.CDLL(build.LIB)
+    ana = ctypes.CDLL(build.LIB_ANALYSIS)
+    assert not hasattr(prod, "vksiftx_setDebugSkip")
+    assert hasattr(ana, "vksiftx_setDebugSkip")
+    blob = open(build.LIB, "rb").read()
+    for needle in (b"VKSIFT_DEBUG_SKIP", b"VKSIFT_MEGA", b"setDebugSkip"):
+        assert needle not in blob, needle
 
 
 def test_struct_layout_matches_reference_abi():
@@ -105,7 +120,7 @@ def test_plain_c_caller_links_against_the_library(tmp_path):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     lib_dir = os.path.join(root, "vulkansift_b200", "lib")
-    for name in ("detect_match", "perf_runtime"):  # the README-style caller and the port of the reference's perf_sift_runtime driver
+    for name in ("detect_match", "perf_runtime", "perf_matching"):  # the README-style caller and the port of the reference's perf_sift_runtime driver
         out = tmp_path / name
         r = subprocess.run(["gcc", "-std=c11", os.path.join(root, "examples", name + ".c"), "-I" + os.path.join(root, "include"), "-L" + lib_dir,
                             "-lvulkansift", "-Wl,-rpath," + lib_dir, "-lm", "-o", str(out)], capture_output=True, text=True)

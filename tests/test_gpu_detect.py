@@ -217,11 +217,11 @@ def test_c2_full_size_matches_oracle(api, oracle_mod):
     inst.close()
 
 
-@pytest.mark.parametrize("env", ["VKSIFT_MEGA=1", "VKSIFT_GRAPH=1", "VKSIFT_GRAPH=0", "VKSIFT_NO_SPLIT=1", "VKSIFT_NO_PDL=1"])
+@pytest.mark.parametrize("env", ["VKSIFT_GRAPH=1", "VKSIFT_GRAPH=0", "VKSIFT_NO_SPLIT=1", "VKSIFT_NO_PDL=1", "VKSIFT_STRIP=0"])
 def test_alternative_schedules_are_bit_exact(api, oracle_mod, env, monkeypatch):
-    """The scale space can be scheduled four ways (per-layer launches = default, one persistent dataflow kernel, CUDA-graph
-    replay (the default with several lanes) or eager launches, no stage overlap / no programmatic dependent launch): same
-    kernels, same bytes out."""
+    """The scale space can be scheduled several ways (CUDA-graph replay (the default with several lanes) or eager launches,
+    no stage overlap, no programmatic dependent launch, per-layer launches instead of the multi-layer strip kernel): same
+    bytes out."""
     from vulkansift_b200.synth import blob_image
     monkeypatch.setenv(*env.split("="))
     imgs = [blob_image(640, 480, 400, seed=11), blob_image(1000, 700, 600, seed=12)]
@@ -340,3 +340,69 @@ def test_single_lane_override(api, oracle_mod, c1_image, monkeypatch):
     assert_features_equal(inst.download_features(0), a, "lanes vs single lane, buffer 0")
     assert_features_equal(inst.download_features(1), b, "lanes vs single lane, buffer 1")
     inst.close()
+
+
+def test_benchmarked_configuration_c2_eight_lanes_graph_replay(api, oracle_mod):
+    """The configuration bench.py times: 1920x1080 (C2), 8 feature buffers = 8 detection lanes, device-resident inputs, every lane
+    replaying its CUDA graph (captured on the second use of a buffer).  Three rounds of 8 detections in flight, every buffer
+    compared with the oracle after every round."""
+    import torch
+    from vulkansift_b200.synth import blob_image, C2
+    imgs = [blob_image(**dict(C2, seed=C2["seed"] + i)) for i in range(4)]
+    orc = oracle_mod.Oracle()
+    exp = [orc.detect(im) for im in imgs]
+    assert all(2500 <= len(e) <= 3800 for e in exp)
+    h, w = imgs[0].shape
+    dev = [torch.from_numpy(im).cuda() for im in imgs]
+    torch.cuda.synchronize()
+    with api.Instance(input_image_max_size=w * h, sift_buffer_count=8) as inst:
+        assert inst.lane_count() == 8
+        for rep in range(3):
+            for b in range(8):
+                inst.detect_device(dev[(b + rep) % 4].data_ptr(), w, h, b)
+            for b in range(8):
+                assert_features_equal(inst.download_features(b), exp[(b + rep) % 4], "round %d buffer %d" % (rep, b))
+
+
+def test_small_images_eight_lanes(api, oracle_mod):
+    """configs[2] pattern on one GPU: 8 x 640x480 in flight on 8 lanes, three rounds (graph replay from the second)."""
+    from vulkansift_b200.synth import blob_image, C1
+    imgs = [blob_image(**dict(C1, seed=C1["seed"] + i)) for i in range(8)]
+    orc = oracle_mod.Oracle()
+    exp = [orc.detect(im) for im in imgs]
+    with api.Instance(input_image_max_size=640 * 480, sift_buffer_count=8) as inst:
+        for rep in range(3):
+            for b in range(8):
+                inst.detect(imgs[(b + 3 * rep) % 8], b)
+            for b in range(8):
+                assert_features_equal(inst.download_features(b), exp[(b + 3 * rep) % 8], "round %d buffer %d" % (rep, b))
+
+
+@pytest.mark.parametrize("max_feats", [50, 300])
+def test_many_raw_extrema_small_buffer_keeps_lowest_accepted_keys(api, oracle_mod, max_feats):
+    """A blocky noise image yields tens of thousands of strict extrema and ~5.6 k accepted keypoints in octave 0 while the buffer holds 50
+    or 300: the kept set must be the oracle's (lowest (s, y, x) keys among the ACCEPTED keypoints of each octave, then the
+    section clamp), whatever order the GPU found them in.  (Round 1 queued raw extrema in a max_nb_sift_per_buffer-sized
+    buffer and dropped the overflow in arrival order.)"""
+    rng = np.random.default_rng(17)
+    img = np.kron(rng.integers(0, 256, (100, 133), dtype=np.uint8), np.ones((3, 3), np.uint8))  # 300x399 field of 3x3 blocks
+    kw = {"max_nb_sift_per_buffer": max_feats}
+    orc = oracle_mod.Oracle(**kw)
+    exp = orc.detect(img)
+    found, kept = orc.section_counts()
+    assert found[0] > 4 * kept[0], "octave 0 must overflow by a wide margin"
+    with api.Instance(**kw) as inst:
+        for rep in range(3):
+            inst.detect(img, rep % 2)
+            assert_features_equal(inst.download_features(rep % 2), exp, "max %d rep %d" % (max_feats, rep))
+
+
+def test_too_many_scales_is_rejected_at_creation(api):
+    """nb_scales_per_octave beyond what the extrema scan can stage must fail in vksift_createInstance with an input error,
+    not later inside every vksift_detectFeatures."""
+    with pytest.raises(api.VksiftError) as e:
+        api.Instance(nb_scales_per_octave=12)
+    assert e.value.code == api.VKSIFT_INVALID_INPUT_ERROR
+    with api.Instance(nb_scales_per_octave=8) as inst:
+        inst.detect(np.full((100, 100), 7, np.uint8), 0)
+        assert inst.features_number(0) == 0

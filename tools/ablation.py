@@ -1,16 +1,14 @@
-"""What each stage costs in the pipelined (8-lane) schedule: throughput with stages left out (vksiftx_setDebugSkip).
-Analysis aid, run on the GPU box."""
+"""What each stage costs in the pipelined (8-lane) schedule: throughput with stages left out (vksiftx_setDebugSkip of the
+ANALYSIS build of the library, vulkansift_b200/analysis.py; the product library has no such switch).  Run on the GPU box."""
 import os
 import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
-from vulkansift_b200 import api  # noqa: E402
+from vulkansift_b200 import analysis as api  # noqa: E402
 from vulkansift_b200.synth import blob_image, C2  # noqa: E402
 
-api.load()
-api.lib.vksift_setLogLevel(api.VKSIFT_LOG_WARNING)
 imgs = [blob_image(**dict(C2, seed=C2["seed"] + i)) for i in range(4)]
 h, w = imgs[0].shape
 dev = [torch.from_numpy(im).cuda() for im in imgs]

@@ -59,11 +59,11 @@ class VksiftError(RuntimeError):
         super().__init__("%s in %s" % (name, where))
 
 
-def _load_library():
-    if not os.path.exists(LIB_PATH):
+def _load_library(path=LIB_PATH, analysis=False):
+    if not os.path.exists(path):
         raise ImportError("%s is missing: build it with `python -m vulkansift_b200.build` (needs nvcc). "
-                          "There is no CPU fallback." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+                          "There is no CPU fallback." % path)
+    lib = C.CDLL(path)
     I, P = C.c_void_p, C.POINTER
     u32, u8 = C.c_uint32, C.c_uint8
     sig = {
@@ -110,8 +110,9 @@ def _load_library():
         "vksiftx_getEffectiveTaps": (None, [I, C.c_void_p, C.c_void_p]),
         "vksiftx_getSectionCapacities": (None, [I, u32, C.c_void_p]),
         "vksiftx_setMatcherImpl": (None, [I, C.c_int32]),
-        "vksiftx_setDebugSkip": (None, [I, C.c_int32]),
     }
+    if analysis:  # libvulkansift_analysis.so only (-DVKS_ANALYSIS)
+        sig["vksiftx_setDebugSkip"] = (None, [I, C.c_int32])
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
@@ -155,22 +156,29 @@ def default_config():
 class Instance:
     """One vksift_Instance (one GPU).  Keyword arguments override vksift_Config fields."""
 
+    _lib = None  # the product library; vulkansift_b200.analysis.Instance binds the analysis build instead
+
     def __init__(self, **overrides):
-        load()
+        if self._lib is None:
+            type(self)._lib = lib
+        self._ensure_loaded()
         self._errors = []
         self._cb = ERROR_CALLBACK(lambda code: self._errors.append(int(code)))
-        self.config = default_config()
+        self.config = self._lib.vksift_getDefaultConfig()
         for k, v in overrides.items():
             if not hasattr(self.config, k):
                 raise AttributeError("vksift_Config has no field %r" % k)
             setattr(self.config, k, v)
         self.config.on_error_callback_function = self._cb
         self._h = C.c_void_p(None)
-        r = lib.vksift_createInstance(C.byref(self._h), C.byref(self.config))
+        r = self._lib.vksift_createInstance(C.byref(self._h), C.byref(self.config))
         if r != VKSIFT_SUCCESS:
             raise VksiftError(r, "vksift_createInstance")
 
     # -- plumbing
+    def _ensure_loaded(self):
+        load()
+
     def _check(self, where):
         if self._errors:
             code = self._errors[0]
@@ -179,7 +187,7 @@ class Instance:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
-            lib.vksift_destroyInstance(C.byref(self._h))
+            self._lib.vksift_destroyInstance(C.byref(self._h))
 
     def __del__(self):
         try:
@@ -198,15 +206,15 @@ class Instance:
         """vksift_detectFeatures: image is a (h,w) uint8 numpy array (host memory)."""
         image = np.ascontiguousarray(image, np.uint8)
         h, w = image.shape
-        lib.vksift_detectFeatures(self._h, image.ctypes.data, w, h, buffer_id)
+        self._lib.vksift_detectFeatures(self._h, image.ctypes.data, w, h, buffer_id)
         self._check("vksift_detectFeatures")
 
     def detect_raw(self, ptr, w, h, buffer_id=0):
-        lib.vksift_detectFeatures(self._h, ptr, w, h, buffer_id)
+        self._lib.vksift_detectFeatures(self._h, ptr, w, h, buffer_id)
         self._check("vksift_detectFeatures")
 
     def features_number(self, buffer_id=0):
-        n = lib.vksift_getFeaturesNumber(self._h, buffer_id)
+        n = self._lib.vksift_getFeaturesNumber(self._h, buffer_id)
         self._check("vksift_getFeaturesNumber")
         return n
 
@@ -219,38 +227,38 @@ class Instance:
         else:
             assert out.dtype == FEATURE_DTYPE and len(out) >= n
             out = out[:n]
-        lib.vksift_downloadFeatures(self._h, out.ctypes.data, buffer_id)
+        self._lib.vksift_downloadFeatures(self._h, out.ctypes.data, buffer_id)
         self._check("vksift_downloadFeatures")
         return out
 
     def upload_features(self, feats, buffer_id=0):
         feats = np.ascontiguousarray(feats)
         assert feats.dtype == FEATURE_DTYPE
-        lib.vksift_uploadFeatures(self._h, feats.ctypes.data, len(feats), buffer_id)
+        self._lib.vksift_uploadFeatures(self._h, feats.ctypes.data, len(feats), buffer_id)
         self._check("vksift_uploadFeatures")
 
     def match(self, buffer_a=0, buffer_b=1):
-        lib.vksift_matchFeatures(self._h, buffer_a, buffer_b)
+        self._lib.vksift_matchFeatures(self._h, buffer_a, buffer_b)
         self._check("vksift_matchFeatures")
 
     def matches_number(self):
-        return lib.vksift_getMatchesNumber(self._h)
+        return self._lib.vksift_getMatchesNumber(self._h)
 
     def download_matches(self):
         out = np.zeros(self.matches_number(), MATCH_DTYPE)
-        lib.vksift_downloadMatches(self._h, out.ctypes.data)
+        self._lib.vksift_downloadMatches(self._h, out.ctypes.data)
         self._check("vksift_downloadMatches")
         return out
 
     def is_buffer_available(self, buffer_id=0):
-        return bool(lib.vksift_isBufferAvailable(self._h, buffer_id))
+        return bool(self._lib.vksift_isBufferAvailable(self._h, buffer_id))
 
     def nb_octaves(self):
-        return lib.vksift_getScaleSpaceNbOctaves(self._h)
+        return self._lib.vksift_getScaleSpaceNbOctaves(self._h)
 
     def octave_resolution(self, octave):
         w, h = C.c_uint32(0), C.c_uint32(0)
-        lib.vksift_getScaleSpaceOctaveResolution(self._h, octave, C.byref(w), C.byref(h))
+        self._lib.vksift_getScaleSpaceOctaveResolution(self._h, octave, C.byref(w), C.byref(h))
         self._check("vksift_getScaleSpaceOctaveResolution")
         return w.value, h.value
 
@@ -265,107 +273,104 @@ class Instance:
         return out
 
     def download_scale_space_image(self, octave, scale):
-        return self._download_layer(lib.vksift_downloadScaleSpaceImage, "vksift_downloadScaleSpaceImage", octave, scale)
+        return self._download_layer(self._lib.vksift_downloadScaleSpaceImage, "vksift_downloadScaleSpaceImage", octave, scale)
 
     def download_dog_image(self, octave, scale):
-        return self._download_layer(lib.vksift_downloadDoGImage, "vksift_downloadDoGImage", octave, scale)
+        return self._download_layer(self._lib.vksift_downloadDoGImage, "vksift_downloadDoGImage", octave, scale)
 
     def present_debug_frame(self):
-        lib.vksift_presentDebugFrame(self._h)
+        self._lib.vksift_presentDebugFrame(self._h)
 
     # -- extensions
     @property
     def device_index(self):
-        return lib.vksiftx_getDeviceIndex(self._h)
+        return self._lib.vksiftx_getDeviceIndex(self._h)
 
     @property
     def stream(self):
-        return lib.vksiftx_getStream(self._h)
+        return self._lib.vksiftx_getStream(self._h)
 
     def detect_device(self, dev_ptr, w, h, buffer_id=0):
-        lib.vksiftx_detectFeaturesDevice(self._h, dev_ptr, w, h, buffer_id)
+        self._lib.vksiftx_detectFeaturesDevice(self._h, dev_ptr, w, h, buffer_id)
         self._check("vksiftx_detectFeaturesDevice")
 
     def wait_idle(self):
-        lib.vksiftx_waitIdle(self._h)
+        self._lib.vksiftx_waitIdle(self._h)
 
     def lane_count(self):
-        return int(lib.vksiftx_getLaneCount(self._h))
+        return int(self._lib.vksiftx_getLaneCount(self._h))
 
     def join_lanes(self):
-        lib.vksiftx_joinLanes(self._h)
+        self._lib.vksiftx_joinLanes(self._h)
 
     def buffer_device_view(self, buffer_id=0):
         n, d, hd = C.c_uint32(0), C.c_void_p(None), C.c_void_p(None)
-        lib.vksiftx_getBufferDeviceView(self._h, buffer_id, C.byref(n), C.byref(d), C.byref(hd))
+        self._lib.vksiftx_getBufferDeviceView(self._h, buffer_id, C.byref(n), C.byref(d), C.byref(hd))
         self._check("vksiftx_getBufferDeviceView")
         return n.value, d.value, hd.value
 
     def upload_descriptors_device(self, dev_ptr, n, buffer_id=0):
-        lib.vksiftx_uploadDescriptorsDevice(self._h, dev_ptr, n, buffer_id)
+        self._lib.vksiftx_uploadDescriptorsDevice(self._h, dev_ptr, n, buffer_id)
         self._check("vksiftx_uploadDescriptorsDevice")
 
     def copy_descriptors_to_device(self, buffer_id, dev_ptr, capacity):
-        n = lib.vksiftx_copyDescriptorsToDevice(self._h, buffer_id, dev_ptr, capacity)
+        n = self._lib.vksiftx_copyDescriptorsToDevice(self._h, buffer_id, dev_ptr, capacity)
         self._check("vksiftx_copyDescriptorsToDevice")
         return n
 
     def match_against_device(self, buffer_a, dev_ptr, n_b):
         """2-NN of buffer_a's features against n_b descriptors read in place from device memory."""
-        lib.vksiftx_matchFeaturesAgainstDevice(self._h, buffer_a, dev_ptr, n_b)
+        self._lib.vksiftx_matchFeaturesAgainstDevice(self._h, buffer_a, dev_ptr, n_b)
         self._check("vksiftx_matchFeaturesAgainstDevice")
 
     def matches_device(self):
-        return lib.vksiftx_getMatchesDevice(self._h)
+        return self._lib.vksiftx_getMatchesDevice(self._h)
 
     def set_profiling(self, enabled=True):
-        lib.vksiftx_setProfiling(self._h, bool(enabled))
+        self._lib.vksiftx_setProfiling(self._h, bool(enabled))
 
     def stage_times_ms(self):
         t = (C.c_float * NB_STAGES)()
-        lib.vksiftx_getStageTimesMs(self._h, t)
+        self._lib.vksiftx_getStageTimesMs(self._h, t)
         return dict(zip(STAGE_NAMES, [float(v) for v in t]))
 
     def match_cross_checked(self, buf_a, buf_b, lowe_ratio=0.75):
         """(n,2) uint32 pairs (idx in A, idx in B): mutual nearest neighbours passing the ratio test in both directions."""
         cap = max(1, self.features_number(buf_a))
         out = np.zeros((cap, 2), np.uint32)
-        n = int(lib.vksiftx_matchFeaturesCrossChecked(self._h, buf_a, buf_b, lowe_ratio, out.ctypes.data_as(C.POINTER(C.c_uint32)), cap))
+        n = int(self._lib.vksiftx_matchFeaturesCrossChecked(self._h, buf_a, buf_b, lowe_ratio, out.ctypes.data_as(C.POINTER(C.c_uint32)), cap))
         self._check("vksiftx_matchFeaturesCrossChecked")
         return out[:min(n, cap)]
 
     def set_launch_trace(self, enabled=True):
-        lib.vksiftx_setLaunchTrace(self._h, bool(enabled))
+        self._lib.vksiftx_setLaunchTrace(self._h, bool(enabled))
 
     def set_serial_schedule(self, enabled=True):
-        lib.vksiftx_setSerialSchedule(self._h, bool(enabled))
+        self._lib.vksiftx_setSerialSchedule(self._h, bool(enabled))
 
     def launch_trace(self, capacity=256):
         """[(name, start_us, end_us)] of the scale-space launches of the last (traced) detection."""
         names = (C.c_char * 32 * capacity)()
         t0 = (C.c_float * capacity)()
         t1 = (C.c_float * capacity)()
-        n = int(lib.vksiftx_getLaunchTrace(self._h, C.cast(names, C.c_void_p), t0, t1, capacity))
+        n = int(self._lib.vksiftx_getLaunchTrace(self._h, C.cast(names, C.c_void_p), t0, t1, capacity))
         return [(bytes(names[i]).split(b"\0")[0].decode(), float(t0[i]), float(t1[i])) for i in range(min(n, capacity))]
 
     def kernel_launch_count(self):
-        return int(lib.vksiftx_getKernelLaunchCount(self._h))
+        return int(self._lib.vksiftx_getKernelLaunchCount(self._h))
 
     def effective_taps(self):
         n = self.config.nb_scales_per_octave + 3
         radius = np.zeros(n, np.uint32)
         taps = np.zeros((n, 21), np.float32)
-        lib.vksiftx_getEffectiveTaps(self._h, radius.ctypes.data, taps.ctypes.data)
+        self._lib.vksiftx_getEffectiveTaps(self._h, radius.ctypes.data, taps.ctypes.data)
         return radius, taps
 
     def section_capacities(self, buffer_id=0):
         caps = np.zeros(16, np.uint32)
-        lib.vksiftx_getSectionCapacities(self._h, buffer_id, caps.ctypes.data)
+        self._lib.vksiftx_getSectionCapacities(self._h, buffer_id, caps.ctypes.data)
         self._check("vksiftx_getSectionCapacities")
         return caps
 
-    def set_debug_skip(self, mask):
-        lib.vksiftx_setDebugSkip(self._h, int(mask))
-
     def set_matcher_impl(self, impl):
-        lib.vksiftx_setMatcherImpl(self._h, int(impl))
+        self._lib.vksiftx_setMatcherImpl(self._h, int(impl))

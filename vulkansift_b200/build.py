@@ -17,6 +17,9 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(HERE, "lib", "libvulkansift.so")
+# same sources with -DVKS_ANALYSIS: adds vksiftx_setDebugSkip (stage ablation, invalid results).  Only tools/ablation.py and
+# bench.py's marginal-cost measurement load it; every timed or parity-checked detection runs on LIB, which has no such switch.
+LIB_ANALYSIS = os.path.join(HERE, "lib", "libvulkansift_analysis.so")
 SOURCES = ["api.cu", "plan.cu", "pyramid.cu", "extrema.cu", "describe.cu", "match.cu"]
 HEADERS = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [
     os.path.join(ROOT, "include", "vksift_arith.h"), os.path.join(ROOT, "include", "vksift_b200_ext.h"),
@@ -46,6 +49,7 @@ def build(force=False, verbose=False):
     cc = nvcc()
     objs = []
     procs = []
+    analysis_objs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
@@ -53,6 +57,14 @@ def build(force=False, verbose=False):
         if force or _stale(o, [s, __file__] + HEADERS):
             cmd = [cc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        if src == "api.cu":  # the only translation unit that looks at VKS_ANALYSIS
+            oa = os.path.join(OBJ, "api_analysis.o")
+            analysis_objs.append(oa)
+            if force or _stale(oa, [s, __file__] + HEADERS):
+                cmd = [cc] + NVCC_FLAGS + ["-DVKS_ANALYSIS", "-c", s, "-o", oa]
+                procs.append((src + " (analysis)", subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        else:
+            analysis_objs.append(o)
     failed = False
     for src, p in procs:
         out, _ = p.communicate()
@@ -67,6 +79,12 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             sys.stderr.write(r.stdout)
             raise RuntimeError("link failed")
+    if force or procs or _stale(LIB_ANALYSIS, analysis_objs):
+        cmd = [cc, "-shared", "-o", LIB_ANALYSIS] + analysis_objs + ["-Xlinker", "--no-undefined"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout)
+            raise RuntimeError("link failed (analysis library)")
     return LIB
 
 

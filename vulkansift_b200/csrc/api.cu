@@ -116,10 +116,10 @@ struct vksift_Instance_T
     std::vector<FusedLaunch> rest;   /* remaining layers, second side stream */
   };
   std::vector<FusedOct> fused_oct;             /* small octaves [k,n): fused kernel, one or two launches per octave */
-  MegaPlan *mega = nullptr;                    /* whole scale space as one persistent launch, when the configuration allows it */
-  bool use_mega = false;
   bool serial = false;   /* vksiftx_setSerialSchedule */
-  int debug_skip = 0;    /* VKSIFT_DEBUG_SKIP bit mask (ablation timing only, results invalid): 1 descriptors, 2 orientation, 4 extrema+order, 8 scale space */
+#ifdef VKS_ANALYSIS
+  int debug_skip = 0;    /* analysis build only (libvulkansift_analysis.so): stages left out for ablation timing, results invalid: 1 descriptors, 2 orientation, 4 extrema+order, 8 scale space */
+#endif
   bool no_split = false; /* VKSIFT_NO_SPLIT=1: extrema/orientation of all octaves after the whole pyramid (debug) */
   cudaStream_t side_stream = nullptr, side2_stream = nullptr;
   cudaEvent_t ev_chain[VKS_MAX_OCT] = {nullptr}; /* chain launches of octave o enqueued on the side stream */
@@ -162,9 +162,8 @@ struct vksift_Instance_T
   std::vector<FeatureBuffer> own_buffers; /* primary only */
   FeatureBuffer *buffers = nullptr;       /* own_buffers.data() of the primary */
   uint32_t n_buffers = 0;
-  Candidate *cand = nullptr;
-  unsigned long long *raw = nullptr; /* queued extrema (s,y,x) per octave */
-  uint32_t cand_cap = 0;
+  uint32_t *compact_mem = nullptr; /* [raw extrema bitmap | accepted bitmap | row counts] of the ordered compaction (extrema.cu) */
+  size_t compact_alloc_words = 0, bm_words = 0, compact_rows = 0;
   FeatHead *prim = nullptr;
   float *ori = nullptr;
   uint32_t *n_ori = nullptr;
@@ -251,7 +250,8 @@ bool config_valid(const vksift_Config *c)
   need(c->sift_buffer_count > 0, "Invalid configuration: number of SIFT buffers must be greater than zero");
   need(c->max_nb_sift_per_buffer > 0, "Invalid configuration: number of SIFT features per buffers must be greater than zero");
   need(c->nb_scales_per_octave > 0, "Invalid configuration: number of scales per octave must be greater than zero");
-  need(c->nb_scales_per_octave + 3 <= VKS_MAX_LAYERS, "Invalid configuration: too many scales per octave for this build");
+  need(c->nb_scales_per_octave + 3 <= VKS_MAX_LAYERS && extrema_scales_supported(c->nb_scales_per_octave),
+       "Invalid configuration: too many scales per octave for this build (the extrema scan stages all DoG layers of a tile in shared memory: at most 9)");
   need(c->input_image_blur_level >= 0.f, "Invalid configuration: input image blur level cannot be negative");
   need(c->seed_scale_sigma >= 0, "Invalid configuration: seed scale blur level cannot be negative");
   need(seed_ok, "Invalid configuration: the input image blur level (2x if upscaling activated) must be less than the seed scale blur level");
@@ -380,30 +380,9 @@ bool build_blur_plan(vksift_Instance inst)
    * (all passes that are ready share a launch) in a side stream and join before the extrema scan. */
   inst->fast_oct.clear();
   inst->steps_side.clear();
-  mega_plan_destroy(inst->mega);
-  inst->mega = nullptr;
   if (p.n_oct == 0)
     return true;
   bool ok = true;
-  if (inst->use_mega)
-  {
-    /* preferred: one persistent launch for the whole scale space */
-    std::vector<std::vector<BlurPass>> all;
-    bool prepared = true;
-    for (int o = 0; o < (int)p.n_oct && prepared; o++)
-    {
-      std::vector<BlurPass> passes;
-      for (int s = (o == 0 ? 0 : 1); s < ns + 3 && prepared; s++)
-      {
-        BlurPass bp = make_pass((uint32_t)o, s);
-        prepared = bp.radius <= 12 && blur_pass_prepare_fast(&bp, true);
-        passes.push_back(bp);
-      }
-      all.push_back(passes);
-    }
-    if (prepared && mega_plan_build(all, ns, &inst->mega))
-      return true;
-  }
   int k = 0;
   for (; k < (int)p.n_oct; k++)
   {
@@ -507,11 +486,29 @@ bool set_resolution(vksift_Instance inst, uint32_t w, uint32_t h)
   if (!build_blur_plan(inst))
     return false;
   {
-    /* tensor maps of the extrema scan only depend on the pyramid geometry */
+    /* tensor maps of the extrema scan and the bitmaps of the ordered compaction only depend on the pyramid geometry */
     DetectParams P;
     FeatureBuffer dummy;
     fill_detect_params(inst, dummy, &P);
     CU_TRY(extrema_plan_build(P, &inst->extrema_plan));
+    size_t words = 0, rows = 0;
+    extrema_layout(&P, &words, &rows);
+    if (words >= (1ull << 31))
+    {
+      LOGE(TAG, "scale space too large for the keypoint bitmaps (%zu words)", words);
+      return false;
+    }
+    inst->bm_words = words;
+    inst->compact_rows = rows;
+    if (2 * words + rows > inst->compact_alloc_words)
+    {
+      if (inst->compact_mem)
+        CU_TRY(cudaFree(inst->compact_mem));
+      inst->compact_mem = nullptr;
+      inst->compact_alloc_words = 0;
+      CU_TRY(cudaMalloc(&inst->compact_mem, sizeof(uint32_t) * (2 * words + rows)));
+      inst->compact_alloc_words = 2 * words + rows;
+    }
   }
   return true;
 }
@@ -555,8 +552,12 @@ void fill_detect_params(vksift_Instance inst, const FeatureBuffer &fb, DetectPar
   P->max_ori = c.max_nb_orientation_per_keypoint;
   P->ori_stride = inst->ori_stride;
   P->vlfeat = (c.descriptor_format == VKSIFT_DESCRIPTOR_FORMAT_VLFEAT) ? 1 : 0;
-  P->cand_cap = inst->cand_cap;
   P->max_feats = c.max_nb_sift_per_buffer;
+  size_t words = 0, rows = 0;
+  extrema_layout(P, &words, &rows);
+  P->raw_bm = inst->compact_mem;
+  P->acc_bm = inst->compact_mem + inst->bm_words;
+  P->row_cnt = inst->compact_mem + 2 * inst->bm_words;
 }
 
 void wait_lane(vksift_Instance lane)
@@ -595,7 +596,7 @@ uint32_t buffer_count(vksift_Instance inst, uint32_t idx, bool log_lost)
   if (log_lost)
   {
     uint32_t lost = 0;
-    for (uint32_t o = 0; o < VKS_MAX_OCT; o++)
+    for (uint32_t o = 0; o < fb.n_oct && o < VKS_MAX_OCT; o++) /* slots of higher octaves may be stale from an earlier, larger resolution */
       lost += fb.host_counts[1 + o] - fb.host_counts[1 + VKS_MAX_OCT + o];
     if (lost > 0)
       LOGE(TAG,
@@ -637,8 +638,7 @@ void destroy_instance(vksift_Instance inst)
   if (inst->h_src_slot)
     cudaFreeHost(inst->h_src_slot);
   cudaFree(inst->d_src_slot);
-  cudaFree(inst->cand);
-  cudaFree(inst->raw);
+  cudaFree(inst->compact_mem);
   cudaFree(inst->prim);
   cudaFree(inst->ori);
   cudaFree(inst->n_ori);
@@ -649,7 +649,6 @@ void destroy_instance(vksift_Instance inst)
   cudaFree(inst->d_matches);
   cudaFree(inst->d_matches_rev);
   cudaFree(inst->d_pairs);
-  mega_plan_destroy(inst->mega);
   match_workspace_destroy(inst->match_ws);
   extrema_plan_destroy(inst->extrema_plan);
   for (int i = 0; i < EV_COUNT; i++)
@@ -735,21 +734,14 @@ bool create_resources(vksift_Instance inst)
   }
   {
     /* Alternative schedules of the same kernels (measurements in DESIGN.md):
-     * VKSIFT_MEGA=1: the whole scale space as one persistent dataflow launch instead of per-layer launches (slower).
      * VKSIFT_GRAPH=0/1: replay of the detection as a CUDA graph, the analogue of the reference's pre-recorded command
      * buffer.  A replay costs 8 us of CPU time instead of 210 us but loses the programmatic-dependent-launch edges and
      * the stream priorities, so one detection alone is ~20 us slower; with several lanes the throughput is what counts
      * and the replay wins (0.315 against 0.321 ms per 1920x1080 image), so it is the default exactly then. */
     const char *g = getenv("VKSIFT_GRAPH");
-    const char *m = getenv("VKSIFT_MEGA");
-    inst->use_mega = (m && m[0] == '1');
     const char *nsp = getenv("VKSIFT_NO_SPLIT");
     inst->no_split = (nsp && nsp[0] == '1');
-    if (const char *ds = getenv("VKSIFT_DEBUG_SKIP"))
-      inst->debug_skip = atoi(ds);
-    if (inst->use_mega)
-      n_lanes = 1; /* the persistent kernel takes a new epoch per launch */
-    inst->use_graph = (g ? g[0] == '1' : n_lanes > 1) && !inst->use_mega;
+    inst->use_graph = (g ? g[0] == '1' : n_lanes > 1);
     if (inst->primary)
       inst->use_graph = inst->primary->use_graph;
   }
@@ -757,9 +749,6 @@ bool create_resources(vksift_Instance inst)
   const size_t maxf = c.max_nb_sift_per_buffer;
   inst->ori_stride = (c.max_nb_orientation_per_keypoint == 0 || c.max_nb_orientation_per_keypoint > VKS_MAX_ORI) ? VKS_MAX_ORI
                                                                                                                    : c.max_nb_orientation_per_keypoint;
-  inst->cand_cap = c.max_nb_sift_per_buffer;
-  CU_TRY(cudaMalloc(&inst->cand, sizeof(Candidate) * (size_t)inst->cand_cap * (inst->max_octaves ? inst->max_octaves : 1)));
-  CU_TRY(cudaMalloc(&inst->raw, sizeof(unsigned long long) * (size_t)inst->cand_cap * (inst->max_octaves ? inst->max_octaves : 1)));
   CU_TRY(cudaMalloc(&inst->prim, sizeof(FeatHead) * (maxf + 1)));
   CU_TRY(cudaMalloc(&inst->ori, sizeof(float) * (maxf + 1) * inst->ori_stride));
   CU_TRY(cudaMalloc(&inst->n_ori, sizeof(uint32_t) * (maxf + 1)));
@@ -821,6 +810,12 @@ bool create_resources(vksift_Instance inst)
   }
   return true;
 }
+
+#ifdef VKS_ANALYSIS
+#define VKS_SKIP(inst) ((inst)->debug_skip)
+#else
+#define VKS_SKIP(inst) 0
+#endif
 
 struct TraceScope
 {
@@ -886,14 +881,9 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D0], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   CU_TRY(cudaMemsetAsync(fb.cnt, 0, sizeof(DetectCounters), st));
+  CU_TRY(cudaMemsetAsync(inst->compact_mem, 0, sizeof(uint32_t) * (2 * inst->bm_words + inst->compact_rows), st));
   const int ns = inst->cfg.nb_scales_per_octave;
   const int n_fast = (int)inst->fast_oct.size();
-  if (inst->mega)
-  {
-    TraceScope ts(inst, st, "persistent pyramid", 0, 0);
-    CU_TRY(launch_mega(inst->mega, st));
-    inst->launches++;
-  }
   /* Split schedule: the extrema scan, ordering and orientation pass of an octave (their per-octave sections are
    * independent) follow that octave's scale space on the same stream, so they overlap the scale space of the later
    * octaves, a latency chain that leaves the GPU nearly idle at its end; everything joins before the feature assembly. */
@@ -901,21 +891,20 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
    * a launch times that kernel alone */
   const bool serial = inst->serial;
   cudaStream_t side2 = serial ? st : inst->side2_stream;
-  const bool split = (n_fast > 0) && !inst->fused_oct.empty() && n_fast < P.n_oct && !inst->no_split && !inst->mega && !serial;
+  const bool split = (n_fast > 0) && !inst->fused_oct.empty() && n_fast < P.n_oct && !inst->no_split && !serial;
   inst->ev_d1b_valid = split && prof;
   inst->n_pyr_events = (split && prof) ? n_fast : 0;
   auto post_chain = [&](int ob, int oe, cudaStream_t s) -> bool {
     DetectParams Q = P;
     Q.ob = ob;
     Q.oe = oe;
-    if (!(inst->debug_skip & 4))
+    if (!(VKS_SKIP(inst) & 4))
     {
-      CU_TRY(launch_extrema(Q, inst->extrema_plan, inst->raw, inst->cand, fb.cnt, s));
-      CU_TRY(launch_order_primaries(Q, inst->cand, fb.cnt, inst->prim, s));
+      CU_TRY(launch_extrema(Q, inst->extrema_plan, fb.cnt, inst->prim, s, &inst->launches));
     }
-    if (!(inst->debug_skip & 2))
+    if (!(VKS_SKIP(inst) & 2))
       CU_TRY(launch_orientation(Q, fb.cnt, inst->prim, inst->ori, inst->n_ori, s));
-    inst->launches += 4;
+    inst->launches += 1;
     return true;
   };
   for (int o = 0; o < n_fast; o++)
@@ -925,7 +914,7 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
       CU_TRY(cudaStreamWaitEvent(so, inst->ev_seed[o], 0));
     for (BlurPass &bp : inst->fast_oct[o])
     {
-      if (!(inst->debug_skip & 8))
+      if (!(VKS_SKIP(inst) & 8))
       {
         TraceScope ts(inst, so, "fast o%d r%d", o, bp.radius);
         CU_TRY(launch_blur_pass_fast(bp, so));
@@ -964,7 +953,7 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
       for (const FusedLaunch &F : fo.chain)
       {
         TraceScope ts(inst, ss, "fused chain o%d n%d", n_fast + (int)j, F.n_layers);
-        if (!(inst->debug_skip & 8))
+        if (!(VKS_SKIP(inst) & 8))
           CU_TRY(launch_fused(F, ss));
         inst->launches++;
       }
@@ -975,7 +964,7 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
         for (const FusedLaunch &F : fo.rest)
         {
           TraceScope ts(inst, side2, "fused rest o%d n%d", n_fast + (int)j, F.n_layers);
-          if (!(inst->debug_skip & 8))
+          if (!(VKS_SKIP(inst) & 8))
             CU_TRY(launch_fused(F, side2));
           inst->launches++;
         }
@@ -1038,15 +1027,13 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   DetectParams PA = P;
   if (split)
     PA.oe = 1; /* octave 0 (its layers are complete on this stream); the other octaves follow on the side stream */
-  if (!(inst->debug_skip & 4))
+  if (!(VKS_SKIP(inst) & 4))
   {
-    CU_TRY(launch_extrema(PA, inst->extrema_plan, inst->raw, inst->cand, fb.cnt, st));
-    CU_TRY(launch_order_primaries(PA, inst->cand, fb.cnt, inst->prim, st));
+    CU_TRY(launch_extrema(PA, inst->extrema_plan, fb.cnt, inst->prim, st, &inst->launches));
   }
-  inst->launches += 3;
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D2], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
-  if (!(inst->debug_skip & 2))
+  if (!(VKS_SKIP(inst) & 2))
     CU_TRY(launch_orientation(PA, fb.cnt, inst->prim, inst->ori, inst->n_ori, st));
   inst->launches++;
   if (split)
@@ -1059,7 +1046,7 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D3], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   CU_TRY(launch_assemble(P, fb.cnt, inst->n_ori, inst->feat_src, fb.host_counts_dev, st));
-  if (!(inst->debug_skip & 1))
+  if (!(VKS_SKIP(inst) & 1))
     CU_TRY(launch_descriptors(P, fb.cnt, inst->desc_m_table, inst->prim, inst->ori, inst->feat_src, fb.heads, fb.desc, st));
   inst->launches += 2;
   if (prof)
@@ -2014,6 +2001,7 @@ extern "C"
 
   void vksiftx_setMatcherImpl(vksift_Instance inst, const int32_t impl) { inst->matcher_impl = impl; }
 
+#ifdef VKS_ANALYSIS
   void vksiftx_setDebugSkip(vksift_Instance inst, const int32_t mask)
   {
     wait_pipelines(inst, true, true);
@@ -2023,5 +2011,6 @@ extern "C"
       invalidate_graphs(lane);
     }
   }
+#endif
 
 } /* extern "C" */

@@ -1,13 +1,22 @@
 /*
- * extrema.cu -- DoG extrema scan, sub-pixel refinement and deterministic ordering.
+ * extrema.cu -- DoG extrema scan, sub-pixel refinement and deterministic ordered compaction.
  *
  * Replaces ExtractKeypoints.comp (reference: shaders/ExtractKeypoints.comp:44-231,
  * dispatched by sift_detector.c:1106-1189).  The reference appends accepted
- * keypoints with atomicAdd, i.e. in a race-dependent order; here accepted
- * keypoints carry the id of the thread that detected them, key = (s, y, x), and
- * a rank pass places them in increasing key order -- the canonical order of
- * SURVEY.md B-D4, which the oracle produces by construction.  Section overflow
- * therefore drops the highest keys deterministically.
+ * keypoints with atomicAdd, i.e. in a race-dependent order; here the order is the
+ * one of the detecting thread ids, key = (s, y, x) -- the canonical order of
+ * SURVEY.md B-D4, which the oracle produces by construction -- and nothing on the
+ * way has a capacity that depends on the image:
+ *   extrema_kernel      every strict extremum sets ONE BIT of a (s, y, x) bitmap (ns*w*h bits per octave)
+ *   refine_mark_kernel  walks that bitmap, refines each extremum (:118-224); an accepted keypoint sets its bit
+ *                       in a second bitmap and counts into its (s, y) row
+ *   row_scan_kernel     exclusive scan of the row counts -> first rank of every row, n_cand, n_prim
+ *   rank_emit_kernel    walks the accepted bitmap: rank = row start + accepted bits in front of it in the row; the
+ *                       keypoints whose rank is below the section capacity are refined again (deterministic, a few
+ *                       thousand of them) and written to slot `rank`
+ * Section overflow therefore keeps exactly the lowest keys among the ACCEPTED keypoints, like the oracle, however many
+ * raw extrema the image produces (the first version queued raw extrema in a buffer of max_nb_sift_per_buffer entries
+ * and dropped the overflow in atomic-arrival order).
  *
  * All float expressions keep the association order of the shader; the library
  * is compiled with -fmad=false so nothing is contracted.
@@ -144,7 +153,7 @@ __device__ __forceinline__ bool extrema_tile_coords(const DetectParams &P, int t
 
 template <int EX_THREADS>
 __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ ExtremaMaps maps, int t_begin,
-                                                      int n_tiles, unsigned long long *__restrict__ raw, DetectCounters *__restrict__ cnt)
+                                                      int n_tiles, DetectCounters *__restrict__ cnt)
 {
   constexpr int EX_RPT = EX_TH / (EX_THREADS / 256); /* rows per thread */
   extern __shared__ __align__(128) float ex_smem[];
@@ -255,13 +264,11 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
 #undef EX_CMP
           if (!(gt || lt))
             continue;
-          /* a strict extremum: queue it.  The sub-pixel refinement (a long serial chain of dependent global
-           * loads and divisions for one lane) runs in its own kernel with one thread per queued candidate,
+          /* a strict extremum: mark it.  The sub-pixel refinement (a long serial chain of dependent global
+           * loads and divisions for one lane) runs in its own kernel over the marked bits,
            * instead of stalling this tile's whole CTA at the next barrier. */
           const int y = y0 + ly + r;
-          const uint32_t slot = atomicAdd(&cnt->n_raw[o], 1u);
-          if (slot < P.cand_cap)
-            raw[(size_t)o * P.cand_cap + slot] = ((unsigned long long)s << 40) | ((unsigned long long)y << 20) | (unsigned long long)x;
+          atomicOr(P.raw_bm + P.bm_off[o] + (size_t)((s - 1) * oh + y) * P.bm_rw[o] + (uint32_t)(x >> 5), 1u << (x & 31));
         }
       }
     }
@@ -269,28 +276,150 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
   }
 }
 
-/* ExtractKeypoints.comp:118-224 for the queued extrema: one thread per candidate, all octaves in one launch */
-__global__ void __launch_bounds__(128) refine_kernel(const __grid_constant__ DetectParams P, const unsigned long long *__restrict__ raw,
-                                                     Candidate *__restrict__ cand, DetectCounters *__restrict__ cnt)
+/* ---- ordered compaction ------------------------------------------------------------------------------------------
+ * Bitmap geometry of the octaves [P.ob, P.oe): the launch covers their words as one range, thread = word. */
+__device__ __forceinline__ bool bm_locate(const DetectParams &P, uint32_t g, int *o_out, uint32_t *word_in_oct)
 {
-  const int o = P.ob + (int)blockIdx.y;
-  const uint32_t n = min(cnt->n_raw[o], P.cand_cap);
-  const OctaveView &ov = P.oct[o];
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  for (int o = P.ob; o < P.oe; o++)
   {
-    const unsigned long long key = raw[(size_t)o * P.cand_cap + i];
-    const int s = (int)(key >> 40), y = (int)((key >> 20) & 0xfffffu), x = (int)(key & 0xfffffu);
-    FeatHead hd;
-    if (!refine_keypoint(P, ov, o, x, y, s, &hd))
-      continue;
-    const uint32_t slot = atomicAdd(&cnt->n_cand[o], 1u);
-    if (slot < P.cand_cap)
+    const uint32_t n = (uint32_t)(P.ns * P.oct[o].h) * P.bm_rw[o];
+    if (g < n)
     {
-      Candidate cd;
-      cd.key = key;
-      cd.head = hd;
-      cd.pad_ = 0;
-      cand[(size_t)o * P.cand_cap + slot] = cd;
+      *o_out = o;
+      *word_in_oct = g;
+      return true;
+    }
+    g -= n;
+  }
+  return false;
+}
+
+/* ExtractKeypoints.comp:118-224 for the marked extrema: thread = one bitmap word (32 consecutive x of one (s, y) row);
+ * almost every word is empty, a thread with set bits refines them one after the other */
+#define BM_THREADS 256
+__global__ void __launch_bounds__(BM_THREADS) refine_mark_kernel(const __grid_constant__ DetectParams P, uint32_t total_words,
+                                                                 DetectCounters *__restrict__ cnt)
+{
+  for (uint32_t g = blockIdx.x * BM_THREADS + threadIdx.x; g < total_words; g += gridDim.x * BM_THREADS)
+  {
+    int o;
+    uint32_t wi;
+    if (!bm_locate(P, g, &o, &wi))
+      break;
+    uint32_t bits = P.raw_bm[P.bm_off[o] + wi];
+    if (bits == 0)
+      continue;
+    const OctaveView &ov = P.oct[o];
+    const uint32_t rw = P.bm_rw[o];
+    const uint32_t row = wi / rw, xw = wi - row * rw; /* row = (s-1)*h + y */
+    const int s = (int)(row / (uint32_t)ov.h) + 1, y = (int)(row % (uint32_t)ov.h);
+    uint32_t acc = 0, n_raw = 0;
+    while (bits)
+    {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      n_raw++;
+      FeatHead hd;
+      if (refine_keypoint(P, ov, o, (int)(xw * 32u) + b, y, s, &hd))
+        acc |= 1u << b;
+    }
+    atomicAdd(&cnt->n_raw[o], n_raw);
+    if (acc)
+    {
+      P.acc_bm[P.bm_off[o] + wi] = acc;
+      atomicAdd(P.row_cnt + P.row_off[o] + row, (uint32_t)__popc(acc));
+    }
+  }
+}
+
+/* one CTA per octave: row_cnt -> exclusive prefix (first rank of each row), n_cand = accepted keypoints (the
+ * reference's counter keeps counting past the capacity, ExtractKeypoints.comp:208-211), n_prim = min(n_cand, cap) */
+#define SCAN_THREADS 1024
+__global__ void __launch_bounds__(SCAN_THREADS) row_scan_kernel(const __grid_constant__ DetectParams P, DetectCounters *__restrict__ cnt)
+{
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int o = P.ob + (int)blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+  const uint32_t n_rows = (uint32_t)(P.ns * P.oct[o].h);
+  uint32_t *__restrict__ rc = P.row_cnt + P.row_off[o];
+  if (tid == 0)
+    s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_rows; base += SCAN_THREADS)
+  {
+    const uint32_t i = base + tid;
+    const uint32_t e = (i < n_rows) ? rc[i] : 0u;
+    uint32_t v = e;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d)
+        v += t;
+    }
+    if (lane == 31)
+      s_warp[wi] = v;
+    __syncthreads();
+    if (wi == 0)
+    {
+      uint32_t wv = s_warp[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
+      {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wv, d);
+        if (lane >= d)
+          wv += t;
+      }
+      s_warp[lane] = wv;
+    }
+    __syncthreads();
+    const uint32_t carry = s_carry;
+    if (i < n_rows)
+      rc[i] = carry + (wi ? s_warp[wi - 1] : 0u) + (v - e);
+    __syncthreads();
+    if (tid == SCAN_THREADS - 1)
+      s_carry = carry + s_warp[31];
+    __syncthreads();
+  }
+  if (tid == 0)
+  {
+    cnt->n_cand[o] = s_carry;
+    cnt->n_prim[o] = min(s_carry, P.cap[o]);
+  }
+}
+
+/* thread = one word of the accepted bitmap; rank of a keypoint = first rank of its row + accepted bits in front of it */
+__global__ void __launch_bounds__(BM_THREADS) rank_emit_kernel(const __grid_constant__ DetectParams P, uint32_t total_words,
+                                                               FeatHead *__restrict__ prim)
+{
+  for (uint32_t g = blockIdx.x * BM_THREADS + threadIdx.x; g < total_words; g += gridDim.x * BM_THREADS)
+  {
+    int o;
+    uint32_t wi;
+    if (!bm_locate(P, g, &o, &wi))
+      break;
+    const uint32_t *__restrict__ bm = P.acc_bm + P.bm_off[o];
+    uint32_t bits = bm[wi];
+    if (bits == 0)
+      continue;
+    const OctaveView &ov = P.oct[o];
+    const uint32_t rw = P.bm_rw[o];
+    const uint32_t row = wi / rw, xw = wi - row * rw;
+    uint32_t rank = P.row_cnt[P.row_off[o] + row];
+    if (rank >= P.cap[o])
+      continue; /* the whole row lies beyond the section capacity */
+    for (uint32_t k = 0; k < xw; k++)
+      rank += (uint32_t)__popc(bm[wi - xw + k]);
+    const int s = (int)(row / (uint32_t)ov.h) + 1, y = (int)(row % (uint32_t)ov.h);
+    while (bits && rank < P.cap[o])
+    {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      FeatHead hd;
+      refine_keypoint(P, ov, o, (int)(xw * 32u) + b, y, s, &hd); /* accepted before: same inputs, same result */
+      prim[P.sec_off[o] + rank] = hd;
+      rank++;
     }
   }
 }
@@ -326,22 +455,40 @@ cudaError_t extrema_plan_build(const DetectParams &P, ExtremaPlan **plan_io)
 
 void extrema_plan_destroy(ExtremaPlan *pl) { delete pl; }
 
-cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, unsigned long long *raw, Candidate *cand, DetectCounters *cnt,
-                           cudaStream_t st)
+void extrema_layout(DetectParams *P, size_t *bm_words, size_t *rows)
+{
+  size_t words = 0, nrows = 0;
+  for (int o = 0; o < P->n_oct; o++)
+  {
+    P->bm_off[o] = (uint32_t)words;
+    P->bm_rw[o] = (uint32_t)((P->oct[o].w + 31) / 32);
+    P->row_off[o] = (uint32_t)nrows;
+    const size_t r = (size_t)P->ns * (size_t)P->oct[o].h;
+    words += r * P->bm_rw[o];
+    nrows += r;
+  }
+  *bm_words = words;
+  *rows = nrows;
+}
+
+cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectCounters *cnt, FeatHead *prim, cudaStream_t st, uint64_t *launch_count)
 {
   if (!pl || !pl->valid || pl->n_tiles == 0 || P.oe <= P.ob)
     return cudaSuccess;
   int t_begin = 0, t_end = 0;
+  uint32_t total_words = 0;
   for (int o = 0; o < P.oe; o++)
   {
     const int n = ((P.oct[o].w + EX_TW - 1) / EX_TW) * ((P.oct[o].h + EX_TH - 1) / EX_TH);
     if (o < P.ob)
       t_begin += n;
+    else
+      total_words += (uint32_t)(P.ns * P.oct[o].h) * P.bm_rw[o];
     t_end += n;
   }
   const size_t smem = 2 * sizeof(float) * (size_t)((((P.ns + 2) * EX_SH * EX_SW) + 31) & ~31);
   if (smem > 220 * 1024)
-    return cudaErrorInvalidConfiguration; /* nb_scales_per_octave too large for the double-buffered tile */
+    return cudaErrorInvalidConfiguration; /* rejected at instance creation (extrema_scales_supported) */
   static bool attr_done[64] = {false};
   static int threads = 0;
   if (threads == 0)
@@ -366,61 +513,24 @@ cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, unsigne
   if (grid > t_end - t_begin)
     grid = t_end - t_begin;
   if (threads == 256)
-    extrema_kernel<256><<<grid, 256, smem, st>>>(P, pl->maps, t_begin, t_end, raw, cnt);
+    extrema_kernel<256><<<grid, 256, smem, st>>>(P, pl->maps, t_begin, t_end, cnt);
   else
-    extrema_kernel<512><<<grid, 512, smem, st>>>(P, pl->maps, t_begin, t_end, raw, cnt);
+    extrema_kernel<512><<<grid, 512, smem, st>>>(P, pl->maps, t_begin, t_end, cnt);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
-  refine_kernel<<<dim3(32, P.oe - P.ob, 1), 128, 0, st>>>(P, raw, cand, cnt);
+  /* one thread per bitmap word, at most 8 CTAs per SM in flight: a thread then visits a handful of words */
+  uint32_t bgrid = (total_words + BM_THREADS - 1) / BM_THREADS;
+  if (bgrid > (uint32_t)sms * 8u)
+    bgrid = (uint32_t)sms * 8u;
+  refine_mark_kernel<<<bgrid, BM_THREADS, 0, st>>>(P, total_words, cnt);
+  row_scan_kernel<<<P.oe - P.ob, SCAN_THREADS, 0, st>>>(P, cnt);
+  rank_emit_kernel<<<bgrid, BM_THREADS, 0, st>>>(P, total_words, prim);
+  *launch_count += 4;
   return cudaGetLastError();
 }
 
-/* Rank pass: candidate i of octave o goes to slot #{j : key_j < key_i}; slots
- * beyond the section capacity are dropped (ExtractKeypoints.comp:208-211 keeps
- * counting past max_nb_feat, so does n_cand). */
-#define ORD_THREADS 256
-__global__ void __launch_bounds__(ORD_THREADS) order_primaries_kernel(const __grid_constant__ DetectParams P, const Candidate *__restrict__ cand,
-                                                                      DetectCounters *__restrict__ cnt, FeatHead *__restrict__ prim)
-{
-  __shared__ unsigned long long s_keys[ORD_THREADS];
-  const int o = P.ob + (int)blockIdx.y;
-  const uint32_t n_all = cnt->n_cand[o];
-  const uint32_t n = min(n_all, P.cand_cap);
-  if (blockIdx.x == 0 && threadIdx.x == 0)
-    cnt->n_prim[o] = min(n, P.cap[o]);
-  if (blockIdx.x * ORD_THREADS >= n)
-    return;
-  const Candidate *__restrict__ lst = cand + (size_t)o * P.cand_cap;
-  const uint32_t i = blockIdx.x * ORD_THREADS + threadIdx.x;
-  const unsigned long long my = (i < n) ? lst[i].key : ~0ull;
-  uint32_t rank = 0;
-  for (uint32_t base = 0; base < n; base += ORD_THREADS)
-  {
-    const uint32_t j = base + threadIdx.x;
-    s_keys[threadIdx.x] = (j < n) ? lst[j].key : ~0ull;
-    __syncthreads();
-    const uint32_t m = min((uint32_t)ORD_THREADS, n - base);
-    for (uint32_t k = 0; k < m; k++)
-      rank += (s_keys[k] < my) ? 1u : 0u;
-    __syncthreads();
-  }
-  if (i < n && rank < P.cap[o])
-    prim[P.sec_off[o] + rank] = lst[i].head;
-}
-
-cudaError_t launch_order_primaries(const DetectParams &P, const Candidate *cand, DetectCounters *cnt, FeatHead *prim, cudaStream_t st)
-{
-  if (P.oe <= P.ob)
-    return cudaSuccess;
-  /* worst case grid; CTAs beyond the candidate count exit immediately */
-  uint32_t max_cap = 0;
-  for (int o = 0; o < P.n_oct; o++)
-    max_cap = P.cap[o] > max_cap ? P.cap[o] : max_cap;
-  uint32_t bx = (P.cand_cap + ORD_THREADS - 1) / ORD_THREADS;
-  dim3 grid(bx, P.oe - P.ob, 1);
-  order_primaries_kernel<<<grid, ORD_THREADS, 0, st>>>(P, cand, cnt, prim);
-  return cudaGetLastError();
-}
+/* largest nb_scales_per_octave whose double-buffered scan tile fits in shared memory */
+bool extrema_scales_supported(int ns) { return 2 * sizeof(float) * (size_t)((((ns + 2) * EX_SH * EX_SW) + 31) & ~31) <= 220 * 1024; }
 
 } // namespace vks

@@ -705,208 +705,6 @@ __global__ void __launch_bounds__(FT_THREADS, ft_ctas_per_sm(R)) blur_pass_fast_
   blur_tile<R, KIND, TH, BAR_OFF>(P.p, &P.p.tmap, P.taps2, ft_smem, x0, y0, 0u, true);
 }
 
-/* --------------------------------------------------------------------------
- * Whole-pyramid persistent kernel ("dataflow" schedule).
- *
- * With one launch per layer the scale space is a chain of ~25 dependent launches (layer s needs layer s-1,
- * octave o+1 needs layer ns of octave o): every link costs a launch gap, a cold instruction cache and a
- * partially filled last wave, and the small octaves at the end of the chain leave the GPU almost empty.
- * Here ONE launch runs the whole scale space: two resident CTAs per SM take tiles from two work lists and
- * synchronise through per-tile completion stamps in global memory instead of kernel boundaries.
- *   - critical list: the layers every later octave waits for (octave 0: 0..ns, octaves >= 1: 1..ns, last
- *     octave: all), octave after octave, tiles in row-major order
- *   - filler list: layers ns+1, ns+2 of the other octaves, which nothing but the extrema scan waits for
- *   A CTA takes the head of the critical list when that tile's sources are complete, otherwise a filler tile,
- *   and only spins when nothing else is left; dependencies always precede dependents inside a list and filler
- *   tiles only depend on critical ones, so a claimed tile never waits for an unclaimed one.
- *   - a tile of layer (o,s>=1) needs the 3x3 neighbourhood of tiles of (o,s-1); a tile of (o>=1,1) needs the
- *     4x4 block of tiles of (o-1,ns) that wrote its part of the seed layer
- *   - completion: every thread fences its stores, the CTA synchronises, one thread publishes the launch's
- *     epoch in the tile's stamp; consumers acquire the stamps, then order the TMA (async proxy) behind them
- * The tile code is blur_tile<R,KIND> with compile-time radii: the kernel is built for the radius table of
- * nb_scales_per_octave = 3 (4, 6, 8, 10, 12 for layers 1..5, which only depends on seed_scale_sigma = 1.6) and
- * a seed radius of 4 or 6; other configurations use the per-layer launches.
- * -------------------------------------------------------------------------- */
-#define MG_MAX_SCALES 6
-struct MegaLayer
-{
-  BlurPass p;         /* geometry, pointers, tensor map of the source layer */
-  uint32_t *done;     /* completion stamp per tile of this layer */
-  const uint32_t *dep_done; /* stamps of the layer this one reads, or NULL */
-  int dep_tiles_x, dep_tiles_y;
-  int dep_kind;       /* 0 none, 1 same octave (3x3 tiles), 2 previous octave (4x4 tiles) */
-  int scale;          /* layer index inside the octave */
-};
-
-struct MegaParams
-{
-  const MegaLayer *layers;
-  const uint32_t *crit, *fill; /* work lists: (layer << 16) | tile */
-  int n_crit, n_fill;
-  uint32_t *heads; /* [0] critical head, [1] filler head; zeroed before every launch */
-  uint32_t epoch;
-  int seed_radius; /* even-rounded radius of layer 0 */
-  int debug_no_deps; /* VKSIFT_MEGA_NODEPS=1: timing experiment, results are wrong */
-  float2 taps2[MG_MAX_SCALES][14];
-};
-
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
-{
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-
-/* stamps of the source tiles of `tile` of layer L all carry `epoch`?  Called by the 32 lanes of one warp: lane i looks
- * at source tile i of the (at most 4x4) block, one L2 round trip in total; the caller fences once they all do. */
-__device__ __forceinline__ bool mega_deps_ready(const MegaLayer *L, int tile, uint32_t epoch, int lane)
-{
-  const int kind = L->dep_kind;
-  if (kind == 0)
-    return true;
-  const int tiles_x = L->p.tiles_x;
-  const int tx = tile % tiles_x, ty = tile / tiles_x;
-  const int span = kind == 1 ? 3 : 4;
-  const int dx = (kind == 1 ? tx - 1 : 2 * tx - 1) + lane % span;
-  const int dy = (kind == 1 ? ty - 1 : 2 * ty - 1) + lane / span;
-  bool ok = true;
-  if (lane < span * span && dx >= 0 && dx < L->dep_tiles_x && dy >= 0 && dy < L->dep_tiles_y)
-    ok = (*(const volatile uint32_t *)(L->dep_done + dy * L->dep_tiles_x + dx) == epoch);
-  return __all_sync(0xffffffffu, ok);
-}
-
-__global__ void __launch_bounds__(FT_THREADS, 2) pyramid_mega_kernel(const __grid_constant__ MegaParams P)
-{
-  extern __shared__ __align__(128) float ft_smem[];
-  __shared__ MegaLayer s_layer;
-  __shared__ int s_item;
-  const int tid = threadIdx.x;
-  if (tid == 0)
-  {
-    const uint32_t bar0 = tma_smem_u32(ft_smem + FT_BAR_OFF);
-#pragma unroll
-    for (int b = 0; b < FT_NB; b++)
-      tma_mbar_init(bar0 + 8 * b, 1);
-    tma_mbar_fence_init();
-  }
-  uint32_t parity = 0;
-  int held = -1, held_fill = -1; /* claimed critical / filler tile whose sources are not complete yet (warp 0) */
-  bool crit_empty = false, fill_empty = false;
-  for (;;)
-  {
-    __syncthreads(); /* previous tile done with s_layer / s_item / the tile buffers; barriers initialised */
-    if (tid < 32)
-    {
-      /* Warp 0 picks the next tile.  A CTA claims tiles in list order (one atomicAdd per claim, no contention) and keeps
-       * a claimed tile until its sources are complete: at most one critical and, while that one waits, one filler tile;
-       * it runs whichever is ready first, critical before filler.  A tile only depends on tiles that come earlier in its
-       * own list or in the critical list, so the earliest unfinished tile always has complete sources and an owner
-       * that will look at it again: no tile waits for an unclaimed one. */
-      int item = -1;
-      uint32_t backoff = 32;
-      for (;;)
-      {
-        if (held < 0 && !crit_empty)
-        {
-          uint32_t h = 0;
-          if (tid == 0)
-            h = atomicAdd(&P.heads[0], 1u);
-          h = __shfl_sync(0xffffffffu, h, 0);
-          if (h < (uint32_t)P.n_crit)
-            held = (int)P.crit[h];
-          else
-            crit_empty = true;
-        }
-        if (held >= 0 && (P.debug_no_deps || mega_deps_ready(P.layers + (held >> 16), held & 0xffff, P.epoch, tid)))
-        {
-          item = held;
-          held = -1;
-          break;
-        }
-        /* the critical tile cannot run yet: claim (once) a filler tile as well and run whichever is ready first */
-        if (held_fill < 0 && !fill_empty)
-        {
-          uint32_t f = 0;
-          if (tid == 0)
-            f = atomicAdd(&P.heads[1], 1u);
-          f = __shfl_sync(0xffffffffu, f, 0);
-          if (f < (uint32_t)P.n_fill)
-            held_fill = (int)P.fill[f];
-          else
-            fill_empty = true;
-        }
-        if (held_fill >= 0 && mega_deps_ready(P.layers + (held_fill >> 16), held_fill & 0xffff, P.epoch, tid))
-        {
-          item = held_fill;
-          held_fill = -1;
-          break;
-        }
-        if (held < 0 && held_fill < 0 && crit_empty && fill_empty)
-          break; /* nothing left */
-        __nanosleep(backoff);
-        backoff = backoff < 512 ? backoff * 2 : 512;
-      }
-      if (item >= 0)
-        __threadfence(); /* acquire: the stamps were read with plain volatile loads */
-      if (tid == 0)
-        s_item = item;
-    }
-    __syncthreads();
-    const int item = s_item;
-    if (item < 0)
-      break;
-    const MegaLayer *gl = P.layers + (item >> 16);
-    {
-      /* layer description -> shared memory (the tensor map is used from global memory) */
-      const uint32_t *src = reinterpret_cast<const uint32_t *>(gl);
-      uint32_t *dst = reinterpret_cast<uint32_t *>(&s_layer);
-      for (int i = tid; i < (int)(sizeof(MegaLayer) / 4); i += FT_THREADS)
-        dst[i] = src[i];
-    }
-    __syncthreads();
-    const BlurPass &p = s_layer.p;
-    const int tile = item & 0xffff;
-    const int x0 = (tile % p.tiles_x) * FT_W;
-    const int y0 = (tile / p.tiles_x) * FT_H;
-    const CUtensorMap *tmap = &gl->p.tmap;
-    switch (s_layer.scale)
-    {
-    case 0:
-      if (P.seed_radius == 4)
-        blur_tile<4, FT_KIND_SEED, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[0], ft_smem, x0, y0, parity, false);
-      else
-        blur_tile<6, FT_KIND_SEED, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[0], ft_smem, x0, y0, parity, false);
-      break;
-    case 1:
-      blur_tile<4, FT_KIND_LAYER, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[1], ft_smem, x0, y0, parity, false);
-      break;
-    case 2:
-      blur_tile<6, FT_KIND_LAYER, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[2], ft_smem, x0, y0, parity, false);
-      break;
-    case 3:
-      if (p.dst_next)
-        blur_tile<8, FT_KIND_NEXT, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[3], ft_smem, x0, y0, parity, false);
-      else /* last octave: nothing to seed */
-        blur_tile<8, FT_KIND_LAYER, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[3], ft_smem, x0, y0, parity, false);
-      break;
-    case 4:
-      blur_tile<10, FT_KIND_LAYER, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[4], ft_smem, x0, y0, parity, false);
-      break;
-    default:
-      blur_tile<12, FT_KIND_LAYER, FT_H, FT_BAR_OFF>(p, tmap, P.taps2[5], ft_smem, x0, y0, parity, false);
-      break;
-    }
-    if (s_layer.scale != 0)
-      parity ^= 1u; /* the TMA barriers completed one phase */
-    /* publish: every thread's stores are visible device-wide before the stamp is */
-    __threadfence();
-    __syncthreads();
-    if (tid == 0)
-      st_release_u32(gl->done + tile, P.epoch);
-  }
-}
-
 /* ==========================================================================
  * Fused kernel for the small octaves.
  *
@@ -1157,190 +955,6 @@ cudaError_t launch_fused(const FusedLaunch &F, cudaStream_t st)
   return launch_pdl(octave_fused_kernel, tiles, FZ_THREADS, FZ_SMEM, st, F);
 }
 
-/* ---- host side of the persistent kernel ---------------------------------- */
-struct MegaPlan
-{
-  MegaParams P;
-  void *d_blob = nullptr; /* layers, stamps, work lists, heads in one allocation */
-  int grid = 0;
-};
-
-void mega_plan_destroy(MegaPlan *pl)
-{
-  if (!pl)
-    return;
-  cudaFree(pl->d_blob);
-  delete pl;
-}
-
-/* oct_passes[o] = the passes of octave o in layer order (octave 0 starts at layer 0, the others at layer 1), prepared with
- * blur_pass_prepare_fast.  Returns false (and no plan) when the configuration is not the one the kernel is built for. */
-bool mega_plan_build(const std::vector<std::vector<BlurPass>> &oct_passes, int ns, MegaPlan **io)
-{
-  mega_plan_destroy(*io);
-  *io = nullptr;
-  static const int want[MG_MAX_SCALES] = {0, 4, 6, 8, 10, 12};
-  const int n_oct = (int)oct_passes.size();
-  if (ns != 3 || n_oct < 1 || n_oct > VKS_MAX_OCT)
-    return false;
-  std::vector<MegaLayer> layers;
-  std::vector<int> first_layer(n_oct, 0), n_tiles_before;
-  size_t n_stamps = 0;
-  int seed_radius = 0;
-  for (int o = 0; o < n_oct; o++)
-  {
-    first_layer[o] = (int)layers.size();
-    const int s_first = (o == 0) ? 0 : 1;
-    if ((int)oct_passes[o].size() != ns + 3 - s_first)
-      return false;
-    for (size_t i = 0; i < oct_passes[o].size(); i++)
-    {
-      const BlurPass &bp = oct_passes[o][i];
-      const int sc = s_first + (int)i;
-      const int re = ft_even(bp.radius);
-      if (bp.radius < 1)
-        return false;
-      if (sc == 0)
-      {
-        if (bp.src_kind == BLUR_SRC_LAYER || (re != 4 && re != 6))
-          return false;
-        seed_radius = re;
-      }
-      else if (bp.src_kind != BLUR_SRC_LAYER || re != want[sc])
-        return false;
-      if (bp.w < 2 * 12 || bp.h < 2 * 12 || bp.tiles_x * bp.tiles_y > 0xffff) /* one reflection per halo; tile index in 16 bits */
-        return false;
-      MegaLayer L;
-      memset(&L, 0, sizeof(L));
-      L.p = bp;
-      L.scale = sc;
-      layers.push_back(L);
-      n_tiles_before.push_back((int)n_stamps);
-      n_stamps += (size_t)bp.tiles_x * bp.tiles_y;
-    }
-  }
-  if (layers.size() > 0xffff)
-    return false;
-  /* work lists */
-  std::vector<uint32_t> crit, fill;
-  for (int o = 0; o < n_oct; o++)
-  {
-    const int s_first = (o == 0) ? 0 : 1;
-    for (int sc = s_first; sc < ns + 3; sc++)
-    {
-      const int li = first_layer[o] + (sc - s_first);
-      const int nt = layers[li].p.tiles_x * layers[li].p.tiles_y;
-      std::vector<uint32_t> &lst = (sc <= ns || o == n_oct - 1) ? crit : fill;
-      for (int t = 0; t < nt; t++)
-        lst.push_back(((uint32_t)li << 16) | (uint32_t)t);
-    }
-  }
-  /* one device blob: [layers][stamps][crit][fill][heads] */
-  auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  const size_t off_layers = 0;
-  const size_t off_stamps = align(off_layers + layers.size() * sizeof(MegaLayer));
-  const size_t off_crit = align(off_stamps + n_stamps * 4);
-  const size_t off_fill = align(off_crit + crit.size() * 4);
-  const size_t off_heads = align(off_fill + fill.size() * 4 + 4);
-  const size_t total = off_heads + 256;
-  MegaPlan *pl = new MegaPlan();
-  if (cudaMalloc(&pl->d_blob, total) != cudaSuccess)
-  {
-    delete pl;
-    cudaGetLastError();
-    return false;
-  }
-  char *base = (char *)pl->d_blob;
-  uint32_t *stamps = (uint32_t *)(base + off_stamps);
-  for (int o = 0; o < n_oct; o++)
-  {
-    const int s_first = (o == 0) ? 0 : 1;
-    for (int sc = s_first; sc < ns + 3; sc++)
-    {
-      const int li = first_layer[o] + (sc - s_first);
-      MegaLayer &L = layers[li];
-      L.done = stamps + n_tiles_before[li];
-      if (sc > s_first)
-      {
-        const MegaLayer &D = layers[li - 1];
-        L.dep_done = stamps + n_tiles_before[li - 1];
-        L.dep_tiles_x = D.p.tiles_x;
-        L.dep_tiles_y = D.p.tiles_y;
-        L.dep_kind = 1;
-      }
-      else if (o > 0)
-      {
-        const int di = first_layer[o - 1] + (ns - ((o - 1 == 0) ? 0 : 1)); /* layer ns of the previous octave */
-        const MegaLayer &D = layers[di];
-        L.dep_done = stamps + n_tiles_before[di];
-        L.dep_tiles_x = D.p.tiles_x;
-        L.dep_tiles_y = D.p.tiles_y;
-        L.dep_kind = 2;
-      }
-    }
-  }
-  bool ok = cudaMemset(pl->d_blob, 0, total) == cudaSuccess;
-  ok = ok && cudaMemcpy(base + off_layers, layers.data(), layers.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice) == cudaSuccess;
-  ok = ok && cudaMemcpy(base + off_crit, crit.data(), crit.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
-  ok = ok && (fill.empty() || cudaMemcpy(base + off_fill, fill.data(), fill.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess);
-  if (!ok)
-  {
-    cudaGetLastError();
-    mega_plan_destroy(pl);
-    return false;
-  }
-  memset(&pl->P, 0, sizeof(pl->P));
-  pl->P.layers = (const MegaLayer *)(base + off_layers);
-  pl->P.crit = (const uint32_t *)(base + off_crit);
-  pl->P.fill = (const uint32_t *)(base + off_fill);
-  pl->P.n_crit = (int)crit.size();
-  pl->P.n_fill = (int)fill.size();
-  pl->P.heads = (uint32_t *)(base + off_heads);
-  pl->P.epoch = 0;
-  pl->P.seed_radius = seed_radius;
-  {
-    const char *e = getenv("VKSIFT_MEGA_NODEPS");
-    pl->P.debug_no_deps = (e && e[0] == '1') ? 1 : 0;
-  }
-  for (int o = 0, li = 0; o < 1; o++)
-    for (size_t i = 0; i < oct_passes[0].size() && i < MG_MAX_SCALES; i++, li++)
-      for (int k = 0; k < 14; k++)
-      {
-        const BlurPass &bp = oct_passes[0][i];
-        const float v = (k <= bp.radius) ? bp.taps[k] : 0.f;
-        pl->P.taps2[i][k] = make_float2(v, v);
-      }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int items = (int)(crit.size() + fill.size());
-  pl->grid = items < 2 * sms ? items : 2 * sms;
-  *io = pl;
-  return true;
-}
-
-cudaError_t launch_mega(MegaPlan *pl, cudaStream_t st)
-{
-  static bool attr_done[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !attr_done[dev])
-  {
-    cudaError_t e = cudaFuncSetAttribute(pyramid_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES);
-    if (e != cudaSuccess)
-      return e;
-    attr_done[dev] = true;
-  }
-  cudaError_t e = cudaMemsetAsync(pl->P.heads, 0, 8, st);
-  if (e != cudaSuccess)
-    return e;
-  pl->P.epoch++;
-  if (pl->P.epoch == 0)
-    pl->P.epoch = 1;
-  pyramid_mega_kernel<<<pl->grid, FT_THREADS, FT_SMEM_BYTES, st>>>(pl->P);
-  return cudaGetLastError();
-}
-
 /* A pass goes to the fast per-layer kernel when its radius is covered and the layer is large enough for
  * throughput to matter (one 64x128 tile per SM or more); smaller octaves are latency bound and take the
  * fused kernel (or, when their radii do not fit it, the compact kernel). */
@@ -1367,10 +981,10 @@ bool blur_step_tiles(BlurStep *step)
   return true;
 }
 
-bool blur_pass_prepare_fast(BlurPass *bpp, bool persistent)
+bool blur_pass_prepare_fast(BlurPass *bpp)
 {
   BlurPass &bp = *bpp;
-  bp.tile_h = persistent ? FT_H : ft_tile_h(ft_even(bp.radius));
+  bp.tile_h = ft_tile_h(ft_even(bp.radius));
   bp.tiles_x = (bp.w + FT_W - 1) / FT_W;
   bp.tiles_y = (bp.h + bp.tile_h - 1) / bp.tile_h;
   bp.tile_begin = 0;

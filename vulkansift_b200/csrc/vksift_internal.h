@@ -58,15 +58,6 @@ struct OctaveView
   int layer_stride; /* floats between layers = pitch*h */
 };
 
-/* accepted keypoint before ordering */
-struct Candidate
-{
-  unsigned long long key; /* (s << 40) | (y << 20) | x : detection-thread order of SURVEY B-D4 */
-  FeatHead head;
-  uint32_t pad_;
-};
-static_assert(sizeof(Candidate) == 48, "Candidate layout");
-
 struct DetectParams
 {
   OctaveView oct[VKS_MAX_OCT];
@@ -78,14 +69,19 @@ struct DetectParams
   uint32_t max_ori;    /* 0 = unlimited */
   uint32_t ori_stride; /* orientation slots per primary */
   int vlfeat;
-  uint32_t cand_cap; /* candidate list capacity per octave */
   uint32_t max_feats;
+  /* ordered compaction of the keypoints (extrema.cu): one bit per (s, y, x) with s in [1, ns], rows of bm_rw[o] 32-bit words;
+   * bit (s, y, x) of octave o = bit (x & 31) of word bm_off[o] + ((s-1)*h + y) * bm_rw[o] + (x >> 5) */
+  uint32_t *raw_bm;   /* strict extrema */
+  uint32_t *acc_bm;   /* keypoints accepted by the refinement */
+  uint32_t *row_cnt;  /* accepted keypoints per (s, y) row, turned into the row's first rank by row_scan_kernel */
+  uint32_t bm_off[VKS_MAX_OCT], bm_rw[VKS_MAX_OCT], row_off[VKS_MAX_OCT];
 };
 
 /* per-buffer device counters, zeroed at the start of every detection */
 struct DetectCounters
 {
-  uint32_t n_raw[VKS_MAX_OCT];    /* strict extrema queued for refinement */
+  uint32_t n_raw[VKS_MAX_OCT];    /* strict extrema found (statistics) */
   uint32_t n_cand[VKS_MAX_OCT];   /* accepted keypoints found (may exceed capacity) */
   uint32_t n_prim[VKS_MAX_OCT];   /* primaries kept = min(n_cand, cap) */
   uint32_t n_found[VKS_MAX_OCT];  /* primaries + extra orientations found */
@@ -177,23 +173,20 @@ bool blur_step_tiles(BlurStep *step);
 /* true when the pass runs on the unrolled packed-fp32 kernel, false for the compact kernel */
 bool blur_pass_is_fast(const BlurPass &bp);
 /* tile geometry + TMA tensor map of a pass for the fast kernel */
-bool blur_pass_prepare_fast(BlurPass *bp, bool persistent = false);
+bool blur_pass_prepare_fast(BlurPass *bp);
 cudaError_t launch_blur_pass_fast(const BlurPass &bp, cudaStream_t st);
 cudaError_t launch_blur_step(const BlurStep &step, cudaStream_t st);
 /* groups consecutive layer passes of one octave into fused launches; false when a pass cannot be fused */
 bool fused_plan_octave(const BlurPass *passes, int n_pass, std::vector<FusedLaunch> *out);
 cudaError_t launch_fused(const FusedLaunch &F, cudaStream_t st);
-/* the whole scale space as one persistent launch (pyramid.cu); build returns false for configurations it is not compiled for */
-struct MegaPlan;
-bool mega_plan_build(const std::vector<std::vector<BlurPass>> &oct_passes, int ns, MegaPlan **io);
-void mega_plan_destroy(MegaPlan *pl);
-cudaError_t launch_mega(MegaPlan *pl, cudaStream_t st);
 struct ExtremaPlan; /* TMA tensor maps over the DoG layers of the current pyramid */
 cudaError_t extrema_plan_build(const DetectParams &P, ExtremaPlan **plan_io);
 void extrema_plan_destroy(ExtremaPlan *pl);
-cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, unsigned long long *raw, Candidate *cand, DetectCounters *cnt,
-                           cudaStream_t st);
-cudaError_t launch_order_primaries(const DetectParams &P, const Candidate *cand, DetectCounters *cnt, FeatHead *prim, cudaStream_t st);
+/* scan + refinement + ordered compaction of the octaves [P.ob, P.oe): prim[sec_off[o] + rank] for rank < cap[o] */
+cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectCounters *cnt, FeatHead *prim, cudaStream_t st, uint64_t *launch_count);
+/* words of each bitmap and rows of row_cnt the current pyramid needs; fills bm_off / bm_rw / row_off of P */
+void extrema_layout(DetectParams *P, size_t *bm_words, size_t *rows);
+bool extrema_scales_supported(int ns);
 cudaError_t launch_orientation(const DetectParams &P, DetectCounters *cnt, const FeatHead *prim, float *ori, uint32_t *n_ori, cudaStream_t st);
 cudaError_t launch_assemble(const DetectParams &P, DetectCounters *cnt, const uint32_t *n_ori, uint32_t *feat_src, uint32_t *host_counts,
                             cudaStream_t st);
