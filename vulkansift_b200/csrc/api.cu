@@ -107,6 +107,9 @@ struct vksift_Instance_T
   Pyramid pyr;
   ExtremaPlan *extrema_plan = nullptr;
   std::vector<std::vector<BlurPass>> fast_oct; /* octaves [0,k) on the fast kernel: one stream per octave, one launch per layer */
+  std::vector<std::vector<StripLaunch>> strip_oct; /* per fast octave: the multi-layer strip launches that replace its per-layer launches
+                                                      of layers >= 1 (empty: the octave keeps the per-layer launches) */
+  bool use_strip = false; /* VKSIFT_STRIP=1: multi-layer strip kernel for the large octaves (first version: bit-exact, slower than the per-layer launches) */
   std::vector<BlurStep> steps_side;            /* small octaves [k,n) that cannot be fused: compact kernel, wavefront steps on the side stream */
   struct FusedOct
   {
@@ -379,6 +382,7 @@ bool build_blur_plan(vksift_Instance inst)
    * The remaining small octaves [k,n) are latency bound; they run on the compact kernel as one wavefront
    * (all passes that are ready share a launch) in a side stream and join before the extrema scan. */
   inst->fast_oct.clear();
+  inst->strip_oct.clear();
   inst->steps_side.clear();
   if (p.n_oct == 0)
     return true;
@@ -409,6 +413,22 @@ bool build_blur_plan(vksift_Instance inst)
       passes.push_back(bp);
     }
     inst->fast_oct.push_back(passes);
+    /* layers 1..ns and ns+1, ns+2 as two launches of the streaming strip kernel where the octave is large enough and the
+     * radii are the ones it is built for (default configuration); the seed pass of octave 0 stays a launch of its own */
+    std::vector<StripLaunch> strips;
+    const int first = (o == 0) ? 1 : 0; /* index of layer 1 in `passes` */
+    if (inst->use_strip && ns == 3 && (int)passes.size() == first + 5)
+    {
+      StripLaunch a, c;
+      if (strip_plan(passes.data() + first, 3, &a) && strip_plan(passes.data() + first + 3, 2, &c))
+      {
+        a.first_layer = 1;
+        c.first_layer = 4;
+        strips.push_back(a);
+        strips.push_back(c);
+      }
+    }
+    inst->strip_oct.push_back(strips);
   }
   auto wavefront = [&](int o_begin, int o_end, std::vector<BlurStep> &out) {
     if (o_end <= o_begin)
@@ -739,6 +759,8 @@ bool create_resources(vksift_Instance inst)
      * the stream priorities, so one detection alone is ~20 us slower; with several lanes the throughput is what counts
      * and the replay wins (0.315 against 0.321 ms per 1920x1080 image), so it is the default exactly then. */
     const char *g = getenv("VKSIFT_GRAPH");
+    if (const char *sp = getenv("VKSIFT_STRIP"))
+      inst->use_strip = (sp[0] == '1');
     const char *nsp = getenv("VKSIFT_NO_SPLIT");
     inst->no_split = (nsp && nsp[0] == '1');
     inst->use_graph = (g ? g[0] == '1' : n_lanes > 1);
@@ -822,7 +844,7 @@ struct TraceScope
   vksift_Instance inst;
   cudaStream_t st;
   size_t idx = (size_t)-1;
-  TraceScope(vksift_Instance i, cudaStream_t s, const char *fmt, int a, int b) : inst(i), st(s)
+  TraceScope(vksift_Instance i, cudaStream_t s, const char *fmt, int a, int b, int c = 0) : inst(i), st(s)
   {
     if (!inst->trace)
       return;
@@ -834,7 +856,7 @@ struct TraceScope
       inst->trace_marks.push_back(m);
     }
     idx = inst->trace_used++;
-    snprintf(inst->trace_marks[idx].name, sizeof(inst->trace_marks[idx].name), fmt, a, b);
+    snprintf(inst->trace_marks[idx].name, sizeof(inst->trace_marks[idx].name), fmt, a, b, c);
     cudaEventRecord(inst->trace_marks[idx].e0, st);
   }
   ~TraceScope()
@@ -881,7 +903,8 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D0], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   CU_TRY(cudaMemsetAsync(fb.cnt, 0, sizeof(DetectCounters), st));
-  CU_TRY(cudaMemsetAsync(inst->compact_mem, 0, sizeof(uint32_t) * (2 * inst->bm_words + inst->compact_rows), st));
+  /* only the row counters need clearing: the extrema scan and the refinement write every word of their bitmaps */
+  CU_TRY(cudaMemsetAsync(inst->compact_mem + 2 * inst->bm_words, 0, sizeof(uint32_t) * inst->compact_rows, st));
   const int ns = inst->cfg.nb_scales_per_octave;
   const int n_fast = (int)inst->fast_oct.size();
   /* Split schedule: the extrema scan, ordering and orientation pass of an octave (their per-octave sections are
@@ -912,17 +935,33 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
     cudaStream_t so = (o == 0 || serial) ? st : inst->oct_stream[o];
     if (o > 0)
       CU_TRY(cudaStreamWaitEvent(so, inst->ev_seed[o], 0));
+    const bool strips = !inst->strip_oct[o].empty();
     for (BlurPass &bp : inst->fast_oct[o])
     {
+      const bool is_seed = (bp.src_kind != BLUR_SRC_LAYER);
+      if (strips && !is_seed)
+        break; /* layers >= 1 come from the strip launches below */
       if (!(VKS_SKIP(inst) & 8))
       {
-        TraceScope ts(inst, so, "fast o%d r%d", o, bp.radius);
+        TraceScope ts(inst, so, is_seed ? "seed o%d r%d" : "fast o%d r%d", o, bp.radius);
         CU_TRY(launch_blur_pass_fast(bp, so));
       }
       inst->launches++;
       if (bp.dst_next && o + 1 < VKS_MAX_OCT)
         CU_TRY(cudaEventRecord(inst->ev_seed[o + 1], so)); /* written by the pass producing layer ns */
     }
+    if (strips)
+      for (const StripLaunch &L : inst->strip_oct[o])
+      {
+        if (!(VKS_SKIP(inst) & 8))
+        {
+          TraceScope ts(inst, so, "strip o%d g%d+%d", o, L.first_layer, L.n_layers);
+          CU_TRY(launch_strip(L, so));
+        }
+        inst->launches++;
+        if (L.first_layer + L.n_layers - 1 == ns && o + 1 < (int)inst->pyr.n_oct)
+          CU_TRY(cudaEventRecord(inst->ev_seed[o + 1], so)); /* the chain ending in layer ns wrote the next octave's seed */
+      }
     if (o > 0)
     {
       if (split)
@@ -935,7 +974,6 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
       CU_TRY(cudaEventRecord(inst->ev_oct_done[o], so));
     }
   }
-  (void)ns;
   if (!inst->fused_oct.empty())
   {
     cudaStream_t ss = (n_fast == 0 || serial) ? st : inst->side_stream;

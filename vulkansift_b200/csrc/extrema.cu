@@ -212,12 +212,21 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
     const int lx = tid & 255, ly = (tid >> 8) * EX_RPT; /* one column of EX_RPT rows per thread */
     const int x = x0 + lx;
     const int ow = ov.w, oh = ov.h;
-    if (lx < EX_TW && x >= 1 && x < ow - 1)
+    const bool active = (lx < EX_TW && x >= 1 && x < ow - 1);
+    /* rows of this thread that are inside [1, h-2] */
+    const int r_lo = max(0, 1 - (y0 + ly)), r_hi = min(EX_RPT, (oh - 1) - (y0 + ly));
+    const uint32_t row_ok = (active && r_hi > r_lo) ? (((1u << r_hi) - 1u) & ~((1u << r_lo) - 1u)) : 0u;
+    /* the 16-bit piece of the extrema bitmap this lane stores for its warp (lanes 0 and 16): 16 consecutive x, always inside
+     * one tile because the tile width is a multiple of 16; pieces beyond the tile or the row's words belong to nobody */
+    const int lane = tid & 31;
+    const int piece_x = x0 + (lx & ~31) + (lane & 16);
+    const bool piece_store = ((lane & 15) == 0) && ((lx & ~31) + (lane & 16) < EX_TW) && (piece_x < 32 * (int)P.bm_rw[o]);
+    unsigned short *const bm16 = reinterpret_cast<unsigned short *>(P.raw_bm + P.bm_off[o]);
+    const size_t pieces_per_row = 2 * (size_t)P.bm_rw[o];
+    for (int s = 1; s <= ns; s++)
     {
-      /* rows of this thread that are inside [1, h-2] */
-      const int r_lo = max(0, 1 - (y0 + ly)), r_hi = min(EX_RPT, (oh - 1) - (y0 + ly));
-      const uint32_t row_ok = (r_hi > r_lo) ? (((1u << r_hi) - 1u) & ~((1u << r_lo) - 1u)) : 0u;
-      for (int s = 1; s <= ns; s++)
+      uint32_t ext = 0; /* bit r: row r of this thread holds a strict extremum at scale s */
+      if (row_ok)
       {
         const float *col = tile + (s * EX_SH + ly + 1) * EX_SW + (lx + 4);
         /* prefilter all centre values first (independent loads), then visit only the survivors */
@@ -262,14 +271,22 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
               break;
           }
 #undef EX_CMP
-          if (!(gt || lt))
-            continue;
-          /* a strict extremum: mark it.  The sub-pixel refinement (a long serial chain of dependent global
-           * loads and divisions for one lane) runs in its own kernel over the marked bits,
-           * instead of stalling this tile's whole CTA at the next barrier. */
-          const int y = y0 + ly + r;
-          atomicOr(P.raw_bm + P.bm_off[o] + (size_t)((s - 1) * oh + y) * P.bm_rw[o] + (uint32_t)(x >> 5), 1u << (x & 31));
+          if (gt || lt)
+            ext |= 1u << r;
         }
+      }
+      /* Warp-ballot compaction: the 32 lanes of a warp are 32 consecutive columns of the same rows, so one ballot per row IS
+       * the row's bitmap word for these columns.  Every piece of every row is stored (mostly zeros), with plain stores: the
+       * bitmap needs no clearing and no atomics.  The sub-pixel refinement (a long serial chain of dependent global loads and
+       * divisions for one lane) runs in its own kernel over the marked bits instead of stalling this tile's CTA. */
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < EX_RPT; r++)
+      {
+        const uint32_t word = __ballot_sync(0xffffffffu, (ext >> r) & 1u);
+        const int y = y0 + ly + r;
+        if (piece_store && y < oh)
+          bm16[((size_t)(s - 1) * oh + y) * pieces_per_row + (piece_x >> 4)] = (unsigned short)(word >> (lane & 16));
       }
     }
     __syncthreads(); /* everyone is done with buffer `cur` before it is refilled two iterations later */
@@ -277,16 +294,17 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
 }
 
 /* ---- ordered compaction ------------------------------------------------------------------------------------------
- * Bitmap geometry of the octaves [P.ob, P.oe): the launch covers their words as one range, thread = word. */
-__device__ __forceinline__ bool bm_locate(const DetectParams &P, uint32_t g, int *o_out, uint32_t *word_in_oct)
+ * Bitmap geometry of the octaves [P.ob, P.oe): a launch covers their words as one range of 4-word groups, thread = group
+ * (one 16-byte load; the word count of an octave is padded to a multiple of 4 by extrema_layout). */
+__device__ __forceinline__ bool bm_locate(const DetectParams &P, uint32_t g, int *o_out, uint32_t *group_in_oct)
 {
   for (int o = P.ob; o < P.oe; o++)
   {
-    const uint32_t n = (uint32_t)(P.ns * P.oct[o].h) * P.bm_rw[o];
+    const uint32_t n = ((uint32_t)(P.ns * P.oct[o].h) * P.bm_rw[o] + 3u) >> 2;
     if (g < n)
     {
       *o_out = o;
-      *word_in_oct = g;
+      *group_in_oct = g;
       return true;
     }
     g -= n;
@@ -294,41 +312,56 @@ __device__ __forceinline__ bool bm_locate(const DetectParams &P, uint32_t g, int
   return false;
 }
 
-/* ExtractKeypoints.comp:118-224 for the marked extrema: thread = one bitmap word (32 consecutive x of one (s, y) row);
- * almost every word is empty, a thread with set bits refines them one after the other */
+/* ExtractKeypoints.comp:118-224 for the marked extrema: thread = four bitmap words (128 consecutive x of (s, y) rows);
+ * almost every word is empty, a thread with set bits refines them one after the other.  The accepted bitmap is written
+ * for every word (mostly zeros), so it needs no clearing either. */
 #define BM_THREADS 256
-__global__ void __launch_bounds__(BM_THREADS) refine_mark_kernel(const __grid_constant__ DetectParams P, uint32_t total_words,
+__global__ void __launch_bounds__(BM_THREADS) refine_mark_kernel(const __grid_constant__ DetectParams P, uint32_t total_groups,
                                                                  DetectCounters *__restrict__ cnt)
 {
-  for (uint32_t g = blockIdx.x * BM_THREADS + threadIdx.x; g < total_words; g += gridDim.x * BM_THREADS)
+  for (uint32_t g = blockIdx.x * BM_THREADS + threadIdx.x; g < total_groups; g += gridDim.x * BM_THREADS)
   {
     int o;
-    uint32_t wi;
-    if (!bm_locate(P, g, &o, &wi))
+    uint32_t gi;
+    if (!bm_locate(P, g, &o, &gi))
       break;
-    uint32_t bits = P.raw_bm[P.bm_off[o] + wi];
-    if (bits == 0)
-      continue;
     const OctaveView &ov = P.oct[o];
     const uint32_t rw = P.bm_rw[o];
-    const uint32_t row = wi / rw, xw = wi - row * rw; /* row = (s-1)*h + y */
-    const int s = (int)(row / (uint32_t)ov.h) + 1, y = (int)(row % (uint32_t)ov.h);
-    uint32_t acc = 0, n_raw = 0;
-    while (bits)
+    const uint32_t n_words = (uint32_t)(P.ns * ov.h) * rw;
+    const uint4 raw4 = reinterpret_cast<const uint4 *>(P.raw_bm + P.bm_off[o])[gi];
+    const uint32_t raw[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
+    uint32_t acc[4] = {0u, 0u, 0u, 0u};
+    if (raw4.x | raw4.y | raw4.z | raw4.w)
     {
-      const int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      n_raw++;
-      FeatHead hd;
-      if (refine_keypoint(P, ov, o, (int)(xw * 32u) + b, y, s, &hd))
-        acc |= 1u << b;
+#pragma unroll 1
+      for (int q = 0; q < 4; q++)
+      {
+        const uint32_t wi = gi * 4u + (uint32_t)q;
+        if (wi >= n_words || raw[q] == 0)
+          continue;
+        const uint32_t row = wi / rw, xw = wi - row * rw; /* row = (s-1)*h + y */
+        /* columns beyond w-2 never hold an extremum; the pieces of the last word that no tile covers are not written */
+        const int x_max = ov.w - 2 - (int)(xw * 32u); /* highest valid bit of this word */
+        uint32_t bits = x_max >= 31 ? raw[q] : (x_max < 0 ? 0u : (raw[q] & ((2u << x_max) - 1u)));
+        const int s = (int)(row / (uint32_t)ov.h) + 1, y = (int)(row % (uint32_t)ov.h);
+        uint32_t a = 0, n_raw = 0;
+        while (bits)
+        {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          n_raw++;
+          FeatHead hd;
+          if (refine_keypoint(P, ov, o, (int)(xw * 32u) + b, y, s, &hd))
+            a |= 1u << b;
+        }
+        acc[q] = a;
+        if (n_raw)
+          atomicAdd(&cnt->n_raw[o], n_raw);
+        if (a)
+          atomicAdd(P.row_cnt + P.row_off[o] + row, (uint32_t)__popc(a));
+      }
     }
-    atomicAdd(&cnt->n_raw[o], n_raw);
-    if (acc)
-    {
-      P.acc_bm[P.bm_off[o] + wi] = acc;
-      atomicAdd(P.row_cnt + P.row_off[o] + row, (uint32_t)__popc(acc));
-    }
+    reinterpret_cast<uint4 *>(P.acc_bm + P.bm_off[o])[gi] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
   }
 }
 
@@ -389,37 +422,47 @@ __global__ void __launch_bounds__(SCAN_THREADS) row_scan_kernel(const __grid_con
   }
 }
 
-/* thread = one word of the accepted bitmap; rank of a keypoint = first rank of its row + accepted bits in front of it */
-__global__ void __launch_bounds__(BM_THREADS) rank_emit_kernel(const __grid_constant__ DetectParams P, uint32_t total_words,
+/* thread = four words of the accepted bitmap; rank of a keypoint = first rank of its row + accepted bits in front of it */
+__global__ void __launch_bounds__(BM_THREADS) rank_emit_kernel(const __grid_constant__ DetectParams P, uint32_t total_groups,
                                                                FeatHead *__restrict__ prim)
 {
-  for (uint32_t g = blockIdx.x * BM_THREADS + threadIdx.x; g < total_words; g += gridDim.x * BM_THREADS)
+  for (uint32_t g = blockIdx.x * BM_THREADS + threadIdx.x; g < total_groups; g += gridDim.x * BM_THREADS)
   {
     int o;
-    uint32_t wi;
-    if (!bm_locate(P, g, &o, &wi))
+    uint32_t gi;
+    if (!bm_locate(P, g, &o, &gi))
       break;
     const uint32_t *__restrict__ bm = P.acc_bm + P.bm_off[o];
-    uint32_t bits = bm[wi];
-    if (bits == 0)
+    const uint4 a4 = reinterpret_cast<const uint4 *>(bm)[gi];
+    if ((a4.x | a4.y | a4.z | a4.w) == 0)
       continue;
+    const uint32_t av[4] = {a4.x, a4.y, a4.z, a4.w};
     const OctaveView &ov = P.oct[o];
     const uint32_t rw = P.bm_rw[o];
-    const uint32_t row = wi / rw, xw = wi - row * rw;
-    uint32_t rank = P.row_cnt[P.row_off[o] + row];
-    if (rank >= P.cap[o])
-      continue; /* the whole row lies beyond the section capacity */
-    for (uint32_t k = 0; k < xw; k++)
-      rank += (uint32_t)__popc(bm[wi - xw + k]);
-    const int s = (int)(row / (uint32_t)ov.h) + 1, y = (int)(row % (uint32_t)ov.h);
-    while (bits && rank < P.cap[o])
+    const uint32_t n_words = (uint32_t)(P.ns * ov.h) * rw;
+#pragma unroll 1
+    for (int q = 0; q < 4; q++)
     {
-      const int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      FeatHead hd;
-      refine_keypoint(P, ov, o, (int)(xw * 32u) + b, y, s, &hd); /* accepted before: same inputs, same result */
-      prim[P.sec_off[o] + rank] = hd;
-      rank++;
+      const uint32_t wi = gi * 4u + (uint32_t)q;
+      uint32_t bits = av[q];
+      if (wi >= n_words || bits == 0)
+        continue;
+      const uint32_t row = wi / rw, xw = wi - row * rw;
+      uint32_t rank = P.row_cnt[P.row_off[o] + row];
+      if (rank >= P.cap[o])
+        continue; /* the whole row lies beyond the section capacity */
+      for (uint32_t k = 0; k < xw; k++)
+        rank += (uint32_t)__popc(bm[wi - xw + k]);
+      const int s = (int)(row / (uint32_t)ov.h) + 1, y = (int)(row % (uint32_t)ov.h);
+      while (bits && rank < P.cap[o])
+      {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        FeatHead hd;
+        refine_keypoint(P, ov, o, (int)(xw * 32u) + b, y, s, &hd); /* accepted before: same inputs, same result */
+        prim[P.sec_off[o] + rank] = hd;
+        rank++;
+      }
     }
   }
 }
@@ -464,7 +507,7 @@ void extrema_layout(DetectParams *P, size_t *bm_words, size_t *rows)
     P->bm_rw[o] = (uint32_t)((P->oct[o].w + 31) / 32);
     P->row_off[o] = (uint32_t)nrows;
     const size_t r = (size_t)P->ns * (size_t)P->oct[o].h;
-    words += r * P->bm_rw[o];
+    words += (r * P->bm_rw[o] + 3) & ~(size_t)3; /* 16-byte groups: the scans load four words at a time */
     nrows += r;
   }
   *bm_words = words;
@@ -476,14 +519,14 @@ cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectC
   if (!pl || !pl->valid || pl->n_tiles == 0 || P.oe <= P.ob)
     return cudaSuccess;
   int t_begin = 0, t_end = 0;
-  uint32_t total_words = 0;
+  uint32_t total_groups = 0;
   for (int o = 0; o < P.oe; o++)
   {
     const int n = ((P.oct[o].w + EX_TW - 1) / EX_TW) * ((P.oct[o].h + EX_TH - 1) / EX_TH);
     if (o < P.ob)
       t_begin += n;
     else
-      total_words += (uint32_t)(P.ns * P.oct[o].h) * P.bm_rw[o];
+      total_groups += ((uint32_t)(P.ns * P.oct[o].h) * P.bm_rw[o] + 3u) >> 2;
     t_end += n;
   }
   const size_t smem = 2 * sizeof(float) * (size_t)((((P.ns + 2) * EX_SH * EX_SW) + 31) & ~31);
@@ -519,13 +562,13 @@ cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectC
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
-  /* one thread per bitmap word, at most 8 CTAs per SM in flight: a thread then visits a handful of words */
-  uint32_t bgrid = (total_words + BM_THREADS - 1) / BM_THREADS;
+  /* one thread per group of four bitmap words, at most 8 CTAs per SM in flight */
+  uint32_t bgrid = (total_groups + BM_THREADS - 1) / BM_THREADS;
   if (bgrid > (uint32_t)sms * 8u)
     bgrid = (uint32_t)sms * 8u;
-  refine_mark_kernel<<<bgrid, BM_THREADS, 0, st>>>(P, total_words, cnt);
+  refine_mark_kernel<<<bgrid, BM_THREADS, 0, st>>>(P, total_groups, cnt);
   row_scan_kernel<<<P.oe - P.ob, SCAN_THREADS, 0, st>>>(P, cnt);
-  rank_emit_kernel<<<bgrid, BM_THREADS, 0, st>>>(P, total_words, prim);
+  rank_emit_kernel<<<bgrid, BM_THREADS, 0, st>>>(P, total_groups, prim);
   *launch_count += 4;
   return cudaGetLastError();
 }

@@ -147,6 +147,16 @@ struct FusedLaunch
   float2 taps2[FZ_MAXL][14];
 };
 
+/* a chain of consecutive layers of one large octave produced by one launch of the streaming strip kernel (pyramid_strip.cu) */
+struct StripLaunch
+{
+  int kind;        /* which instantiation: 0 = three layers with radii (4, 6, 8), 1 = two layers with radii (10, 12) */
+  int grid;        /* strips x segments */
+  int first_layer; /* layer index of the chain's first layer inside the octave (trace label) */
+  int n_layers;
+  alignas(16) unsigned char params[512]; /* StripParams */
+};
+
 /* ---- host-side plan ------------------------------------------------------ */
 struct ScalePlan
 {
@@ -179,6 +189,10 @@ cudaError_t launch_blur_step(const BlurStep &step, cudaStream_t st);
 /* groups consecutive layer passes of one octave into fused launches; false when a pass cannot be fused */
 bool fused_plan_octave(const BlurPass *passes, int n_pass, std::vector<FusedLaunch> *out);
 cudaError_t launch_fused(const FusedLaunch &F, cudaStream_t st);
+/* plan a chain of passes (consecutive layers of one octave, float source) for the strip kernel; false when the chain or the
+ * octave size is not one the kernel is built for (the caller keeps the per-layer launches) */
+bool strip_plan(const BlurPass *passes, int n, StripLaunch *out);
+cudaError_t launch_strip(const StripLaunch &L, cudaStream_t st);
 struct ExtremaPlan; /* TMA tensor maps over the DoG layers of the current pyramid */
 cudaError_t extrema_plan_build(const DetectParams &P, ExtremaPlan **plan_io);
 void extrema_plan_destroy(ExtremaPlan *pl);
