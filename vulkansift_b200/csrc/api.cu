@@ -109,7 +109,7 @@ struct vksift_Instance_T
   std::vector<std::vector<BlurPass>> fast_oct; /* octaves [0,k) on the fast kernel: one stream per octave, one launch per layer */
   std::vector<std::vector<StripLaunch>> strip_oct; /* per fast octave: the multi-layer strip launches that replace its per-layer launches
                                                       of layers >= 1 (empty: the octave keeps the per-layer launches) */
-  bool use_strip = false; /* VKSIFT_STRIP=1: multi-layer strip kernel for the large octaves (first version: bit-exact, slower than the per-layer launches) */
+  bool use_strip = false; /* VKSIFT_STRIP=1: multi-layer strip kernel for the large octaves (bit-exact; measured slower than the per-layer launches) */
   std::vector<BlurStep> steps_side;            /* small octaves [k,n) that cannot be fused: compact kernel, wavefront steps on the side stream */
   struct FusedOct
   {
