@@ -378,12 +378,16 @@ def test_small_images_eight_lanes(api, oracle_mod):
                 assert_features_equal(inst.download_features(b), exp[(b + 3 * rep) % 8], "round %d buffer %d" % (rep, b))
 
 
+@pytest.mark.parametrize("queue", [None, "16"], ids=["default_queue", "overflowing_queue"])
 @pytest.mark.parametrize("max_feats", [50, 300])
-def test_many_raw_extrema_small_buffer_keeps_lowest_accepted_keys(api, oracle_mod, max_feats):
+def test_many_raw_extrema_small_buffer_keeps_lowest_accepted_keys(api, oracle_mod, max_feats, queue, monkeypatch):
     """A blocky noise image yields tens of thousands of strict extrema and ~5.6 k accepted keypoints in octave 0 while the buffer holds 50
     or 300: the kept set must be the oracle's (lowest (s, y, x) keys among the ACCEPTED keypoints of each octave, then the
     section clamp), whatever order the GPU found them in.  (Round 1 queued raw extrema in a max_nb_sift_per_buffer-sized
-    buffer and dropped the overflow in arrival order.)"""
+    buffer and dropped the overflow in arrival order.)  With VKSIFT_RAW_QUEUE=16 every large octave overflows its extrema
+    queue (256 entries minimum per octave) and takes the queue-less slow path; the result must not change."""
+    if queue:
+        monkeypatch.setenv("VKSIFT_RAW_QUEUE", queue)
     rng = np.random.default_rng(17)
     img = np.kron(rng.integers(0, 256, (100, 133), dtype=np.uint8), np.ones((3, 3), np.uint8))  # 300x399 field of 3x3 blocks
     kw = {"max_nb_sift_per_buffer": max_feats}
@@ -395,6 +399,17 @@ def test_many_raw_extrema_small_buffer_keeps_lowest_accepted_keys(api, oracle_mo
         for rep in range(3):
             inst.detect(img, rep % 2)
             assert_features_equal(inst.download_features(rep % 2), exp, "max %d rep %d" % (max_feats, rep))
+
+
+def test_extrema_queue_overflow_path_equals_default_on_c1(api, oracle_mod, c1_image, monkeypatch):
+    """The slow path that needs no extrema queue (taken when an octave yields more strict extrema than its queue share) on an
+    ordinary image: same features, same order, same bytes as the oracle."""
+    monkeypatch.setenv("VKSIFT_RAW_QUEUE", "16")
+    with api.Instance() as inst:
+        exp = oracle_mod.Oracle().detect(c1_image)
+        for rep in range(2):
+            inst.detect(c1_image, rep)
+            assert_features_equal(inst.download_features(rep), exp, "rep %d" % rep)
 
 
 def test_too_many_scales_is_rejected_at_creation(api):

@@ -165,8 +165,12 @@ struct vksift_Instance_T
   std::vector<FeatureBuffer> own_buffers; /* primary only */
   FeatureBuffer *buffers = nullptr;       /* own_buffers.data() of the primary */
   uint32_t n_buffers = 0;
-  uint32_t *compact_mem = nullptr; /* [raw extrema bitmap | accepted bitmap | row counts] of the ordered compaction (extrema.cu) */
+  uint32_t *compact_mem = nullptr; /* [accepted bitmap | row counts] of the ordered compaction (extrema.cu), cleared per detection */
   size_t compact_alloc_words = 0, bm_words = 0, compact_rows = 0;
+  unsigned long long *raw_q = nullptr; /* extrema queue, all octaves */
+  FeatHead *q_heads = nullptr;
+  size_t q_alloc = 0;
+  uint32_t q_total = 0; /* queue entries shared by the octaves (4 x max_nb_sift_per_buffer, at least 16 k; VKSIFT_RAW_QUEUE overrides) */
   FeatHead *prim = nullptr;
   float *ori = nullptr;
   uint32_t *n_ori = nullptr;
@@ -511,8 +515,21 @@ bool set_resolution(vksift_Instance inst, uint32_t w, uint32_t h)
     FeatureBuffer dummy;
     fill_detect_params(inst, dummy, &P);
     CU_TRY(extrema_plan_build(P, &inst->extrema_plan));
-    size_t words = 0, rows = 0;
-    extrema_layout(&P, &words, &rows);
+    size_t words = 0, rows = 0, qn = 0;
+    extrema_layout(&P, &words, &rows, &qn, inst->q_total);
+    if (qn > inst->q_alloc)
+    {
+      if (inst->raw_q)
+        CU_TRY(cudaFree(inst->raw_q));
+      if (inst->q_heads)
+        CU_TRY(cudaFree(inst->q_heads));
+      inst->raw_q = nullptr;
+      inst->q_heads = nullptr;
+      inst->q_alloc = 0;
+      CU_TRY(cudaMalloc(&inst->raw_q, sizeof(unsigned long long) * qn));
+      CU_TRY(cudaMalloc(&inst->q_heads, sizeof(FeatHead) * qn));
+      inst->q_alloc = qn;
+    }
     if (words >= (1ull << 31))
     {
       LOGE(TAG, "scale space too large for the keypoint bitmaps (%zu words)", words);
@@ -520,14 +537,14 @@ bool set_resolution(vksift_Instance inst, uint32_t w, uint32_t h)
     }
     inst->bm_words = words;
     inst->compact_rows = rows;
-    if (2 * words + rows > inst->compact_alloc_words)
+    if (words + rows > inst->compact_alloc_words)
     {
       if (inst->compact_mem)
         CU_TRY(cudaFree(inst->compact_mem));
       inst->compact_mem = nullptr;
       inst->compact_alloc_words = 0;
-      CU_TRY(cudaMalloc(&inst->compact_mem, sizeof(uint32_t) * (2 * words + rows)));
-      inst->compact_alloc_words = 2 * words + rows;
+      CU_TRY(cudaMalloc(&inst->compact_mem, sizeof(uint32_t) * (words + rows)));
+      inst->compact_alloc_words = words + rows;
     }
   }
   return true;
@@ -573,11 +590,12 @@ void fill_detect_params(vksift_Instance inst, const FeatureBuffer &fb, DetectPar
   P->ori_stride = inst->ori_stride;
   P->vlfeat = (c.descriptor_format == VKSIFT_DESCRIPTOR_FORMAT_VLFEAT) ? 1 : 0;
   P->max_feats = c.max_nb_sift_per_buffer;
-  size_t words = 0, rows = 0;
-  extrema_layout(P, &words, &rows);
-  P->raw_bm = inst->compact_mem;
-  P->acc_bm = inst->compact_mem + inst->bm_words;
-  P->row_cnt = inst->compact_mem + 2 * inst->bm_words;
+  size_t words = 0, rows = 0, qn = 0;
+  extrema_layout(P, &words, &rows, &qn, inst->q_total);
+  P->acc_bm = inst->compact_mem;
+  P->row_cnt = inst->compact_mem + inst->bm_words;
+  P->raw_q = inst->raw_q;
+  P->q_heads = inst->q_heads;
 }
 
 void wait_lane(vksift_Instance lane)
@@ -659,6 +677,8 @@ void destroy_instance(vksift_Instance inst)
     cudaFreeHost(inst->h_src_slot);
   cudaFree(inst->d_src_slot);
   cudaFree(inst->compact_mem);
+  cudaFree(inst->raw_q);
+  cudaFree(inst->q_heads);
   cudaFree(inst->prim);
   cudaFree(inst->ori);
   cudaFree(inst->n_ori);
@@ -769,6 +789,18 @@ bool create_resources(vksift_Instance inst)
   }
 
   const size_t maxf = c.max_nb_sift_per_buffer;
+  {
+    /* extrema queue: raw extrema outnumber accepted keypoints 2-3x; an overflow is handled (slow path), never dropped */
+    unsigned long long q = 4ull * c.max_nb_sift_per_buffer;
+    q = q < 16384ull ? 16384ull : (q > (1ull << 22) ? (1ull << 22) : q);
+    if (const char *e = getenv("VKSIFT_RAW_QUEUE"))
+    {
+      const long v = strtol(e, nullptr, 10);
+      if (v >= 1)
+        q = (unsigned long long)v;
+    }
+    inst->q_total = (uint32_t)q;
+  }
   inst->ori_stride = (c.max_nb_orientation_per_keypoint == 0 || c.max_nb_orientation_per_keypoint > VKS_MAX_ORI) ? VKS_MAX_ORI
                                                                                                                    : c.max_nb_orientation_per_keypoint;
   CU_TRY(cudaMalloc(&inst->prim, sizeof(FeatHead) * (maxf + 1)));
@@ -903,8 +935,7 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D0], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   CU_TRY(cudaMemsetAsync(fb.cnt, 0, sizeof(DetectCounters), st));
-  /* only the row counters need clearing: the extrema scan and the refinement write every word of their bitmaps */
-  CU_TRY(cudaMemsetAsync(inst->compact_mem + 2 * inst->bm_words, 0, sizeof(uint32_t) * inst->compact_rows, st));
+  CU_TRY(cudaMemsetAsync(inst->compact_mem, 0, sizeof(uint32_t) * (inst->bm_words + inst->compact_rows), st)); /* accepted bitmap + row counters */
   const int ns = inst->cfg.nb_scales_per_octave;
   const int n_fast = (int)inst->fast_oct.size();
   /* Split schedule: the extrema scan, ordering and orientation pass of an octave (their per-octave sections are

@@ -7,16 +7,20 @@
  * one of the detecting thread ids, key = (s, y, x) -- the canonical order of
  * SURVEY.md B-D4, which the oracle produces by construction -- and nothing on the
  * way has a capacity that depends on the image:
- *   extrema_kernel      every strict extremum sets ONE BIT of a (s, y, x) bitmap (ns*w*h bits per octave)
- *   refine_mark_kernel  walks that bitmap, refines each extremum (:118-224); an accepted keypoint sets its bit
- *                       in a second bitmap and counts into its (s, y) row
- *   row_scan_kernel     exclusive scan of the row counts -> first rank of every row, n_cand, n_prim
- *   rank_emit_kernel    walks the accepted bitmap: rank = row start + accepted bits in front of it in the row; the
- *                       keypoints whose rank is below the section capacity are refined again (deterministic, a few
- *                       thousand of them) and written to slot `rank`
- * Section overflow therefore keeps exactly the lowest keys among the ACCEPTED keypoints, like the oracle, however many
- * raw extrema the image produces (the first version queued raw extrema in a buffer of max_nb_sift_per_buffer entries
- * and dropped the overflow in atomic-arrival order).
+ *   extrema_kernel   queues every strict extremum (key (s, y, x)) in a per-octave queue
+ *   refine_kernel    one thread per queued extremum (small CTAs: a refinement is a long latency chain for one lane, so the
+ *                    kernel must not hold many thread slots): ExtractKeypoints.comp:118-224; an accepted keypoint keeps its
+ *                    refined record beside the queue entry, sets its bit in a (s, y, x) bitmap (ns*w*h bits per octave)
+ *                    and counts into its (s, y) row
+ *   row_scan_kernel  exclusive scan of the row counts -> first rank of every row, n_cand, n_prim
+ *   rank_kernel      rank of an accepted keypoint = row start + accepted bits in front of it in its row; the keypoints whose
+ *                    rank is below the section capacity are written to slot `rank`
+ * The queue is sized generously (4 x max_nb_sift_per_buffer shared by the octaves, at least 16 k) but an image may produce
+ * more strict extrema than any fixed queue holds.  When an octave's queue overflows, refine_kernel and rank_kernel take a
+ * slow path for that octave that needs no queue: every (s, y, x) is tested again straight from global memory, accepted
+ * keypoints only set their bit, and the ranking pass walks the bitmap and refines the kept ones once more (deterministic,
+ * same inputs).  Either way section overflow keeps exactly the lowest keys among the ACCEPTED keypoints, like the oracle,
+ * however many raw extrema the image produces (the first version dropped queue overflow in atomic-arrival order).
  *
  * All float expressions keep the association order of the shader; the library
  * is compiled with -fmad=false so nothing is contracted.
@@ -212,21 +216,12 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
     const int lx = tid & 255, ly = (tid >> 8) * EX_RPT; /* one column of EX_RPT rows per thread */
     const int x = x0 + lx;
     const int ow = ov.w, oh = ov.h;
-    const bool active = (lx < EX_TW && x >= 1 && x < ow - 1);
-    /* rows of this thread that are inside [1, h-2] */
-    const int r_lo = max(0, 1 - (y0 + ly)), r_hi = min(EX_RPT, (oh - 1) - (y0 + ly));
-    const uint32_t row_ok = (active && r_hi > r_lo) ? (((1u << r_hi) - 1u) & ~((1u << r_lo) - 1u)) : 0u;
-    /* the 16-bit piece of the extrema bitmap this lane stores for its warp (lanes 0 and 16): 16 consecutive x, always inside
-     * one tile because the tile width is a multiple of 16; pieces beyond the tile or the row's words belong to nobody */
-    const int lane = tid & 31;
-    const int piece_x = x0 + (lx & ~31) + (lane & 16);
-    const bool piece_store = ((lane & 15) == 0) && ((lx & ~31) + (lane & 16) < EX_TW) && (piece_x < 32 * (int)P.bm_rw[o]);
-    unsigned short *const bm16 = reinterpret_cast<unsigned short *>(P.raw_bm + P.bm_off[o]);
-    const size_t pieces_per_row = 2 * (size_t)P.bm_rw[o];
-    for (int s = 1; s <= ns; s++)
+    if (lx < EX_TW && x >= 1 && x < ow - 1)
     {
-      uint32_t ext = 0; /* bit r: row r of this thread holds a strict extremum at scale s */
-      if (row_ok)
+      /* rows of this thread that are inside [1, h-2] */
+      const int r_lo = max(0, 1 - (y0 + ly)), r_hi = min(EX_RPT, (oh - 1) - (y0 + ly));
+      const uint32_t row_ok = (r_hi > r_lo) ? (((1u << r_hi) - 1u) & ~((1u << r_lo) - 1u)) : 0u;
+      for (int s = 1; s <= ns; s++)
       {
         const float *col = tile + (s * EX_SH + ly + 1) * EX_SW + (lx + 4);
         /* prefilter all centre values first (independent loads), then visit only the survivors */
@@ -271,97 +266,89 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
               break;
           }
 #undef EX_CMP
-          if (gt || lt)
-            ext |= 1u << r;
+          if (!(gt || lt))
+            continue;
+          /* a strict extremum: queue it.  The sub-pixel refinement (a long serial chain of dependent global loads and
+           * divisions for one lane) runs in its own kernel with one thread per queued extremum instead of stalling this
+           * tile's whole CTA at the next barrier.  The counter keeps counting past the queue capacity: that is how the
+           * later kernels see an overflow (and switch to the path that needs no queue). */
+          const int y = y0 + ly + r;
+          const uint32_t slot = atomicAdd(&cnt->n_raw[o], 1u);
+          if (slot < P.q_cap[o])
+            P.raw_q[P.q_off[o] + slot] = ((unsigned long long)s << 40) | ((unsigned long long)y << 20) | (unsigned long long)x;
         }
-      }
-      /* Warp-ballot compaction: the 32 lanes of a warp are 32 consecutive columns of the same rows, so one ballot per row IS
-       * the row's bitmap word for these columns.  Every piece of every row is stored (mostly zeros), with plain stores: the
-       * bitmap needs no clearing and no atomics.  The sub-pixel refinement (a long serial chain of dependent global loads and
-       * divisions for one lane) runs in its own kernel over the marked bits instead of stalling this tile's CTA. */
-      __syncwarp();
-#pragma unroll
-      for (int r = 0; r < EX_RPT; r++)
-      {
-        const uint32_t word = __ballot_sync(0xffffffffu, (ext >> r) & 1u);
-        const int y = y0 + ly + r;
-        if (piece_store && y < oh)
-          bm16[((size_t)(s - 1) * oh + y) * pieces_per_row + (piece_x >> 4)] = (unsigned short)(word >> (lane & 16));
       }
     }
     __syncthreads(); /* everyone is done with buffer `cur` before it is refilled two iterations later */
   }
 }
 
-/* ---- ordered compaction ------------------------------------------------------------------------------------------
- * Bitmap geometry of the octaves [P.ob, P.oe): a launch covers their words as one range of 4-word groups, thread = group
- * (one 16-byte load; the word count of an octave is padded to a multiple of 4 by extrema_layout). */
-__device__ __forceinline__ bool bm_locate(const DetectParams &P, uint32_t g, int *o_out, uint32_t *group_in_oct)
+/* ---- ordered compaction ------------------------------------------------------------------------------------------ */
+#define RF_THREADS 64 /* small CTAs: most of a refinement is waiting for one lane's dependent loads */
+#define RF_CTAS 96    /* per octave */
+#define RQ_ACCEPTED (1ull << 63)
+
+/* strict extremum test straight from global memory: the slow path's twin of the shared-memory test in extrema_kernel */
+__device__ bool is_extremum_global(const DetectParams &P, const OctaveView &ov, int x, int y, int s)
 {
-  for (int o = P.ob; o < P.oe; o++)
-  {
-    const uint32_t n = ((uint32_t)(P.ns * P.oct[o].h) * P.bm_rw[o] + 3u) >> 2;
-    if (g < n)
-    {
-      *o_out = o;
-      *group_in_oct = g;
-      return true;
-    }
-    g -= n;
-  }
-  return false;
+  const float c = dog_at(ov, P.ns, s, x, y);
+  if (!(fabsf(c) > P.prefilter))
+    return false;
+  bool gt = true, lt = true;
+  for (int ds = -1; ds <= 1; ds++)
+    for (int dy = -1; dy <= 1; dy++)
+      for (int dx = -1; dx <= 1; dx++)
+      {
+        if (ds == 0 && dy == 0 && dx == 0)
+          continue;
+        const float n = dog_at(ov, P.ns, s + ds, x + dx, y + dy);
+        gt = gt && (c > n);
+        lt = lt && (c < n);
+      }
+  return gt || lt;
 }
 
-/* ExtractKeypoints.comp:118-224 for the marked extrema: thread = four bitmap words (128 consecutive x of (s, y) rows);
- * almost every word is empty, a thread with set bits refines them one after the other.  The accepted bitmap is written
- * for every word (mostly zeros), so it needs no clearing either. */
-#define BM_THREADS 256
-__global__ void __launch_bounds__(BM_THREADS) refine_mark_kernel(const __grid_constant__ DetectParams P, uint32_t total_groups,
-                                                                 DetectCounters *__restrict__ cnt)
+__device__ __forceinline__ void mark_accepted(const DetectParams &P, int o, int x, int y, int s)
 {
-  for (uint32_t g = blockIdx.x * BM_THREADS + threadIdx.x; g < total_groups; g += gridDim.x * BM_THREADS)
+  const uint32_t row = (uint32_t)((s - 1) * P.oct[o].h + y);
+  atomicOr(P.acc_bm + P.bm_off[o] + (size_t)row * P.bm_rw[o] + (uint32_t)(x >> 5), 1u << (x & 31));
+  atomicAdd(P.row_cnt + P.row_off[o] + row, 1u);
+}
+
+/* ExtractKeypoints.comp:118-224: grid (RF_CTAS, octaves of the launch) */
+__global__ void __launch_bounds__(RF_THREADS) refine_kernel(const __grid_constant__ DetectParams P, const DetectCounters *__restrict__ cnt)
+{
+  const int o = P.ob + (int)blockIdx.y;
+  const OctaveView &ov = P.oct[o];
+  const uint32_t n = cnt->n_raw[o];
+  const uint32_t tid = blockIdx.x * RF_THREADS + threadIdx.x, stride = gridDim.x * RF_THREADS;
+  if (n <= P.q_cap[o])
   {
-    int o;
-    uint32_t gi;
-    if (!bm_locate(P, g, &o, &gi))
-      break;
-    const OctaveView &ov = P.oct[o];
-    const uint32_t rw = P.bm_rw[o];
-    const uint32_t n_words = (uint32_t)(P.ns * ov.h) * rw;
-    const uint4 raw4 = reinterpret_cast<const uint4 *>(P.raw_bm + P.bm_off[o])[gi];
-    const uint32_t raw[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
-    uint32_t acc[4] = {0u, 0u, 0u, 0u};
-    if (raw4.x | raw4.y | raw4.z | raw4.w)
+    unsigned long long *__restrict__ q = P.raw_q + P.q_off[o];
+    FeatHead *__restrict__ qh = P.q_heads + P.q_off[o];
+    for (uint32_t i = tid; i < n; i += stride)
     {
-#pragma unroll 1
-      for (int q = 0; q < 4; q++)
-      {
-        const uint32_t wi = gi * 4u + (uint32_t)q;
-        if (wi >= n_words || raw[q] == 0)
-          continue;
-        const uint32_t row = wi / rw, xw = wi - row * rw; /* row = (s-1)*h + y */
-        /* columns beyond w-2 never hold an extremum; the pieces of the last word that no tile covers are not written */
-        const int x_max = ov.w - 2 - (int)(xw * 32u); /* highest valid bit of this word */
-        uint32_t bits = x_max >= 31 ? raw[q] : (x_max < 0 ? 0u : (raw[q] & ((2u << x_max) - 1u)));
-        const int s = (int)(row / (uint32_t)ov.h) + 1, y = (int)(row % (uint32_t)ov.h);
-        uint32_t a = 0, n_raw = 0;
-        while (bits)
-        {
-          const int b = __ffs(bits) - 1;
-          bits &= bits - 1;
-          n_raw++;
-          FeatHead hd;
-          if (refine_keypoint(P, ov, o, (int)(xw * 32u) + b, y, s, &hd))
-            a |= 1u << b;
-        }
-        acc[q] = a;
-        if (n_raw)
-          atomicAdd(&cnt->n_raw[o], n_raw);
-        if (a)
-          atomicAdd(P.row_cnt + P.row_off[o] + row, (uint32_t)__popc(a));
-      }
+      const unsigned long long key = q[i];
+      const int s = (int)(key >> 40), y = (int)((key >> 20) & 0xfffffu), x = (int)(key & 0xfffffu);
+      FeatHead hd;
+      if (!refine_keypoint(P, ov, o, x, y, s, &hd))
+        continue;
+      qh[i] = hd;
+      q[i] = key | RQ_ACCEPTED;
+      mark_accepted(P, o, x, y, s);
     }
-    reinterpret_cast<uint4 *>(P.acc_bm + P.bm_off[o])[gi] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+    return;
+  }
+  /* queue overflow: every inner (s, y, x) again, from global memory */
+  const unsigned long long total = (unsigned long long)P.ns * (unsigned long long)(ov.h - 2) * (unsigned long long)(ov.w - 2);
+  for (unsigned long long i = tid; i < total; i += stride)
+  {
+    const int x = 1 + (int)(i % (unsigned long long)(ov.w - 2));
+    const unsigned long long t = i / (unsigned long long)(ov.w - 2);
+    const int y = 1 + (int)(t % (unsigned long long)(ov.h - 2)), s = 1 + (int)(t / (unsigned long long)(ov.h - 2));
+    FeatHead hd;
+    if (is_extremum_global(P, ov, x, y, s) && refine_keypoint(P, ov, o, x, y, s, &hd))
+      mark_accepted(P, o, x, y, s);
   }
 }
 
@@ -422,47 +409,60 @@ __global__ void __launch_bounds__(SCAN_THREADS) row_scan_kernel(const __grid_con
   }
 }
 
-/* thread = four words of the accepted bitmap; rank of a keypoint = first rank of its row + accepted bits in front of it */
-__global__ void __launch_bounds__(BM_THREADS) rank_emit_kernel(const __grid_constant__ DetectParams P, uint32_t total_groups,
-                                                               FeatHead *__restrict__ prim)
+/* rank of an accepted keypoint = first rank of its (s, y) row + accepted bits in front of it in that row */
+__device__ __forceinline__ uint32_t rank_of(const DetectParams &P, int o, uint32_t row, int x)
 {
-  for (uint32_t g = blockIdx.x * BM_THREADS + threadIdx.x; g < total_groups; g += gridDim.x * BM_THREADS)
+  const uint32_t *__restrict__ bm = P.acc_bm + P.bm_off[o] + (size_t)row * P.bm_rw[o];
+  uint32_t rank = P.row_cnt[P.row_off[o] + row];
+  const uint32_t xw = (uint32_t)x >> 5;
+  for (uint32_t k = 0; k < xw; k++)
+    rank += (uint32_t)__popc(bm[k]);
+  return rank + (uint32_t)__popc(bm[xw] & ((1u << (x & 31)) - 1u));
+}
+
+__global__ void __launch_bounds__(RF_THREADS) rank_kernel(const __grid_constant__ DetectParams P, const DetectCounters *__restrict__ cnt,
+                                                          FeatHead *__restrict__ prim)
+{
+  const int o = P.ob + (int)blockIdx.y;
+  const OctaveView &ov = P.oct[o];
+  const uint32_t n = cnt->n_raw[o];
+  const uint32_t tid = blockIdx.x * RF_THREADS + threadIdx.x, stride = gridDim.x * RF_THREADS;
+  if (n <= P.q_cap[o])
   {
-    int o;
-    uint32_t gi;
-    if (!bm_locate(P, g, &o, &gi))
-      break;
-    const uint32_t *__restrict__ bm = P.acc_bm + P.bm_off[o];
-    const uint4 a4 = reinterpret_cast<const uint4 *>(bm)[gi];
-    if ((a4.x | a4.y | a4.z | a4.w) == 0)
-      continue;
-    const uint32_t av[4] = {a4.x, a4.y, a4.z, a4.w};
-    const OctaveView &ov = P.oct[o];
-    const uint32_t rw = P.bm_rw[o];
-    const uint32_t n_words = (uint32_t)(P.ns * ov.h) * rw;
-#pragma unroll 1
-    for (int q = 0; q < 4; q++)
+    const unsigned long long *__restrict__ q = P.raw_q + P.q_off[o];
+    const FeatHead *__restrict__ qh = P.q_heads + P.q_off[o];
+    for (uint32_t i = tid; i < n; i += stride)
     {
-      const uint32_t wi = gi * 4u + (uint32_t)q;
-      uint32_t bits = av[q];
-      if (wi >= n_words || bits == 0)
+      const unsigned long long key = q[i];
+      if (!(key & RQ_ACCEPTED))
         continue;
-      const uint32_t row = wi / rw, xw = wi - row * rw;
-      uint32_t rank = P.row_cnt[P.row_off[o] + row];
-      if (rank >= P.cap[o])
-        continue; /* the whole row lies beyond the section capacity */
-      for (uint32_t k = 0; k < xw; k++)
-        rank += (uint32_t)__popc(bm[wi - xw + k]);
-      const int s = (int)(row / (uint32_t)ov.h) + 1, y = (int)(row % (uint32_t)ov.h);
-      while (bits && rank < P.cap[o])
-      {
-        const int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        FeatHead hd;
-        refine_keypoint(P, ov, o, (int)(xw * 32u) + b, y, s, &hd); /* accepted before: same inputs, same result */
-        prim[P.sec_off[o] + rank] = hd;
-        rank++;
-      }
+      const int s = (int)((key >> 40) & 0xfffffu), y = (int)((key >> 20) & 0xfffffu), x = (int)(key & 0xfffffu);
+      const uint32_t rank = rank_of(P, o, (uint32_t)((s - 1) * ov.h + y), x);
+      if (rank < P.cap[o])
+        prim[P.sec_off[o] + rank] = qh[i];
+    }
+    return;
+  }
+  /* queue overflow: walk the accepted bitmap, refine the kept keypoints once more (same inputs, same result) */
+  const uint32_t rw = P.bm_rw[o];
+  const uint32_t n_words = (uint32_t)(P.ns * ov.h) * rw;
+  const uint32_t *__restrict__ bm = P.acc_bm + P.bm_off[o];
+  for (uint32_t wi = tid; wi < n_words; wi += stride)
+  {
+    uint32_t bits = bm[wi];
+    if (bits == 0)
+      continue;
+    const uint32_t row = wi / rw, xw = wi - row * rw;
+    uint32_t rank = rank_of(P, o, row, (int)(xw * 32u));
+    const int s = (int)(row / (uint32_t)ov.h) + 1, y = (int)(row % (uint32_t)ov.h);
+    while (bits && rank < P.cap[o])
+    {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      FeatHead hd;
+      refine_keypoint(P, ov, o, (int)(xw * 32u) + b, y, s, &hd);
+      prim[P.sec_off[o] + rank] = hd;
+      rank++;
     }
   }
 }
@@ -498,20 +498,31 @@ cudaError_t extrema_plan_build(const DetectParams &P, ExtremaPlan **plan_io)
 
 void extrema_plan_destroy(ExtremaPlan *pl) { delete pl; }
 
-void extrema_layout(DetectParams *P, size_t *bm_words, size_t *rows)
+void extrema_layout(DetectParams *P, size_t *bm_words, size_t *rows, size_t *queue_entries, uint32_t queue_total)
 {
-  size_t words = 0, nrows = 0;
+  size_t words = 0, nrows = 0, qn = 0;
+  double px_total = 0.;
+  for (int o = 0; o < P->n_oct; o++)
+    px_total += (double)P->oct[o].w * (double)P->oct[o].h;
   for (int o = 0; o < P->n_oct; o++)
   {
     P->bm_off[o] = (uint32_t)words;
     P->bm_rw[o] = (uint32_t)((P->oct[o].w + 31) / 32);
     P->row_off[o] = (uint32_t)nrows;
     const size_t r = (size_t)P->ns * (size_t)P->oct[o].h;
-    words += (r * P->bm_rw[o] + 3) & ~(size_t)3; /* 16-byte groups: the scans load four words at a time */
+    words += (r * P->bm_rw[o] + 3) & ~(size_t)3;
     nrows += r;
+    /* the octave's share of the extrema queue, by pixel count, at least 256 entries */
+    size_t share = (size_t)((double)queue_total * ((double)P->oct[o].w * (double)P->oct[o].h) / (px_total > 0. ? px_total : 1.));
+    if (share < 256)
+      share = 256;
+    P->q_off[o] = (uint32_t)qn;
+    P->q_cap[o] = (uint32_t)share;
+    qn += share;
   }
   *bm_words = words;
   *rows = nrows;
+  *queue_entries = qn;
 }
 
 cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectCounters *cnt, FeatHead *prim, cudaStream_t st, uint64_t *launch_count)
@@ -519,14 +530,11 @@ cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectC
   if (!pl || !pl->valid || pl->n_tiles == 0 || P.oe <= P.ob)
     return cudaSuccess;
   int t_begin = 0, t_end = 0;
-  uint32_t total_groups = 0;
   for (int o = 0; o < P.oe; o++)
   {
     const int n = ((P.oct[o].w + EX_TW - 1) / EX_TW) * ((P.oct[o].h + EX_TH - 1) / EX_TH);
     if (o < P.ob)
       t_begin += n;
-    else
-      total_groups += ((uint32_t)(P.ns * P.oct[o].h) * P.bm_rw[o] + 3u) >> 2;
     t_end += n;
   }
   const size_t smem = 2 * sizeof(float) * (size_t)((((P.ns + 2) * EX_SH * EX_SW) + 31) & ~31);
@@ -562,13 +570,10 @@ cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectC
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
-  /* one thread per group of four bitmap words, at most 8 CTAs per SM in flight */
-  uint32_t bgrid = (total_groups + BM_THREADS - 1) / BM_THREADS;
-  if (bgrid > (uint32_t)sms * 8u)
-    bgrid = (uint32_t)sms * 8u;
-  refine_mark_kernel<<<bgrid, BM_THREADS, 0, st>>>(P, total_groups, cnt);
+  const dim3 rgrid(RF_CTAS, P.oe - P.ob, 1);
+  refine_kernel<<<rgrid, RF_THREADS, 0, st>>>(P, cnt);
   row_scan_kernel<<<P.oe - P.ob, SCAN_THREADS, 0, st>>>(P, cnt);
-  rank_emit_kernel<<<bgrid, BM_THREADS, 0, st>>>(P, total_groups, prim);
+  rank_kernel<<<rgrid, RF_THREADS, 0, st>>>(P, cnt, prim);
   *launch_count += 4;
   return cudaGetLastError();
 }

@@ -72,16 +72,19 @@ struct DetectParams
   uint32_t max_feats;
   /* ordered compaction of the keypoints (extrema.cu): one bit per (s, y, x) with s in [1, ns], rows of bm_rw[o] 32-bit words;
    * bit (s, y, x) of octave o = bit (x & 31) of word bm_off[o] + ((s-1)*h + y) * bm_rw[o] + (x >> 5) */
-  uint32_t *raw_bm;   /* strict extrema */
-  uint32_t *acc_bm;   /* keypoints accepted by the refinement */
+  uint32_t *acc_bm;   /* keypoints accepted by the refinement (cleared before every detection) */
   uint32_t *row_cnt;  /* accepted keypoints per (s, y) row, turned into the row's first rank by row_scan_kernel */
   uint32_t bm_off[VKS_MAX_OCT], bm_rw[VKS_MAX_OCT], row_off[VKS_MAX_OCT];
+  /* queue of strict extrema per octave: key (s << 40 | y << 20 | x), bit 63 = accepted; q_heads[i] = refined record of entry i */
+  unsigned long long *raw_q;
+  FeatHead *q_heads;
+  uint32_t q_off[VKS_MAX_OCT], q_cap[VKS_MAX_OCT];
 };
 
 /* per-buffer device counters, zeroed at the start of every detection */
 struct DetectCounters
 {
-  uint32_t n_raw[VKS_MAX_OCT];    /* strict extrema found (statistics) */
+  uint32_t n_raw[VKS_MAX_OCT];    /* strict extrema found = queue fill (keeps counting past the queue capacity) */
   uint32_t n_cand[VKS_MAX_OCT];   /* accepted keypoints found (may exceed capacity) */
   uint32_t n_prim[VKS_MAX_OCT];   /* primaries kept = min(n_cand, cap) */
   uint32_t n_found[VKS_MAX_OCT];  /* primaries + extra orientations found */
@@ -199,7 +202,8 @@ void extrema_plan_destroy(ExtremaPlan *pl);
 /* scan + refinement + ordered compaction of the octaves [P.ob, P.oe): prim[sec_off[o] + rank] for rank < cap[o] */
 cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectCounters *cnt, FeatHead *prim, cudaStream_t st, uint64_t *launch_count);
 /* words of each bitmap and rows of row_cnt the current pyramid needs; fills bm_off / bm_rw / row_off of P */
-void extrema_layout(DetectParams *P, size_t *bm_words, size_t *rows);
+/* also: the octaves' shares (q_off / q_cap) of an extrema queue of queue_total entries */
+void extrema_layout(DetectParams *P, size_t *bm_words, size_t *rows, size_t *queue_entries, uint32_t queue_total);
 bool extrema_scales_supported(int ns);
 cudaError_t launch_orientation(const DetectParams &P, DetectCounters *cnt, const FeatHead *prim, float *ori, uint32_t *n_ori, cudaStream_t st);
 cudaError_t launch_assemble(const DetectParams &P, DetectCounters *cnt, const uint32_t *n_ori, uint32_t *feat_src, uint32_t *host_counts,
