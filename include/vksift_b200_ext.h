@@ -73,6 +73,19 @@ extern "C"
   VKSIFT_EXPORT void vksiftx_matchFeaturesAgainstDevice(vksift_Instance instance, const uint32_t gpu_buffer_id_A, const void *d_descriptors_B,
                                                         const uint32_t nb_feats_B);
 
+  /* All-pairs step of cross-image matching (one image per GPU, descriptor blocks exchanged with an all-gather): 2-NN of
+   * buffer A's features against EACH of n_blocks descriptor blocks read in place from caller-owned device memory (block j =
+   * counts[j] rows of 128 bytes at d_blocks + j * block_stride_bytes, 128-byte aligned), all searches enqueued back to back
+   * with no host round trip in between.  Blocks with fewer than 2 rows and block `skip_block` (the caller's own block; pass
+   * 0xffffffff to skip none) are left out.  Asynchronous like vksift_matchFeatures.  vksiftx_downloadMatchesBlocks blocks
+   * until the searches are done and writes n_blocks consecutive lists of vksift_getFeaturesNumber(A) records (list j =
+   * matches against block j, same record semantics as vksift_downloadMatches; the lists of left-out blocks are zero-filled)
+   * with ONE device-to-host copy. */
+  VKSIFT_EXPORT void vksiftx_matchFeaturesAgainstBlocks(vksift_Instance instance, const uint32_t gpu_buffer_id_A, const void *d_blocks,
+                                                        const uint32_t n_blocks, const uint64_t block_stride_bytes, const uint32_t *counts,
+                                                        const uint32_t skip_block);
+  VKSIFT_EXPORT void vksiftx_downloadMatchesBlocks(vksift_Instance instance, vksift_Match_2NN *matches, const uint32_t n_blocks);
+
   /* Device pointer of the last match result: vksift_getMatchesNumber() rows of vksift_Match_2NN. */
   VKSIFT_EXPORT void *vksiftx_getMatchesDevice(vksift_Instance instance);
 

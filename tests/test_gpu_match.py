@@ -193,3 +193,40 @@ def test_match_against_device_descriptors_in_place(api, oracle_mod, shape):
         inst.match_against_device(0, slot[1].data_ptr(), 1)
     assert e.value.code == api.VKSIFT_INVALID_INPUT_ERROR
     inst.close()
+
+
+def test_match_against_blocks_batched_equals_oracle(api, oracle_mod):
+    """vksiftx_matchFeaturesAgainstBlocks (the all-pairs step: A against every gathered peer block, enqueued back to back, one
+    download): every list equals the oracle's, the skipped block and a block with one row come back zero-filled."""
+    import torch
+    from vulkansift_b200.synth import random_descriptors
+    cap = 1023
+    counts = [700, 1, 1023, 333]
+    da = random_descriptors(900, 51)
+    blocks = torch.zeros((len(counts), cap + 1, 128), dtype=torch.uint8, device="cuda")
+    host = []
+    for j, n in enumerate(counts):
+        d = random_descriptors(n, 60 + j)
+        if j == 2:
+            d[5] = d[4]          # a tie inside a block
+            d[:2] = da[10]       # b = 0 and b = 1 tie for A row 10
+        host.append(d)
+        blocks[j, :n] = torch.from_numpy(d).cuda()
+    torch.cuda.synchronize()
+    with api.Instance(max_nb_sift_per_buffer=4096) as inst:
+        inst.upload_features(_feats(api, da), 0)
+        inst.match_against_blocks(0, blocks.data_ptr(), counts, blocks.stride(0), skip_block=3)
+        res = inst.download_matches_blocks(len(da))
+        assert res.shape == (4, 900)
+        _check(res[0], oracle_mod.match_descriptors(da, host[0]), "block 0")
+        _check(res[2], oracle_mod.match_descriptors(da, host[2]), "block 2")
+        assert not res[1].view(np.uint8).any() and not res[3].view(np.uint8).any()
+        # a second call with other blocks skipped reuses the buffers
+        inst.match_against_blocks(0, blocks.data_ptr(), counts, blocks.stride(0), skip_block=0)
+        res = inst.download_matches_blocks(len(da))
+        _check(res[3], oracle_mod.match_descriptors(da, host[3]), "block 3")
+        assert not res[0].view(np.uint8).any()
+        # the ordinary single-result API is untouched
+        inst.upload_features(_feats(api, host[0]), 1)
+        inst.match(0, 1)
+        _check(inst.download_matches(), oracle_mod.match_descriptors(da, host[0]), "plain match afterwards")

@@ -100,6 +100,8 @@ def _load_library(path=LIB_PATH, analysis=False):
         "vksiftx_copyDescriptorsToDevice": (u32, [I, u32, C.c_void_p, u32]),
         "vksiftx_getMatchesDevice": (C.c_void_p, [I]),
         "vksiftx_matchFeaturesAgainstDevice": (None, [I, u32, C.c_void_p, u32]),
+        "vksiftx_matchFeaturesAgainstBlocks": (None, [I, u32, C.c_void_p, u32, C.c_uint64, P(u32), u32]),
+        "vksiftx_downloadMatchesBlocks": (None, [I, C.c_void_p, u32]),
         "vksiftx_setProfiling": (None, [I, C.c_bool]),
         "vksiftx_getStageTimesMs": (None, [I, P(C.c_float)]),
         "vksiftx_matchFeaturesCrossChecked": (C.c_uint32, [I, C.c_uint32, C.c_uint32, C.c_float, P(C.c_uint32), C.c_uint32]),
@@ -322,6 +324,25 @@ class Instance:
         """2-NN of buffer_a's features against n_b descriptors read in place from device memory."""
         self._lib.vksiftx_matchFeaturesAgainstDevice(self._h, buffer_a, dev_ptr, n_b)
         self._check("vksiftx_matchFeaturesAgainstDevice")
+
+    def match_against_blocks(self, buffer_a, dev_ptr, counts, block_stride_bytes, skip_block=0xFFFFFFFF):
+        """2-NN of buffer_a's features against every descriptor block (block j = counts[j] rows at dev_ptr + j * stride), enqueued
+        back to back; fetch the results with download_matches_blocks()."""
+        arr = (C.c_uint32 * len(counts))(*[int(c) for c in counts])
+        self._n_blocks = len(counts)
+        self._blocks_na = None
+        self._lib.vksiftx_matchFeaturesAgainstBlocks(self._h, buffer_a, dev_ptr, len(counts), int(block_stride_bytes), arr, int(skip_block))
+        self._check("vksiftx_matchFeaturesAgainstBlocks")
+
+    def download_matches_blocks(self, n_rows, out=None):
+        """(n_blocks, n_rows) MATCH_DTYPE array; n_rows = feature count of buffer A of the last match_against_blocks."""
+        nb = self._n_blocks
+        if out is None:
+            out = np.zeros((nb, n_rows), MATCH_DTYPE)
+        assert out.dtype == MATCH_DTYPE and out.size >= nb * n_rows
+        self._lib.vksiftx_downloadMatchesBlocks(self._h, out.ctypes.data, nb)
+        self._check("vksiftx_downloadMatchesBlocks")
+        return out.reshape(-1)[:nb * n_rows].reshape(nb, n_rows)
 
     def matches_device(self):
         return self._lib.vksiftx_getMatchesDevice(self._h)

@@ -182,6 +182,8 @@ struct vksift_Instance_T
   MatchWorkspace *match_ws = nullptr;
   vksift_Match_2NN *d_matches = nullptr;
   vksift_Match_2NN *d_matches_rev = nullptr; /* B->A list of the cross-checked matcher */
+  vksift_Match_2NN *d_matches_blocks = nullptr; /* [blocks_cap][max_nb_sift_per_buffer]: results of vksiftx_matchFeaturesAgainstBlocks */
+  uint32_t blocks_cap = 0, blocks_n = 0, blocks_na = 0;
   uint32_t *d_pairs = nullptr;               /* [2*max + 1]: filtered pairs, count at the end */
   uint32_t nb_matches = 0;
   int matcher_impl = 0;
@@ -688,6 +690,7 @@ void destroy_instance(vksift_Instance inst)
   cudaFree(inst->d_aos);
   cudaFree(inst->d_matches);
   cudaFree(inst->d_matches_rev);
+  cudaFree(inst->d_matches_blocks);
   cudaFree(inst->d_pairs);
   match_workspace_destroy(inst->match_ws);
   extrema_plan_destroy(inst->extrema_plan);
@@ -1701,6 +1704,105 @@ extern "C"
       return;
     }
     match_common(inst, gpu_buffer_id_A, 0, (const uint8_t *)d_descriptors_B, nb_feats_B, "vksiftx_matchFeaturesAgainstDevice");
+  }
+
+  void vksiftx_matchFeaturesAgainstBlocks(vksift_Instance inst, const uint32_t gpu_buffer_id_A, const void *d_blocks, const uint32_t n_blocks,
+                                          const uint64_t block_stride_bytes, const uint32_t *counts, const uint32_t skip_block)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id_A) || d_blocks == NULL || counts == NULL || n_blocks == 0 || n_blocks > 1024u ||
+        ((uintptr_t)d_blocks & 127u) != 0 || (block_stride_bytes & 127u) != 0)
+    {
+      LOGE(TAG, "vksiftx_matchFeaturesAgainstBlocks() error: invalid input (blocks must be 128-byte aligned device memory, at most 1024 blocks).");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    for (uint32_t j = 0; j < n_blocks; j++)
+      if (counts[j] > inst->cfg.max_nb_sift_per_buffer || (uint64_t)counts[j] * 128u > block_stride_bytes)
+      {
+        LOGE(TAG, "vksiftx_matchFeaturesAgainstBlocks() error: block %u holds %u descriptors (more than a block or max_nb_sift_per_buffer).", j, counts[j]);
+        inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+        return;
+      }
+    bool ok = true;
+    {
+      DeviceGuard g(inst->device);
+      wait_pipelines(inst, true, true);
+      const uint32_t na = buffer_count(inst, gpu_buffer_id_A, false);
+      FeatureBuffer &A = inst->buffers[gpu_buffer_id_A];
+      const size_t maxf = inst->cfg.max_nb_sift_per_buffer;
+      auto run = [&]() -> bool {
+        if (n_blocks > inst->blocks_cap)
+        {
+          if (inst->d_matches_blocks)
+            CU_TRY(cudaFree(inst->d_matches_blocks));
+          inst->d_matches_blocks = nullptr;
+          inst->blocks_cap = 0;
+          CU_TRY(cudaMalloc(&inst->d_matches_blocks, sizeof(vksift_Match_2NN) * maxf * n_blocks));
+          inst->blocks_cap = n_blocks;
+        }
+        inst->blocks_n = n_blocks;
+        inst->blocks_na = na;
+        if (na == 0)
+          return true;
+        if (!ensure_norms(inst, A, na))
+          return false;
+        for (uint32_t j = 0; j < n_blocks; j++)
+        {
+          vksift_Match_2NN *out = inst->d_matches_blocks + (size_t)j * maxf;
+          if (j == skip_block || counts[j] < 2)
+          {
+            CU_TRY(cudaMemsetAsync(out, 0, sizeof(vksift_Match_2NN) * (size_t)na, inst->stream));
+            continue;
+          }
+          const uint8_t *b = (const uint8_t *)d_blocks + (size_t)j * block_stride_bytes;
+          /* the searches share the workspace (B-side norms, partial keys): they are ordered by the stream */
+          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, A.norm_plain, b, counts[j], nullptr, out, inst->stream, nullptr,
+                              &inst->launches));
+        }
+        CU_TRY(cudaEventRecord(inst->ev_match_done, inst->stream));
+        return true;
+      };
+      ok = run();
+      inst->match_pending = ok && na > 0;
+      inst->match_a = inst->match_b = gpu_buffer_id_A;
+    }
+    if (!ok)
+    {
+      LOGE(TAG, "vksiftx_matchFeaturesAgainstBlocks() error: Failed to start the matching pipeline.");
+      inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
+    }
+  }
+
+  void vksiftx_downloadMatchesBlocks(vksift_Instance inst, vksift_Match_2NN *matches, const uint32_t n_blocks)
+  {
+    if (matches == NULL || n_blocks != inst->blocks_n)
+    {
+      LOGE(TAG, "vksiftx_downloadMatchesBlocks() error: invalid input (%u blocks asked, the last search had %u).", n_blocks, inst->blocks_n);
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return;
+    }
+    bool ok = true;
+    {
+      DeviceGuard g(inst->device);
+      wait_pipelines(inst, false, true);
+      if (inst->blocks_na > 0)
+      {
+        auto run = [&]() -> bool {
+          /* [n_blocks][na] on the host from [n_blocks][max] on the device: one strided copy */
+          CU_TRY(cudaMemcpy2DAsync(matches, sizeof(vksift_Match_2NN) * (size_t)inst->blocks_na, inst->d_matches_blocks,
+                                   sizeof(vksift_Match_2NN) * (size_t)inst->cfg.max_nb_sift_per_buffer, sizeof(vksift_Match_2NN) * (size_t)inst->blocks_na,
+                                   n_blocks, cudaMemcpyDeviceToHost, inst->stream));
+          CU_TRY(cudaStreamSynchronize(inst->stream));
+          return true;
+        };
+        ok = run();
+      }
+    }
+    if (!ok)
+    {
+      LOGE(TAG, "vksiftx_downloadMatchesBlocks() error when downloading SIFT matches from GPU memory.");
+      inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
+    }
   }
 
   uint32_t vksift_getMatchesNumber(vksift_Instance inst) { return inst->nb_matches; }

@@ -101,6 +101,17 @@ def gather_instance_descriptors(inst, buffer_id, group=None, capacity=None):
     return counts, xb.recv
 
 
+def match_against_peers_batched(inst, buffer_a, counts, blocks, rank, out=None):
+    """Match the local features (buffer_a) against EVERY peer block of the gathered tensor with one library call
+    (vksiftx_matchFeaturesAgainstBlocks: the searches are enqueued back to back, no host round trip in between) and ONE
+    download.  Returns {peer: matches or None (peer holds fewer than 2 descriptors)}."""
+    assert blocks.data_ptr() % 128 == 0 and (blocks.stride(0) * blocks.element_size()) % 128 == 0
+    n_a = inst.features_number(buffer_a)
+    inst.match_against_blocks(buffer_a, blocks.data_ptr(), counts, blocks.stride(0) * blocks.element_size(), skip_block=rank)
+    res = inst.download_matches_blocks(n_a, out=out)
+    return {j: (res[j] if (j != rank and counts[j] >= 2) else None) for j in range(len(counts)) if j != rank}
+
+
 def match_against_peers(inst, buffer_a, scratch_buffer, counts, blocks, rank, world, download=True):
     """Match the local features (buffer_a) against every peer block, read in place from the gathered tensor
     (vksiftx_matchFeaturesAgainstDevice; a block whose address is not 128-byte aligned goes through `scratch_buffer`).
