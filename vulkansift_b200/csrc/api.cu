@@ -13,6 +13,8 @@
  */
 #include "vksift_internal.h"
 
+#include <nvtx3/nvToolsExt.h> /* header-only: ranges are no-ops unless a profiler injects its library */
+
 #include <cassert>
 #include <cstdarg>
 #include <cstdio>
@@ -814,9 +816,24 @@ bool create_resources(vksift_Instance inst)
     inst->desc_m_table = inst->primary->desc_m_table; /* read-only table, built once per instance */
   else
   {
+    /* M(hr) of ComputeDescriptors.comp:116-124 only depends on the window radius: tabulated on the host with the shared
+     * arithmetic of include/vksift_arith.h (same IEEE sequence under g++ -ffp-contract=off as in the kernels) */
+    float h_table[VKS_DESC_M_TABLE];
+    for (int hr = 0; hr < VKS_DESC_M_TABLE; hr++)
+    {
+      float m = 0.f;
+      for (int i = 0; i < hr; i++)
+        for (int j = i; j < hr; j++)
+        {
+          float t = vks_mul(vks_expf(vks_mul(-0.125f, (float)((i * i) + (j * j)))), VKS_SQRT2_F);
+          if (j > i)
+            t = vks_mul(t, 2.f);
+          m = vks_add(m, t);
+        }
+      h_table[hr] = m;
+    }
     CU_TRY(cudaMalloc(&inst->desc_m_table, sizeof(float) * VKS_DESC_M_TABLE));
-    CU_TRY(launch_descriptor_scale_table(inst->desc_m_table, inst->stream));
-    CU_TRY(cudaStreamSynchronize(inst->stream)); /* the other lanes read it from their own streams */
+    CU_TRY(cudaMemcpy(inst->desc_m_table, h_table, sizeof(h_table), cudaMemcpyHostToDevice));
   }
   CU_TRY(cudaMalloc(&inst->d_aos, sizeof(vksift_Feature) * maxf));
   inst->graphs.resize(c.sift_buffer_count);
@@ -873,6 +890,25 @@ bool create_resources(vksift_Instance inst)
 #else
 #define VKS_SKIP(inst) 0
 #endif
+
+/* Named ranges around the enqueue of each stage, with the region names the reference gives its debug markers
+ * (beginMarkerRegion, sift_detector.c:29-50, 865-1297; sift_matcher.c:251) and, like there, only when the instance was
+ * created with use_gpu_debug_functions: an Nsight timeline of this library reads like a RenderDoc / Nsight Graphics capture
+ * of the reference. */
+struct MarkerRegion
+{
+  bool on;
+  MarkerRegion(vksift_Instance inst, const char *name) : on(inst->cfg.use_gpu_debug_functions)
+  {
+    if (on)
+      nvtxRangePushA(name);
+  }
+  ~MarkerRegion()
+  {
+    if (on)
+      nvtxRangePop();
+  }
+};
 
 struct TraceScope
 {
@@ -934,7 +970,11 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   const bool capturing = (cap_status == cudaStreamCaptureStatusActive);
 
   inst->trace_used = 0;
-  CU_TRY(cudaMemcpyAsync(inst->d_src_slot, inst->h_src_slot, sizeof(void *), cudaMemcpyHostToDevice, st));
+  {
+    MarkerRegion mr(inst, "Clear buffer data");
+    CU_TRY(cudaMemcpyAsync(inst->d_src_slot, inst->h_src_slot, sizeof(void *), cudaMemcpyHostToDevice, st));
+  }
+  MarkerRegion mr_pyr(inst, "Scale space construction + DoG computation");
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D0], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   CU_TRY(cudaMemsetAsync(fb.cnt, 0, sizeof(DetectCounters), st));
@@ -952,6 +992,7 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   inst->ev_d1b_valid = split && prof;
   inst->n_pyr_events = (split && prof) ? n_fast : 0;
   auto post_chain = [&](int ob, int oe, cudaStream_t s) -> bool {
+    MarkerRegion mr(inst, "ExtractKeypoints + ComputeOrientation");
     DetectParams Q = P;
     Q.ob = ob;
     Q.oe = oe;
@@ -1099,6 +1140,7 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   DetectParams PA = P;
   if (split)
     PA.oe = 1; /* octave 0 (its layers are complete on this stream); the other octaves follow on the side stream */
+  MarkerRegion mr_feat(inst, "ExtractKeypoints + ComputeOrientation + ComputeDescriptors + CopySiftCount");
   if (!(VKS_SKIP(inst) & 4))
   {
     CU_TRY(launch_extrema(PA, inst->extrema_plan, fb.cnt, inst->prim, st, &inst->launches));
@@ -1403,7 +1445,8 @@ extern "C"
       return VKSIFT_VULKAN_ERROR;
     }
     if (config->use_gpu_debug_functions)
-      LOGW(TAG, "use_gpu_debug_functions is accepted but has no effect: CUDA profilers need no frame delimiters.");
+      LOGI(TAG, "use_gpu_debug_functions: NVTX ranges with the reference's marker region names are emitted around every stage (the debug "
+                "presenter and frame delimiters have no CUDA counterpart).");
     LOGI(TAG, "vksift_createInstance() success");
     return VKSIFT_SUCCESS;
   }
@@ -1639,6 +1682,7 @@ extern "C"
         FeatureBuffer &A = inst->buffers[gpu_buffer_id_A];
         const uint8_t *b_desc = d_desc_b ? d_desc_b : inst->buffers[gpu_buffer_id_B].desc;
         auto run = [&]() -> bool {
+          MarkerRegion mr(inst, "Matching");
           const bool prof = inst->profiling;
           if (prof)
             CU_TRY(cudaEventRecord(inst->ev[EV_M0], inst->stream));

@@ -304,34 +304,10 @@ cudaError_t launch_assemble(const DetectParams &P, DetectCounters *cnt, const ui
 #define DESC_THREADS 128
 #define DESC_MAXBOX 160 /* window rows the row-interval tables hold (2R+1 <= 77 for the default configuration) */
 
-/* M(hr) of ComputeDescriptors.comp:116-124 for hr = R/2 < VKS_DESC_M_TABLE:
+/* m_table[hr] = M(hr) of ComputeDescriptors.comp:116-124 for hr = R/2 < VKS_DESC_M_TABLE:
  *   for i<hr { m += e(i,i)*sqrt2; for j in (i, hr) m += e(i,j)*sqrt2*2 },  e(i,j) = exp(-0.125*(i*i+j*j))
- * in the shader's sequential fp32 order.  The sum only depends on the window radius, so it is tabulated once per instance
- * instead of being rebuilt (2*hr block barriers and a serial sum) for every feature. */
-__global__ void descriptor_scale_table_kernel(float *__restrict__ table)
-{
-  const int hr = blockIdx.x * blockDim.x + threadIdx.x;
-  if (hr >= VKS_DESC_M_TABLE)
-    return;
-  const float es = -0.125f;
-  float m = 0.f;
-  for (int i = 0; i < hr; i++)
-    for (int j = i; j < hr; j++)
-    {
-      float t = vks_expf(es * (float)((i * i) + (j * j))) * VKS_SQRT2_F;
-      if (j > i)
-        t = t * 2.f;
-      m += t;
-    }
-  table[hr] = m;
-}
-
-cudaError_t launch_descriptor_scale_table(float *table, cudaStream_t st)
-{
-  descriptor_scale_table_kernel<<<1, VKS_DESC_M_TABLE, 0, st>>>(table);
-  return cudaGetLastError();
-}
-
+ * in the shader's sequential fp32 order.  The sum only depends on the window radius, so it is tabulated once per instance (on the
+ * host, api.cu) instead of being rebuilt (2*hr block barriers and a serial sum) for every feature. */
 __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_constant__ DetectParams P, DetectCounters *__restrict__ cnt,
                                                                   const float *__restrict__ m_table, const FeatHead *__restrict__ prim,
                                                                   const float *__restrict__ ori,

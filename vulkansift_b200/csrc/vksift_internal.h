@@ -210,7 +210,6 @@ cudaError_t launch_assemble(const DetectParams &P, DetectCounters *cnt, const ui
                             cudaStream_t st);
 /* table of the descriptor's fixed-point scale sums M(R/2) (ComputeDescriptors.comp:116-124 only depends on the window radius) */
 #define VKS_DESC_M_TABLE 128
-cudaError_t launch_descriptor_scale_table(float *table, cudaStream_t st);
 cudaError_t launch_descriptors(const DetectParams &P, DetectCounters *cnt, const float *m_table, const FeatHead *prim, const float *ori, const uint32_t *feat_src,
                                FeatHead *out_heads, uint8_t *out_desc, cudaStream_t st);
 /* AoS <-> SoA for host transfers */

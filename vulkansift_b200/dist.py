@@ -67,6 +67,7 @@ class _ExchangeBuffers:
         self.send = torch.zeros((capacity + 1, 128), dtype=torch.uint8, device=dev)
         self.recv = torch.empty((world, capacity + 1, 128), dtype=torch.uint8, device=dev)
         self.count_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.counts_host = torch.zeros((world, 8), dtype=torch.uint8).pin_memory()  # the in-band counts of all ranks, read back with one strided copy
 
 
 _exchange_buffers = {}
@@ -97,7 +98,9 @@ def gather_instance_descriptors(inst, buffer_id, group=None, capacity=None):
     xb.count_host[0] = n
     xb.send[capacity].view(torch.int64)[:1].copy_(xb.count_host, non_blocking=True)
     dist.all_gather_into_tensor(xb.recv.view(world * (capacity + 1), 128), xb.send, group=group)
-    counts = [int(c) for c in xb.recv[:, capacity, :8].contiguous().view(torch.int64).flatten().tolist()]
+    xb.counts_host.copy_(xb.recv[:, capacity, :8], non_blocking=True)  # one strided device-to-host copy, no staging kernel
+    torch.cuda.current_stream(dev).synchronize()
+    counts = [int(c) for c in xb.counts_host.view(torch.int64).flatten().tolist()]
     return counts, xb.recv
 
 
