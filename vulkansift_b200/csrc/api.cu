@@ -57,11 +57,10 @@ struct FeatureBuffer
   uint32_t cur_w = 0, cur_h = 0;
   bool uploaded = false; /* content came from vksift_uploadFeatures (is_packed in the reference) */
   uint32_t n_uploaded = 0;
-  /* matcher operands of the descriptors (|d|^2 and the binary16 blocks of the tensor-core kernel), prepared by the first match
+  /* |d|^2 of the descriptors in the two forms the matcher reads (A side plain, B side packed), computed by the first match
    * that uses the buffer and kept until its content changes: matching one image against many (all-pairs) or the same pair
-   * repeatedly does not prepare them again */
-  uint32_t *norm_plain = nullptr;
-  void *op16 = nullptr;
+   * repeatedly does not recompute them */
+  uint32_t *norm_plain = nullptr, *norm_packed = nullptr;
   bool norms_valid = false;
   uint32_t norms_n = 0;
 };
@@ -665,7 +664,7 @@ void destroy_instance(vksift_Instance inst)
     cudaFree(fb.desc);
     cudaFree(fb.cnt);
     cudaFree(fb.norm_plain);
-    cudaFree(fb.op16);
+    cudaFree(fb.norm_packed);
     if (fb.host_counts)
       cudaFreeHost(fb.host_counts);
   }
@@ -862,7 +861,7 @@ bool create_resources(vksift_Instance inst)
     CU_TRY(cudaMalloc(&fb.cnt, sizeof(DetectCounters)));
     CU_TRY(cudaMemset(fb.cnt, 0, sizeof(DetectCounters)));
     CU_TRY(cudaMalloc(&fb.norm_plain, sizeof(uint32_t) * (maxf + 256)));
-    CU_TRY(cudaMalloc(&fb.op16, match_operand_bytes((uint32_t)maxf)));
+    CU_TRY(cudaMalloc(&fb.norm_packed, sizeof(uint32_t) * (maxf + 256)));
     CU_TRY(cudaHostAlloc(&fb.host_counts, sizeof(uint32_t) * (1 + 2 * VKS_MAX_OCT), cudaHostAllocMapped));
     memset(fb.host_counts, 0, sizeof(uint32_t) * (1 + 2 * VKS_MAX_OCT));
     CU_TRY(cudaHostGetDevicePointer(&fb.host_counts_dev, fb.host_counts, 0));
@@ -1654,7 +1653,7 @@ extern "C"
   {
     if (fb.norms_valid && fb.norms_n == n)
       return true;
-    CU_TRY(launch_match_prepare(fb.desc, n, fb.norm_plain, fb.op16, inst->stream));
+    CU_TRY(launch_norms(fb.desc, n, fb.norm_plain, fb.norm_packed, inst->stream));
     inst->launches++;
     fb.norms_valid = true;
     fb.norms_n = n;
@@ -1690,17 +1689,15 @@ extern "C"
           if (na > 0 && !ensure_norms(inst, A, na))
             return false;
           const uint32_t *nb_cached = nullptr;
-          const void *opb_cached = nullptr;
           if (na > 0 && !d_desc_b)
           {
             FeatureBuffer &B = inst->buffers[gpu_buffer_id_B];
             if (!ensure_norms(inst, B, nb))
               return false;
-            nb_cached = B.norm_plain;
-            opb_cached = B.op16;
+            nb_cached = B.norm_packed;
           }
-          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, A.norm_plain, A.op16, b_desc, nb, nb_cached, opb_cached, inst->d_matches,
-                              inst->stream, prof ? inst->ev[EV_M1] : nullptr, &inst->launches));
+          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, A.norm_plain, b_desc, nb, nb_cached, inst->d_matches, inst->stream,
+                              prof ? inst->ev[EV_M1] : nullptr, &inst->launches));
           if (prof)
           {
             if (na == 0)
@@ -1803,8 +1800,8 @@ extern "C"
           }
           const uint8_t *b = (const uint8_t *)d_blocks + (size_t)j * block_stride_bytes;
           /* the searches share the workspace (B-side norms, partial keys): they are ordered by the stream */
-          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, A.norm_plain, A.op16, b, counts[j], nullptr, nullptr, out, inst->stream,
-                              nullptr, &inst->launches));
+          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, A.norm_plain, b, counts[j], nullptr, out, inst->stream, nullptr,
+                              &inst->launches));
         }
         CU_TRY(cudaEventRecord(inst->ev_match_done, inst->stream));
         return true;
@@ -2074,10 +2071,10 @@ extern "C"
         auto run = [&]() -> bool {
           if (!ensure_norms(inst, A, na) || !ensure_norms(inst, B, nb))
             return false;
-          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, B.desc, nb, B.norm_plain, B.op16, A.desc, na, A.norm_plain, A.op16, inst->d_matches_rev,
-                              inst->stream, nullptr, &inst->launches));
-          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, A.norm_plain, A.op16, B.desc, nb, B.norm_plain, B.op16, inst->d_matches,
-                              inst->stream, nullptr, &inst->launches));
+          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, B.desc, nb, B.norm_plain, A.desc, na, A.norm_packed, inst->d_matches_rev, inst->stream,
+                              nullptr, &inst->launches));
+          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, A.norm_plain, B.desc, nb, B.norm_packed, inst->d_matches, inst->stream,
+                              nullptr, &inst->launches));
           CU_TRY(launch_match_filter(inst->d_matches, na, inst->d_matches_rev, nb, lowe_ratio, inst->d_pairs, (uint32_t)maxf, inst->d_pairs + 2 * maxf,
                                      inst->stream));
           inst->launches++;

@@ -2,8 +2,8 @@
  * match.cu -- brute-force 2-nearest-neighbour search on 128-byte descriptors.
  *
  * Replaces shaders/Get2NearestNeighbors.comp:43-104 (dispatched by
- * sift_matcher.c:246-279).  d(a,b)^2 = |a|^2 + |b|^2 - 2 a.b: a dense contraction that the tensor cores evaluate exactly
- * (match_tc.cuh: binary16 operands with the norms in extension columns, fp32 accumulation of integers below 2^24).
+ * sift_matcher.c:246-279).  d(a,b)^2 = |a|^2 + |b|^2 - 2 a.b with exact integer
+ * arithmetic; the a.b term is a dense u8 x u8 -> s32 contraction.
  *
  * Tie rule of the shader (strict '<', b=0 and b=1 initialised specially,
  * :69-96) == stable top-2 of B under the key (d, pos) with pos(0)=1, pos(1)=0,
@@ -21,11 +21,38 @@ namespace vks
 struct MatchWorkspace
 {
   uint32_t max_feats;
-  uint32_t *norm_a; /* |a|^2 per row (sides that come without cached operands) */
+  uint32_t *norm_a; /* |a|^2 per row */
   uint32_t *norm_b;
-  void *op_a, *op_b; /* binary16 operand blocks of such sides */
-  void *tc; /* tensor-core path state */
+  unsigned long long *partial; /* [splits][na][2] packed (d2 << 32 | pos) keys */
+  uint32_t partial_splits;
+  void *tc; /* tensor-core path state (tensor maps) */
 };
+
+/* ---- |x|^2 per descriptor ------------------------------------------------ */
+__device__ __forceinline__ uint32_t match_pos_host_device(uint32_t b) { return b < 2u ? (b ^ 1u) : b; }
+/* |x|^2 per descriptor.  packed == 0: plain norms (A side).  packed == 1 (B side): nbk = |b|^2 * 256 + (pos(b) & 255),
+ * the per-column constant of the tensor-core epilogue's 32-bit keys; |b|^2 <= 128*255^2 < 2^23 so nbk fits int32.
+ * Rows in [n, n_padded) do not exist and get the largest nbk: they lose every comparison. */
+#define NORM_PAD_VALUE 0x7fffffffu
+__global__ void norms_kernel(const uint8_t *__restrict__ desc, uint32_t n, uint32_t n_padded, uint32_t *__restrict__ out, int packed)
+{
+  /* one warp per descriptor, 4 bytes per lane */
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n)
+  {
+    if (row < n_padded && lane == 0)
+      out[row] = NORM_PAD_VALUE;
+    return;
+  }
+  const uint32_t v = __ldg((const uint32_t *)(desc + (size_t)row * 128) + lane);
+  uint32_t s = __dp4a(v, v, 0u);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, d);
+  if (lane == 0)
+    out[row] = packed ? (s * 256u + (match_pos_host_device(row) & 255u)) : s;
+}
 
 /* ---- SIMT cross-check kernel (verification only, vksiftx_setMatcherImpl(1)) */
 #define MS_ROWS 128
@@ -62,7 +89,7 @@ __global__ void __launch_bounds__(MS_ROWS) match_simt_kernel(const uint8_t *__re
     for (uint32_t i = threadIdx.x; i < cnt * 32; i += MS_ROWS)
       s_b[i >> 5][i & 31] = __ldg((const uint32_t *)(db + (size_t)b0 * 128) + i);
     if (threadIdx.x < cnt)
-      s_nb[threadIdx.x] = norm_b[b0 + threadIdx.x];
+      s_nb[threadIdx.x] = norm_b[b0 + threadIdx.x] >> 8; /* norm_b holds the packed nbk */
     __syncthreads();
     for (uint32_t j = 0; j < cnt; j++)
     {
@@ -92,15 +119,11 @@ cudaError_t match_workspace_create(MatchWorkspace **out, uint32_t max_feats)
   MatchWorkspace *ws = new MatchWorkspace();
   ws->max_feats = max_feats;
   ws->tc = nullptr;
-  ws->norm_a = ws->norm_b = nullptr;
-  ws->op_a = ws->op_b = nullptr;
+  ws->partial = nullptr;
+  ws->partial_splits = 0;
   cudaError_t e = cudaMalloc(&ws->norm_a, sizeof(uint32_t) * (size_t)(max_feats + 256));
   if (e == cudaSuccess)
     e = cudaMalloc(&ws->norm_b, sizeof(uint32_t) * (size_t)(max_feats + 256));
-  if (e == cudaSuccess)
-    e = cudaMalloc(&ws->op_a, match_operand_bytes(max_feats));
-  if (e == cudaSuccess)
-    e = cudaMalloc(&ws->op_b, match_operand_bytes(max_feats));
   if (e == cudaSuccess)
     e = match_tc_create(&ws->tc, max_feats);
   if (e != cudaSuccess)
@@ -119,8 +142,7 @@ void match_workspace_destroy(MatchWorkspace *ws)
   match_tc_destroy(ws->tc);
   cudaFree(ws->norm_a);
   cudaFree(ws->norm_b);
-  cudaFree(ws->op_a);
-  cudaFree(ws->op_b);
+  cudaFree(ws->partial);
   delete ws;
 }
 
@@ -194,40 +216,57 @@ cudaError_t launch_match_filter(const vksift_Match_2NN *m12, uint32_t na, const 
   return cudaGetLastError();
 }
 
-size_t match_operand_bytes(uint32_t max_feats) { return (size_t)MT_OP_ROW_BYTES * (((size_t)max_feats + 255) & ~(size_t)255); }
-
-cudaError_t launch_match_prepare(const uint8_t *desc, uint32_t n, uint32_t *norm, void *op, cudaStream_t st)
+__global__ void norms_both_kernel(const uint8_t *__restrict__ desc, uint32_t n, uint32_t n_padded, uint32_t *__restrict__ out_plain,
+                                  uint32_t *__restrict__ out_packed)
 {
-  const uint32_t n_pad = (n + 255u) & ~255u; /* whole pairs of row blocks */
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n)
+  {
+    if (row < n_padded && lane == 0)
+      out_packed[row] = NORM_PAD_VALUE;
+    return;
+  }
+  const uint32_t v = __ldg((const uint32_t *)(desc + (size_t)row * 128) + lane);
+  uint32_t s = __dp4a(v, v, 0u);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, d);
+  if (lane == 0)
+  {
+    out_plain[row] = s;
+    out_packed[row] = s * 256u + (match_pos_host_device(row) & 255u);
+  }
+}
+
+cudaError_t launch_norms(const uint8_t *desc, uint32_t n, uint32_t *out_plain, uint32_t *out_packed, cudaStream_t st)
+{
+  const uint32_t n_pad = (n + 127u) & ~127u;
   if (n_pad == 0)
     return cudaSuccess;
-  match_prepare_kernel<<<(n_pad * 32 + 255) / 256, 256, 0, st>>>(desc, n, n_pad, norm, (__half *)op);
+  norms_both_kernel<<<(n_pad * 32 + 255) / 256, 256, 0, st>>>(desc, n, n_pad, out_plain, out_packed);
   return cudaGetLastError();
 }
 
-cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *da, uint32_t na, const uint32_t *norm_a, const void *op_a, const uint8_t *db,
-                         uint32_t nb, const uint32_t *norm_b, const void *op_b, vksift_Match_2NN *out, cudaStream_t st, cudaEvent_t ev_after_prepare,
-                         uint64_t *launch_count)
+cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *da, uint32_t na, const uint32_t *norm_a, const uint8_t *db, uint32_t nb,
+                         const uint32_t *norm_b, vksift_Match_2NN *out, cudaStream_t st, cudaEvent_t ev_after_prepare, uint64_t *launch_count)
 {
   if (na == 0)
     return cudaSuccess;
-  if (na > ws->max_feats || nb > ws->max_feats)
-    return cudaErrorInvalidValue;
-  cudaError_t e = cudaSuccess;
-  if (!norm_a || !op_a)
+  const uint32_t nb_pad = (nb + 127u) & ~127u; /* the tensor-core path reads |b|^2 in tiles of 128 */
+  if (!norm_a)
   {
-    e = launch_match_prepare(da, na, ws->norm_a, ws->op_a, st);
+    norms_kernel<<<(na * 32 + 255) / 256, 256, 0, st>>>(da, na, na, ws->norm_a, 0);
     *launch_count += 1;
     norm_a = ws->norm_a;
-    op_a = ws->op_a;
   }
-  if (e == cudaSuccess && (!norm_b || !op_b))
+  if (!norm_b)
   {
-    e = launch_match_prepare(db, nb, ws->norm_b, ws->op_b, st);
+    norms_kernel<<<(nb_pad * 32 + 255) / 256, 256, 0, st>>>(db, nb, nb_pad, ws->norm_b, 1);
     *launch_count += 1;
     norm_b = ws->norm_b;
-    op_b = ws->op_b;
   }
+  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
   if (ev_after_prepare)
@@ -238,7 +277,7 @@ cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *da, uint32
     *launch_count += 1;
     return cudaGetLastError();
   }
-  return match_tc_launch(ws->tc, da, na, norm_a, op_a, db, nb, norm_b, op_b, out, st, launch_count);
+  return match_tc_launch(ws->tc, da, na, norm_a, db, nb, norm_b, out, st, launch_count);
 }
 
 } // namespace vks

@@ -220,14 +220,11 @@ cudaError_t launch_unpack_aos(const uint8_t *aos, uint32_t n, FeatHead *heads, u
 struct MatchWorkspace;
 cudaError_t match_workspace_create(MatchWorkspace **ws, uint32_t max_feats);
 void match_workspace_destroy(MatchWorkspace *ws);
-/* matcher operands of n descriptors: |x|^2 per row and the binary16 operand blocks of the tensor-core kernel (match_tc.cuh);
- * `op` holds match_operand_bytes(n) bytes */
-size_t match_operand_bytes(uint32_t max_feats);
-cudaError_t launch_match_prepare(const uint8_t *desc, uint32_t n, uint32_t *norm, void *op, cudaStream_t st);
-/* norm_x / op_x: cached operands of a side (launch_match_prepare) or nullptr, in which case they are prepared into the workspace */
-cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *desc_a, uint32_t na, const uint32_t *norm_a, const void *op_a, const uint8_t *desc_b,
-                         uint32_t nb, const uint32_t *norm_b, const void *op_b, vksift_Match_2NN *out, cudaStream_t st, cudaEvent_t ev_after_prepare,
-                         uint64_t *launch_count);
+/* |x|^2 of n descriptors in both forms the matcher uses: plain (A side) and packed nbk (B side, padded to a multiple of 128 rows) */
+cudaError_t launch_norms(const uint8_t *desc, uint32_t n, uint32_t *out_plain, uint32_t *out_packed, cudaStream_t st);
+/* norm_a / norm_b: cached norms of the two sides (launch_norms) or nullptr, in which case they are computed into the workspace */
+cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *desc_a, uint32_t na, const uint32_t *norm_a, const uint8_t *desc_b, uint32_t nb,
+                         const uint32_t *norm_b, vksift_Match_2NN *out, cudaStream_t st, cudaEvent_t ev_after_prepare, uint64_t *launch_count);
 
 cudaError_t launch_match_filter(const vksift_Match_2NN *m12, uint32_t na, const vksift_Match_2NN *m21, uint32_t nb, float ratio, uint32_t *pairs,
                                 uint32_t capacity, uint32_t *count, cudaStream_t st);
