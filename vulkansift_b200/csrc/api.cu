@@ -69,10 +69,11 @@ struct Pyramid
 {
   uint32_t n_oct = 0;
   uint32_t w[VKS_MAX_OCT] = {0}, h[VKS_MAX_OCT] = {0}, pitch[VKS_MAX_OCT] = {0};
-  float *G[VKS_MAX_OCT] = {nullptr};
-  float *D[VKS_MAX_OCT] = {nullptr};
-  size_t alloc_floats_g[VKS_MAX_OCT] = {0};
-  size_t alloc_floats_d[VKS_MAX_OCT] = {0};
+  void *G[VKS_MAX_OCT] = {nullptr}; /* fp32 elements, or binary16 with VKSIFT_PYRAMID_PRECISION_FLOAT16 (sift_memory.c:139) */
+  void *D[VKS_MAX_OCT] = {nullptr};
+  size_t alloc_bytes_g[VKS_MAX_OCT] = {0};
+  size_t alloc_bytes_d[VKS_MAX_OCT] = {0};
+  int es = 4; /* bytes per element */
 };
 
 enum
@@ -314,26 +315,28 @@ bool alloc_pyramid(vksift_Instance inst)
 {
   Pyramid &p = inst->pyr;
   const size_t ns = inst->cfg.nb_scales_per_octave;
+  p.es = (inst->cfg.pyramid_precision_mode == VKSIFT_PYRAMID_PRECISION_FLOAT16) ? 2 : 4;
+  const uint32_t row_align = 128u / (uint32_t)p.es; /* rows start on 128-byte boundaries */
   for (uint32_t o = 0; o < p.n_oct; o++)
   {
-    p.pitch[o] = (p.w[o] + 31u) & ~31u;
-    const size_t layer = (size_t)p.pitch[o] * p.h[o];
+    p.pitch[o] = (p.w[o] + row_align - 1u) & ~(row_align - 1u);
+    const size_t layer = (size_t)p.pitch[o] * p.h[o] * (size_t)p.es;
     const size_t need_g = layer * (ns + 3), need_d = layer * (ns + 2);
-    if (need_g > p.alloc_floats_g[o])
+    if (need_g > p.alloc_bytes_g[o])
     {
       if (p.G[o])
         CU_TRY(cudaFree(p.G[o]));
       p.G[o] = nullptr;
-      CU_TRY(cudaMalloc(&p.G[o], need_g * sizeof(float)));
-      p.alloc_floats_g[o] = need_g;
+      CU_TRY(cudaMalloc(&p.G[o], need_g));
+      p.alloc_bytes_g[o] = need_g;
     }
-    if (need_d > p.alloc_floats_d[o])
+    if (need_d > p.alloc_bytes_d[o])
     {
       if (p.D[o])
         CU_TRY(cudaFree(p.D[o]));
       p.D[o] = nullptr;
-      CU_TRY(cudaMalloc(&p.D[o], need_d * sizeof(float)));
-      p.alloc_floats_d[o] = need_d;
+      CU_TRY(cudaMalloc(&p.D[o], need_d));
+      p.alloc_bytes_d[o] = need_d;
     }
   }
   return true;
@@ -348,11 +351,11 @@ bool build_blur_plan(vksift_Instance inst)
   auto make_pass = [&](uint32_t o, int s) {
     BlurPass bp;
     memset(&bp, 0, sizeof(bp));
-    const size_t layer = (size_t)p.pitch[o] * p.h[o];
+    const size_t layer = (size_t)p.pitch[o] * p.h[o] * (size_t)p.es; /* bytes */
     bp.w = (int)p.w[o];
     bp.h = (int)p.h[o];
     bp.dst_pitch = (int)p.pitch[o];
-    bp.dst_g = p.G[o] + layer * s;
+    bp.dst_g = (char *)p.G[o] + layer * s;
     if (s == 0)
     {
       bp.src = inst->d_src_slot; /* slot holding the address of the image (staging copy or caller's device buffer) */
@@ -364,10 +367,10 @@ bool build_blur_plan(vksift_Instance inst)
     }
     else
     {
-      bp.src = p.G[o] + layer * (s - 1);
+      bp.src = (const char *)p.G[o] + layer * (s - 1);
       bp.src_kind = BLUR_SRC_LAYER;
       bp.src_pitch = (int)p.pitch[o];
-      bp.dst_d = p.D[o] + layer * (s - 1);
+      bp.dst_d = (char *)p.D[o] + layer * (s - 1);
     }
     if (s == ns && o + 1 < p.n_oct)
     {
@@ -577,6 +580,7 @@ void fill_detect_params(vksift_Instance inst, const FeatureBuffer &fb, DetectPar
     P->oct[o].h = (int)p.h[o];
     P->oct[o].pitch = (int)p.pitch[o];
     P->oct[o].layer_stride = (int)(p.pitch[o] * p.h[o]);
+    P->oct[o].fp16 = (p.es == 2) ? 1 : 0;
     P->cap[o] = fb.cap[o];
     P->sec_off[o] = off;
     off += fb.cap[o];
@@ -1910,9 +1914,23 @@ extern "C"
     {
       DeviceGuard g(inst->device);
       wait_pipelines(inst, true, false);
-      const size_t layer = (size_t)p.pitch[octave] * p.h[octave];
-      const float *src = (dog ? p.D[octave] : p.G[octave]) + layer * scale;
+      const size_t layer = (size_t)p.pitch[octave] * p.h[octave] * (size_t)p.es;
+      const char *src = (const char *)(dog ? p.D[octave] : p.G[octave]) + layer * scale;
       auto run = [&]() -> bool {
+        if (p.es == 2)
+        {
+          /* binary16 layers are widened on the device (exact), the caller always receives floats (vulkansift.h:98-100) */
+          float *tmp = nullptr;
+          CU_TRY(cudaMalloc(&tmp, sizeof(float) * (size_t)p.w[octave] * p.h[octave]));
+          cudaError_t e = launch_widen_layer(src, (int)p.w[octave], (int)p.h[octave], (int)p.pitch[octave], tmp, inst->stream);
+          if (e == cudaSuccess)
+            e = cudaMemcpyAsync(out, tmp, sizeof(float) * (size_t)p.w[octave] * p.h[octave], cudaMemcpyDeviceToHost, inst->stream);
+          if (e == cudaSuccess)
+            e = cudaStreamSynchronize(inst->stream);
+          cudaFree(tmp);
+          CU_TRY(e);
+          return true;
+        }
         CU_TRY(cudaMemcpy2DAsync(out, sizeof(float) * p.w[octave], src, sizeof(float) * p.pitch[octave], sizeof(float) * p.w[octave], p.h[octave],
                                  cudaMemcpyDeviceToHost, inst->stream));
         CU_TRY(cudaStreamSynchronize(inst->stream));

@@ -14,15 +14,17 @@
  */
 #include "vksift_internal.h"
 
+#include "layer_io.cuh"
+
 namespace vks
 {
 
 /* imageLoad on the Gaussian array, out of bounds -> 0 (SURVEY B-D3) */
-__device__ __forceinline__ float gauss_at(const float *__restrict__ L, int w, int h, int pitch, int x, int y)
+__device__ __forceinline__ float gauss_at(const void *__restrict__ L, int fp16, int w, int h, int pitch, int x, int y)
 {
   if (x < 0 || x >= w || y < 0 || y >= h)
     return 0.f;
-  return __ldg(L + (size_t)y * pitch + x);
+  return layer_ld(L, (size_t)y * pitch + x, fp16);
 }
 
 /* ---- orientation --------------------------------------------------------- */
@@ -59,7 +61,8 @@ __global__ void __launch_bounds__(ORI_THREADS) orientation_kernel(const __grid_c
     const uint32_t slot = P.sec_off[o] + idx;
     const FeatHead kp = prim[slot];
     const OctaveView &ov = P.oct[o];
-    const float *__restrict__ L = ov.G + (size_t)kp.scale_idx * ov.layer_stride;
+    const void *__restrict__ L = layer_ptr(ov.G, (size_t)kp.scale_idx * ov.layer_stride, ov.fp16);
+    const int f16 = ov.fp16;
 
     const float sf = vks_pow2i(kp.octave_idx);
     const float lambda = 1.5f * (kp.sigma / sf);
@@ -106,8 +109,8 @@ __global__ void __launch_bounds__(ORI_THREADS) orientation_kernel(const __grid_c
       const float d2 = (sdx * sdx) + (sdy * sdy);
       if ((gx < 1 || gx >= (ov.w - 1) || gy < 1 || gy >= (ov.h - 1)) && (d2 > r2))
         continue;
-      const float gX = 0.5f * (gauss_at(L, ov.w, ov.h, ov.pitch, gx + 1, gy) - gauss_at(L, ov.w, ov.h, ov.pitch, gx - 1, gy));
-      const float gY = 0.5f * (gauss_at(L, ov.w, ov.h, ov.pitch, gx, gy + 1) - gauss_at(L, ov.w, ov.h, ov.pitch, gx, gy - 1));
+      const float gX = 0.5f * (gauss_at(L, f16, ov.w, ov.h, ov.pitch, gx + 1, gy) - gauss_at(L, f16, ov.w, ov.h, ov.pitch, gx - 1, gy));
+      const float gY = 0.5f * (gauss_at(L, f16, ov.w, ov.h, ov.pitch, gx, gy + 1) - gauss_at(L, f16, ov.w, ov.h, ov.pitch, gx, gy - 1));
       const float mag = vks_expf(d2 * es) * vks_sqrt((gX * gX) + (gY * gY));
       float th = vks_atan2f(gY, gX);
       if (th < 0.f)
@@ -340,7 +343,8 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
     FeatHead kp = prim[pi];
     kp.orientation = ori[(size_t)pi * P.ori_stride + k];
     const OctaveView &ov = P.oct[o];
-    const float *__restrict__ L = ov.G + (size_t)kp.scale_idx * ov.layer_stride;
+    const void *__restrict__ L = layer_ptr(ov.G, (size_t)kp.scale_idx * ov.layer_stride, ov.fp16);
+    const int f16 = ov.fp16;
 
     s_desc[tid] = 0;
     const float sf = vks_pow2i(kp.octave_idx);
@@ -412,8 +416,8 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
       if (hx < -1 || hx > 3 || hy < -1 || hy > 3)
         return;
       const int off = iy * pitch + ix; /* 32-bit index: a layer has fewer than 2^31 cells */
-      const float gX = 0.5f * (__ldg(L + (off + 1)) - __ldg(L + (off - 1)));
-      const float gY = 0.5f * (__ldg(L + (off + pitch)) - __ldg(L + (off - pitch)));
+      const float gX = 0.5f * (layer_ld(L, (size_t)(off + 1), f16) - layer_ld(L, (size_t)(off - 1), f16));
+      const float gY = 0.5f * (layer_ld(L, (size_t)(off + pitch), f16) - layer_ld(L, (size_t)(off - pitch), f16));
       float th = vks_atan2f(gY, gX);
       if (th < 0.f)
         th += VKS_TWO_PI_F;

@@ -27,6 +27,10 @@
  */
 #include "vksift_internal.h"
 
+#include <cstdio>
+#include <cstdlib>
+
+#include "layer_io.cuh"
 #include "tma_util.cuh"
 
 namespace vks
@@ -37,7 +41,7 @@ __device__ __forceinline__ float dog_at(const OctaveView &ov, int ns, int s, int
 {
   if (s < 0 || s >= ns + 2 || x < 0 || x >= ov.w || y < 0 || y >= ov.h)
     return 0.f;
-  return __ldg(ov.D + (size_t)s * ov.layer_stride + (size_t)y * ov.pitch + x);
+  return layer_ld(ov.D, (size_t)s * ov.layer_stride + (size_t)y * ov.pitch + x, ov.fp16);
 }
 
 /* ExtractKeypoints.comp:118-224 */
@@ -155,18 +159,25 @@ __device__ __forceinline__ bool extrema_tile_coords(const DetectParams &P, int t
   return false;
 }
 
-template <int EX_THREADS>
+__device__ __forceinline__ float ex_to_float(float v) { return v; }
+__device__ __forceinline__ float ex_to_float(__half v) { return __half2float(v); }
+
+/* T = element type of the DoG layers (float, or __half with VKSIFT_PYRAMID_PRECISION_FLOAT16): the tile is staged and compared in
+ * that type (binary16 comparisons order exactly like the fp32 values they convert to) */
+template <int EX_THREADS, class T>
 __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_constant__ DetectParams P, const __grid_constant__ ExtremaMaps maps, int t_begin,
                                                       int n_tiles, DetectCounters *__restrict__ cnt)
 {
   constexpr int EX_RPT = EX_TH / (EX_THREADS / 256); /* rows per thread */
-  extern __shared__ __align__(128) float ex_smem[];
+  constexpr int EX_HALO = 16 / (int)sizeof(T);       /* columns left of the tile in a staged row: a TMA box starts on a 16-byte boundary of the layer */
+  extern __shared__ __align__(128) unsigned char ex_smem_raw[];
+  T *const ex_smem = reinterpret_cast<T *>(ex_smem_raw);
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ int s_tile[2][4]; /* (octave, x0, y0) of the tile in each buffer: computed once by the thread that requests it */
   const int ns = P.ns, nl = P.ns + 2;
   const float prefilter = P.prefilter;
-  const uint32_t tile_bytes = (uint32_t)(nl * EX_SH * EX_SW) * 4u;
-  const int buf_floats = (nl * EX_SH * EX_SW + 31) & ~31; /* TMA destinations must be 128-byte aligned */
+  const uint32_t tile_bytes = (uint32_t)(nl * EX_SH * EX_SW) * (uint32_t)sizeof(T);
+  const int buf_floats = (nl * EX_SH * EX_SW + 63) & ~63; /* elements per buffer: TMA destinations must be 128-byte aligned */
   const int tid = threadIdx.x;
   const uint32_t bar0 = tma_smem_u32(&s_bar[0]);
 
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
       s_tile[0][2] = y0;
       tma_mbar_expect_tx(bar0, tile_bytes);
       for (int l = 0; l < nl; l++) /* one request per layer: the TMA unit pipelines independent requests */
-        tma_load_3d(tma_smem_u32(ex_smem + l * EX_SH * EX_SW), &maps.m[o], x0 - 4, y0 - 1, l, bar0);
+        tma_load_3d(tma_smem_u32(ex_smem + l * EX_SH * EX_SW), &maps.m[o], (x0 - EX_HALO) / (int)(4 / sizeof(T)), y0 - 1, l, bar0);
     }
   }
   __syncthreads();
@@ -206,13 +217,14 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
         tma_fence_proxy_async();
         tma_mbar_expect_tx(bar0 + 8 * (cur ^ 1), tile_bytes);
         for (int l = 0; l < nl; l++)
-          tma_load_3d(tma_smem_u32(ex_smem + (cur ^ 1) * buf_floats + l * EX_SH * EX_SW), &maps.m[on], xn - 4, yn - 1, l, bar0 + 8 * (cur ^ 1));
+          tma_load_3d(tma_smem_u32(ex_smem + (cur ^ 1) * buf_floats + l * EX_SH * EX_SW), &maps.m[on], (xn - EX_HALO) / (int)(4 / sizeof(T)), yn - 1, l,
+                      bar0 + 8 * (cur ^ 1));
       }
     }
     tma_mbar_wait(bar0 + 8 * cur, (uint32_t)(it >> 1) & 1u);
 
     const OctaveView &ov = P.oct[o];
-    const float *tile = ex_smem + cur * buf_floats;
+    const T *tile = ex_smem + cur * buf_floats;
     const int lx = tid & 255, ly = (tid >> 8) * EX_RPT; /* one column of EX_RPT rows per thread */
     const int x = x0 + lx;
     const int ow = ov.w, oh = ov.h;
@@ -223,28 +235,28 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
       const uint32_t row_ok = (r_hi > r_lo) ? (((1u << r_hi) - 1u) & ~((1u << r_lo) - 1u)) : 0u;
       for (int s = 1; s <= ns; s++)
       {
-        const float *col = tile + (s * EX_SH + ly + 1) * EX_SW + (lx + 4);
+        const T *col = tile + (s * EX_SH + ly + 1) * EX_SW + (lx + EX_HALO);
         /* prefilter all centre values first (independent loads), then visit only the survivors */
-        float cv[EX_RPT];
+        T cv[EX_RPT];
 #pragma unroll
         for (int r = 0; r < EX_RPT; r++)
           cv[r] = col[r * EX_SW];
         uint32_t mask = 0;
 #pragma unroll
         for (int r = 0; r < EX_RPT; r++)
-          mask |= (fabsf(cv[r]) > prefilter) ? (1u << r) : 0u;
+          mask |= (fabsf(ex_to_float(cv[r])) > prefilter) ? (1u << r) : 0u;
         mask &= row_ok;
         while (mask)
         {
           const int r = __ffs(mask) - 1;
           mask &= mask - 1;
-          const float *pc = col + r * EX_SW;
-          const float c = pc[0];
+          const T *pc = col + r * EX_SW;
+          const T c = pc[0];
           /* strict 26-neighbour test (:59-116), staged so that the many non-extrema leave after 4 compares */
           bool gt = true, lt = true;
 #define EX_CMP(off)                                                                                                                                  \
   {                                                                                                                                                  \
-    const float n = pc[off];                                                                                                                         \
+    const T n = pc[off];                                                                                                                             \
     gt = gt && (c > n);                                                                                                                              \
     lt = lt && (c < n);                                                                                                                              \
   }
@@ -486,9 +498,13 @@ cudaError_t extrema_plan_build(const DetectParams &P, ExtremaPlan **plan_io)
   {
     const OctaveView &ov = P.oct[o];
     const uint64_t dims[3] = {(uint64_t)ov.w, (uint64_t)ov.h, (uint64_t)(P.ns + 2)};
-    const uint64_t strides[2] = {(uint64_t)ov.pitch * 4, (uint64_t)ov.layer_stride * 4};
-    const uint32_t box[3] = {EX_SW, EX_SH, 1}; /* one layer per request */
-    if (!tma_make_map_f32(&pl->maps.m[o], ov.D, 3, dims, strides, box))
+    /* binary16 layers are described to the TMA unit as fp32 tensors of half the width (a pair of halves = one 32-bit element;
+     * tile origins are even): same box bytes, same zero fill outside the image */
+    const uint64_t es = ov.fp16 ? 2 : 4;
+    const uint64_t strides[2] = {(uint64_t)ov.pitch * es, (uint64_t)ov.layer_stride * es};
+    const uint32_t box[3] = {(uint32_t)(ov.fp16 ? EX_SW / 2 : EX_SW), EX_SH, 1}; /* one layer per request */
+    const uint64_t dims32[3] = {(uint64_t)(ov.fp16 ? (ov.w + 1) / 2 : ov.w), dims[1], dims[2]};
+    if (!tma_make_map_f32(&pl->maps.m[o], ov.D, 3, dims32, strides, box))
       return cudaErrorInvalidValue;
     pl->n_tiles += ((ov.w + EX_TW - 1) / EX_TW) * ((ov.h + EX_TH - 1) / EX_TH);
   }
@@ -537,7 +553,8 @@ cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectC
       t_begin += n;
     t_end += n;
   }
-  const size_t smem = 2 * sizeof(float) * (size_t)((((P.ns + 2) * EX_SH * EX_SW) + 31) & ~31);
+  const bool fp16 = P.oct[P.ob].fp16 != 0;
+  const size_t smem = 2 * (fp16 ? sizeof(__half) : sizeof(float)) * (size_t)((((P.ns + 2) * EX_SH * EX_SW) + 63) & ~63);
   if (smem > 220 * 1024)
     return cudaErrorInvalidConfiguration; /* rejected at instance creation (extrema_scales_supported) */
   static bool attr_done[64] = {false};
@@ -551,9 +568,13 @@ cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectC
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_done[dev])
   {
-    cudaError_t e = cudaFuncSetAttribute(extrema_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(extrema_kernel<256, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(extrema_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      e = cudaFuncSetAttribute(extrema_kernel<512, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(extrema_kernel<256, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(extrema_kernel<512, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess)
       return e;
     attr_done[dev] = true;
@@ -563,10 +584,14 @@ cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectC
   int grid = sms * (per_sm > 2 ? 2 : per_sm);
   if (grid > t_end - t_begin)
     grid = t_end - t_begin;
-  if (threads == 256)
-    extrema_kernel<256><<<grid, 256, smem, st>>>(P, pl->maps, t_begin, t_end, cnt);
+  if (threads == 256 && fp16)
+    extrema_kernel<256, __half><<<grid, 256, smem, st>>>(P, pl->maps, t_begin, t_end, cnt);
+  else if (threads == 256)
+    extrema_kernel<256, float><<<grid, 256, smem, st>>>(P, pl->maps, t_begin, t_end, cnt);
+  else if (fp16)
+    extrema_kernel<512, __half><<<grid, 512, smem, st>>>(P, pl->maps, t_begin, t_end, cnt);
   else
-    extrema_kernel<512><<<grid, 512, smem, st>>>(P, pl->maps, t_begin, t_end, cnt);
+    extrema_kernel<512, float><<<grid, 512, smem, st>>>(P, pl->maps, t_begin, t_end, cnt);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;

@@ -20,6 +20,7 @@
 #include "vksift_internal.h"
 #include "tma_util.cuh"
 #include "blur_arith.cuh"
+#include "layer_io.cuh"
 
 #include <cuda_fp16.h>
 
@@ -79,7 +80,7 @@ __device__ __forceinline__ float fetch_src(const BlurPass &p, int x, int y)
   x = vks_mirror(x, p.w);
   y = vks_mirror(y, p.h);
   if (p.src_kind == BLUR_SRC_LAYER)
-    return ((const float *)p.src)[(size_t)y * p.src_pitch + x];
+    return layer_ld(p.src, (size_t)y * p.src_pitch + x, p.fp16);
   if (p.src_kind == BLUR_SRC_U8_UP2)
     return fetch_u8_up2(*(const uint8_t *const *)p.src, p.src_w, p.src_h, x, y);
   return vks_unorm8((*(const uint8_t *const *)p.src)[(size_t)y * p.src_w + x]);
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) blur_step_small_kernel(const __grid_const
   if (p.src_kind == BLUR_SRC_LAYER)
   {
     const bool once = (x0 - R >= -p.w) && (x0 + SB_W + R <= 2 * p.w) && (y0 - R >= -p.h) && (y0 + SB_H + R <= 2 * p.h);
-    const float *__restrict__ src = (const float *)p.src;
+    const void *__restrict__ src = p.src;
     for (int i0 = tid; i0 < n_el; i0 += 8 * 256)
     {
       float v[8];
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256) blur_step_small_kernel(const __grid_const
           int gx = x0 - R + c, gy = y0 - R + m;
           gx = once ? mirror_once(gx, p.w) : vks_mirror(gx, p.w);
           gy = once ? mirror_once(gy, p.h) : vks_mirror(gy, p.h);
-          v[k] = __ldg(src + (size_t)gy * p.src_pitch + gx);
+          v[k] = layer_ld(src, (size_t)gy * p.src_pitch + gx, p.fp16);
         }
       }
 #pragma unroll
@@ -184,17 +185,14 @@ __global__ void __launch_bounds__(256) blur_step_small_kernel(const __grid_const
       acc = vks_blur_tap(acc, col[k * SB_W], col[-k * SB_W], p.taps[k]);
     if (p.fp16)
       acc = __half2float(__float2half_rn(acc));
-    p.dst_g[(size_t)y * p.dst_pitch + x] = acc;
+    layer_st(p.dst_g, (size_t)y * p.dst_pitch + x, acc, p.fp16);
     if (p.dst_d)
-    {
-      const float d = vks_sub(acc, s_in[(yy + R) * in_w + xx + R]);
-      p.dst_d[(size_t)y * p.dst_pitch + x] = p.fp16 ? __half2float(__float2half_rn(d)) : d;
-    }
+      layer_st(p.dst_d, (size_t)y * p.dst_pitch + x, vks_sub(acc, s_in[(yy + R) * in_w + xx + R]), p.fp16);
     if (p.dst_next && (x & 1) && (y & 1))
     {
       const int nx = x >> 1, ny = y >> 1;
       if (nx < p.next_w && ny < p.next_h)
-        p.dst_next[(size_t)ny * p.next_pitch + nx] = acc;
+        layer_st(p.dst_next, (size_t)ny * p.next_pitch + nx, acc, p.fp16);
     }
   }
 }
@@ -266,7 +264,7 @@ struct BlurPassFast
 /* One 64x128 tile of one layer.  The TMA barriers at the end of the shared memory block are initialised by the
  * caller; `parity` is the phase they complete next (a persistent caller flips it for every float-source tile).
  * `taps2` must point into the kernel parameters at a compile-time offset (constant operands). */
-template <int R, int KIND, int TH, int BAR_OFF>
+template <int R, int KIND, int TH, int BAR_OFF, bool H16>
 __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *tmap, const float2 *__restrict__ taps2, float *ft_smem, int x0, int y0,
                                           uint32_t parity, bool pdl)
 {
@@ -289,7 +287,44 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
   int bands_seen = FT_NB;                      /* TMA bands this thread has already waited for */
 
   /* ---- stage 1: source tile -> smem ---- */
-  if (KIND != FT_KIND_SEED)
+  if (KIND != FT_KIND_SEED && H16)
+  {
+    /* binary16 layers: the tile is fetched with vectorised half2 loads (the pair of a column pair is 4-byte aligned: tile
+     * origin and pitch are even) and widened to the fp32 tile the passes work on; MIRRORED_REPEAT resolved on the way */
+    if (pdl)
+      pdl_wait();
+    const __half *__restrict__ src = reinterpret_cast<const __half *>(p.src);
+    const bool once = (x0 - RX >= -p.w) && (x0 - RX + S <= 2 * p.w) && (y0 - R >= -p.h) && (y0 + TH + R <= 2 * p.h);
+    /* one warp per tile row, a lane per group of four columns: one 8-byte load (four halves; tile origin, pitch and group are
+     * multiples of four elements), groups that touch the image border go element by element through the mirror */
+    for (int r = wi; r < rows_in; r += FT_THREADS / 32)
+    {
+      const int gy = once ? mirror_once(y0 - R + r, p.h) : vks_mirror(y0 - R + r, p.h);
+      const __half *row = src + (size_t)gy * p.src_pitch;
+      for (int c = 4 * lane; c < S; c += 128)
+      {
+        const int gx = x0 - RX + c;
+        float4 v;
+        if (gx >= 0 && gx + 3 < p.w)
+        {
+          const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(row + gx));
+          const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+          v = make_float4(a.x, a.y, b.x, b.y);
+        }
+        else
+        {
+          float e[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            e[k] = __half2float(__ldg(row + (once ? mirror_once(gx + k, p.w) : vks_mirror(gx + k, p.w))));
+          v = make_float4(e[0], e[1], e[2], e[3]);
+        }
+        *reinterpret_cast<float4 *>(s_in + r * S + c) = v;
+      }
+    }
+    __syncthreads();
+  }
+  else if (KIND != FT_KIND_SEED)
   {
     if (tid == 0)
     {
@@ -552,7 +587,6 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
     uint32_t off = ((uint32_t)yb * (uint32_t)p.dst_pitch + (uint32_t)x) * 4u;
     uint32_t noff = ((uint32_t)(yb >> 1) * (uint32_t)p.next_pitch + (uint32_t)(x >> 1)) * 4u;
     const uint32_t pitch4 = (uint32_t)p.dst_pitch * 4u, npitch4 = (uint32_t)p.next_pitch * 4u;
-    const bool fp16 = p.fp16 != 0;
     pk2 wv[VR + 2 * R];
 #pragma unroll
     for (int j = 0; j < 2 * R; j++)
@@ -580,14 +614,30 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
         const int q = qb + j;
         if (q < nrows)
         {
-          if (fp16)
-            acc[j] = round_half2(acc[j]);
+          if (H16)
+          {
+            /* binary16 layers: one rounding to nearest even, the rounded value is what the DoG is taken from (it is what
+             * the layer holds), half2 stores */
+            const __half2 hg = __floats2half2_rn(pk_lo(acc[j]), pk_hi(acc[j]));
+            *reinterpret_cast<__half2 *>(gbase + (off >> 1)) = hg;
+            const float2 fg = __half22float2(hg);
+            if (KIND != FT_KIND_SEED)
+            {
+              const pk2 d = pk_sub(pk_make(fg.x, fg.y), *(const pk2 *)(ccol + q * S));
+              __stcs(reinterpret_cast<__half2 *>(dbase + (off >> 1)), __floats2half2_rn(pk_lo(d), pk_hi(d)));
+            }
+            if (KIND == FT_KIND_NEXT && (q & 1))
+            {
+              *reinterpret_cast<__half *>(nbase + (noff >> 1)) = __high2half(hg);
+              noff += npitch4;
+            }
+          }
+          else
+          {
           *(pk2 *)(gbase + off) = acc[j];
           if (KIND != FT_KIND_SEED)
           {
             pk2 d = pk_sub(acc[j], *(const pk2 *)(ccol + q * S));
-            if (fp16)
-              d = round_half2(d);
             __stcs((pk2 *)(dbase + off), d); /* streaming: the DoG layer is not read before the extrema scan, the L2 lines are better spent on G, which the next layer's launch reads back */
           }
           if (KIND == FT_KIND_NEXT && (q & 1))
@@ -595,6 +645,7 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
             /* x even, y odd: the odd column of the pair feeds next(x>>1, y>>1) */
             *(float *)(nbase + noff) = pk_hi(acc[j]);
             noff += npitch4;
+          }
           }
         }
         off += pitch4;
@@ -614,19 +665,16 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
       float acc = vks_mul(mc[0], taps2[0].x);
       for (int i = 1; i <= R; i++)
         acc = vks_blur_tap(acc, mc[i * FT_MS], mc[-i * FT_MS], taps2[i].x);
-      if (p.fp16)
+      if (H16)
         acc = round_half1(acc);
-      p.dst_g[(size_t)y * p.dst_pitch + x] = acc;
+      layer_st(p.dst_g, (size_t)y * p.dst_pitch + x, acc, H16);
       if (KIND != FT_KIND_SEED)
-      {
-        const float d = vks_sub(acc, s_in[(R + ry + q) * S + RX + col]);
-        p.dst_d[(size_t)y * p.dst_pitch + x] = p.fp16 ? round_half1(d) : d;
-      }
+        layer_st(p.dst_d, (size_t)y * p.dst_pitch + x, vks_sub(acc, s_in[(R + ry + q) * S + RX + col]), H16);
       if (KIND == FT_KIND_NEXT && (x & 1) && (y & 1))
       {
         const int nx = x >> 1, ny = y >> 1;
         if (nx < p.next_w && ny < p.next_h)
-          p.dst_next[(size_t)ny * p.next_pitch + nx] = acc;
+          layer_st(p.dst_next, (size_t)ny * p.next_pitch + nx, acc, H16);
       }
     }
   }
@@ -635,7 +683,7 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
 /* one launch = one pass (one Gaussian layer): every parameter sits at a fixed constant-bank address, the
  * taps are constant operands of the FFMA2s.  Passes that are independent (different octaves) run
  * concurrently from different streams; the block scheduler fills the tail of one with the head of another. */
-template <int R, int KIND>
+template <int R, int KIND, bool H16>
 __global__ void __launch_bounds__(FT_THREADS, ft_ctas_per_sm(R)) blur_pass_fast_kernel(const __grid_constant__ BlurPassFast P)
 {
   extern __shared__ __align__(128) float ft_smem[];
@@ -654,7 +702,7 @@ __global__ void __launch_bounds__(FT_THREADS, ft_ctas_per_sm(R)) blur_pass_fast_
   const int t = (int)blockIdx.x;
   const int x0 = (t % P.p.tiles_x) * FT_W;
   const int y0 = (t / P.p.tiles_x) * TH;
-  blur_tile<R, KIND, TH, BAR_OFF>(P.p, &P.p.tmap, P.taps2, ft_smem, x0, y0, 0u, true);
+  blur_tile<R, KIND, TH, BAR_OFF, H16>(P.p, &P.p.tmap, P.taps2, ft_smem, x0, y0, 0u, true);
 }
 
 /* ==========================================================================
@@ -723,12 +771,12 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) octave_fused_kernel(const __gri
     for (int rr = wi; rr < n; rr += FZ_THREADS / 32)
     {
       const int gy = once ? mirror_once(y0 - halo + rr, P.h) : vks_mirror(y0 - halo + rr, P.h);
-      const float *row = P.src + (size_t)gy * P.pitch;
+      const size_t row = (size_t)gy * P.pitch;
       float *dst = cur + rr * FZ_WB + lane;
 #pragma unroll
       for (int j = 0; j < 3; j++)
         if (lane + 32 * j < n)
-          dst[32 * j] = __ldg(row + gxs[j]);
+          dst[32 * j] = layer_ld(P.src, row + gxs[j], P.fp16);
     }
   }
   __syncthreads();
@@ -758,8 +806,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) octave_fused_kernel(const __gri
     FZ_MARK();
     /* vertical over [lo+R, lo+R+n)^2, plus the global stores of the pixels that lie in the tile core and in the image */
     {
-      float *gl = P.g0 + (size_t)k * P.layer_stride;
-      float *dl = P.d0 + (size_t)k * P.layer_stride;
+      const size_t lofs = (size_t)k * P.layer_stride; /* elements */
       const bool is_next = (k == P.next_k);
 #pragma unroll 1
       for (int r = lo + R + wi; r < lo + R + n; r += FZ_THREADS / 32)
@@ -780,15 +827,14 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) octave_fused_kernel(const __gri
           const int gx = x0 - halo + c;
           if (row_ok && c >= halo && c < halo + FZ_T && gx < P.w)
           {
-            const size_t o = (size_t)gy * P.pitch + gx;
-            gl[o] = acc;
-            const float dd = vks_sub(acc, cur[r * FZ_WB + c]);
-            dl[o] = P.fp16 ? round_half1(dd) : dd;
+            const size_t o = lofs + (size_t)gy * P.pitch + gx;
+            layer_st(P.g0, o, acc, P.fp16);
+            layer_st(P.d0, o, vks_sub(acc, cur[r * FZ_WB + c]), P.fp16);
             if (is_next && (gx & 1) && (gy & 1))
             {
               const int nx = gx >> 1, ny = gy >> 1;
               if (nx < P.next_w && ny < P.next_h)
-                P.dst_next[(size_t)ny * P.next_pitch + nx] = acc;
+                layer_st(P.dst_next, (size_t)ny * P.next_pitch + nx, acc, P.fp16);
             }
           }
         }
@@ -844,7 +890,7 @@ bool fused_plan_octave(const BlurPass *passes, int n_pass, std::vector<FusedLaun
     const BlurPass &first = passes[i];
     if (first.src_kind != BLUR_SRC_LAYER)
       return false;
-    F.src = (const float *)first.src;
+    F.src = first.src;
     F.g0 = first.dst_g;
     F.d0 = first.dst_d;
     F.w = first.w;
@@ -864,7 +910,7 @@ bool fused_plan_octave(const BlurPass *passes, int n_pass, std::vector<FusedLaun
         break;
       const int k = F.n_layers;
       if (k == 1)
-        F.layer_stride = (int)(bp.dst_g - F.g0);
+        F.layer_stride = (int)(((const char *)bp.dst_g - (const char *)F.g0) / (first.fp16 ? 2 : 4));
       F.radius[k] = re;
       for (int j = 0; j < 14; j++)
       {
@@ -940,9 +986,10 @@ bool blur_pass_prepare_fast(BlurPass *bpp)
   bp.tiles_x = (bp.w + FT_W - 1) / FT_W;
   bp.tiles_y = (bp.h + bp.tile_h - 1) / bp.tile_h;
   bp.tile_begin = 0;
-  if (bp.src_kind == BLUR_SRC_LAYER)
+  if (bp.src_kind == BLUR_SRC_LAYER && !bp.fp16)
   {
-    /* one TMA box = source tile + halo; cells outside the layer read as zero and are patched by the kernel */
+    /* one TMA box = source tile + halo; cells outside the layer read as zero and are patched by the kernel
+     * (binary16 layers are fetched with half2 loads instead) */
     const int re = ft_even(bp.radius);
     const uint64_t dims[2] = {(uint64_t)bp.w, (uint64_t)bp.h};
     const uint64_t strides[1] = {(uint64_t)bp.src_pitch * 4};
@@ -953,8 +1000,8 @@ bool blur_pass_prepare_fast(BlurPass *bpp)
   return true;
 }
 
-template <int R, int KIND>
-static cudaError_t launch_fast_rk(const BlurPassFast &F, int n_tiles, cudaStream_t st)
+template <int R, int KIND, bool H16>
+static cudaError_t launch_fast_rkh(const BlurPassFast &F, int n_tiles, cudaStream_t st)
 {
   static bool attr_done[64] = {false};
   int dev = 0;
@@ -962,12 +1009,18 @@ static cudaError_t launch_fast_rk(const BlurPassFast &F, int n_tiles, cudaStream
   if (dev < 64 && !attr_done[dev])
   {
     cudaError_t e =
-        cudaFuncSetAttribute(blur_pass_fast_kernel<R, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes(R, ft_tile_h(R)));
+        cudaFuncSetAttribute(blur_pass_fast_kernel<R, KIND, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes(R, ft_tile_h(R)));
     if (e != cudaSuccess)
       return e;
     attr_done[dev] = true;
   }
-  return launch_pdl(blur_pass_fast_kernel<R, KIND>, n_tiles, FT_THREADS, ft_smem_bytes(R, ft_tile_h(R)), st, F);
+  return launch_pdl(blur_pass_fast_kernel<R, KIND, H16>, n_tiles, FT_THREADS, ft_smem_bytes(R, ft_tile_h(R)), st, F);
+}
+
+template <int R, int KIND>
+static cudaError_t launch_fast_rk(const BlurPassFast &F, int n_tiles, cudaStream_t st)
+{
+  return F.p.fp16 ? launch_fast_rkh<R, KIND, true>(F, n_tiles, st) : launch_fast_rkh<R, KIND, false>(F, n_tiles, st);
 }
 
 template <int R>
@@ -1005,6 +1058,20 @@ cudaError_t launch_blur_pass_fast(const BlurPass &bp, cudaStream_t st)
   default:
     return launch_fast_r<12>(F, n_tiles, st);
   }
+}
+
+/* binary16 layer -> dense fp32 image (vksift_downloadScaleSpaceImage / vksift_downloadDoGImage with VKSIFT_PYRAMID_PRECISION_FLOAT16) */
+__global__ void widen_layer_kernel(const __half *__restrict__ src, int w, int h, int pitch, float *__restrict__ dst)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x < w && y < h)
+    dst[(size_t)y * w + x] = __half2float(src[(size_t)y * pitch + x]);
+}
+
+cudaError_t launch_widen_layer(const void *src, int w, int h, int pitch, float *dst, cudaStream_t st)
+{
+  widen_layer_kernel<<<dim3((w + 255) / 256, h, 1), 256, 0, st>>>((const __half *)src, w, h, pitch, dst);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_blur_step(const BlurStep &step, cudaStream_t st)

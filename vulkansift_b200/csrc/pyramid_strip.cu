@@ -555,7 +555,7 @@ bool strip_plan(const BlurPass *passes, int n, StripLaunch *out)
   const BlurPass &first = passes[0];
   /* large octaves only: a CTA walks its segment row block by row block (about a microsecond per step), which only pays when
    * the octave fills the GPU with strips x segments; smaller octaves keep the per-layer launches */
-  if (first.w < 1024 || first.h < 256)
+  if (first.w < 1024 || first.h < 256 || first.fp16) /* binary16 layers: per-layer launches */
     return false;
   memset(out, 0, sizeof(*out));
   StripParams &P = *reinterpret_cast<StripParams *>(out->params);
@@ -573,8 +573,8 @@ bool strip_plan(const BlurPass *passes, int n, StripLaunch *out)
       return false;
     if (passes[k].dst_next && k != n - 1)
       return false;
-    P.g[k] = passes[k].dst_g;
-    P.d[k] = passes[k].dst_d;
+    P.g[k] = (float *)passes[k].dst_g;
+    P.d[k] = (float *)passes[k].dst_d;
     for (int j = 0; j < 14; j++)
     {
       const float v = (j <= passes[k].radius) ? passes[k].taps[j] : 0.f;
@@ -582,7 +582,7 @@ bool strip_plan(const BlurPass *passes, int n, StripLaunch *out)
     }
   }
   const BlurPass &last = passes[n - 1];
-  P.next = last.dst_next;
+  P.next = (float *)last.dst_next;
   P.next_w = last.next_w;
   P.next_h = last.next_h;
   P.next_pitch = last.next_pitch;

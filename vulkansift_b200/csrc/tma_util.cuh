@@ -30,9 +30,9 @@ static inline PFN_encodeTiled tma_encoder()
   return fn;
 }
 
-/* fp32 tensor of up to 3 dims (x fastest), no swizzle, out-of-bounds elements read as zero */
-static inline bool tma_make_map_f32(CUtensorMap *map, const float *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                                    const uint32_t *box)
+/* fp32 (or, with fp16 = true, binary16) tensor of up to 3 dims (x fastest), no swizzle, out-of-bounds elements read as zero */
+static inline bool tma_make_map_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+                                    const uint32_t *box, bool fp16 = false)
 {
   PFN_encodeTiled enc = tma_encoder();
   if (!enc)
@@ -48,7 +48,8 @@ static inline bool tma_make_map_f32(CUtensorMap *map, const float *base, int ran
     if (i > 0)
       gstr[i - 1] = strides_bytes[i - 1];
   }
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void *)base, gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return enc(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void *)base, gdim, gstr, bx, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

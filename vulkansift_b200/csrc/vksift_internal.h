@@ -48,14 +48,16 @@ struct FeatHead
 };
 static_assert(sizeof(FeatHead) == 36, "FeatHead layout");
 
-/* one octave of the scale space in HBM: (ns+3) Gaussian and (ns+2) DoG layers,
- * rows padded to `pitch` floats (multiple of 32 -> 128-byte aligned rows) */
+/* one octave of the scale space in HBM: (ns+3) Gaussian and (ns+2) DoG layers of fp32 values, or of binary16 values with
+ * VKSIFT_PYRAMID_PRECISION_FLOAT16 (the reference allocates VK_FORMAT_R16_SFLOAT images then, sift_memory.c:139); rows padded to
+ * `pitch` elements (a multiple of 128 bytes).  Kernels read and write layers through layer_ld / layer_st (layer_io.cuh). */
 struct OctaveView
 {
-  float *G;
-  float *D;
+  void *G;
+  void *D;
   int w, h, pitch;
-  int layer_stride; /* floats between layers = pitch*h */
+  int layer_stride; /* elements between layers = pitch*h */
+  int fp16;         /* element type: 0 float, 1 __half */
 };
 
 struct DetectParams
@@ -106,17 +108,18 @@ enum BlurSrcKind
 
 struct BlurPass
 {
-  const void *src; /* float layer, or (u8 kinds) the address of a device slot holding the image pointer: the launch
-                      sequence is captured in a CUDA graph once and replayed for every image */
-  float *dst_g;    /* Gaussian layer written */
-  float *dst_d;    /* DoG layer (dst_g - src) or NULL */
-  float *dst_next; /* next octave layer 0 (NEAREST blit of this layer) or NULL */
+  const void *src; /* layer (float or __half elements, see fp16), or (u8 kinds) the address of a device slot holding the image
+                      pointer: the launch sequence is captured in a CUDA graph once and replayed for every image */
+  void *dst_g;     /* Gaussian layer written */
+  void *dst_d;     /* DoG layer (dst_g - src) or NULL */
+  void *dst_next;  /* next octave layer 0 (NEAREST blit of this layer) or NULL */
   int w, h;        /* layer size */
   int src_pitch, dst_pitch, next_pitch;
   int src_w, src_h; /* u8 input size for the seed pass */
   int next_w, next_h;
   int src_kind;
-  int fp16; /* VKSIFT_PYRAMID_PRECISION_FLOAT16: every layer value is rounded through binary16 when it is stored (SURVEY B-D11) */
+  int fp16; /* VKSIFT_PYRAMID_PRECISION_FLOAT16: layers hold binary16 elements; arithmetic stays fp32, a value is rounded to nearest
+               even when it is stored (SURVEY B-D11) */
   int radius;
   int tiles_x, tiles_y, tile_begin; /* CTA range of this pass inside the launch */
   int tile_h;                       /* output rows per tile chosen for this pass */
@@ -135,16 +138,16 @@ struct BlurStep
 #define FZ_MAXL 3
 struct FusedLaunch
 {
-  const float *src; /* layer s_begin-1 of the octave */
-  float *g0;        /* Gaussian layer s_begin */
-  float *d0;        /* DoG layer s_begin-1 */
-  int layer_stride; /* floats between consecutive layers */
+  const void *src;  /* layer s_begin-1 of the octave */
+  void *g0;         /* Gaussian layer s_begin */
+  void *d0;         /* DoG layer s_begin-1 */
+  int layer_stride; /* elements between consecutive layers */
   int w, h, pitch;
   int n_layers;
   int fp16;
   int radius[FZ_MAXL]; /* rounded up to even, taps zero padded */
   int next_k;          /* layer (0-based inside the launch) whose NEAREST decimation seeds the next octave, or -1 */
-  float *dst_next;
+  void *dst_next;
   int next_w, next_h, next_pitch;
   int tiles_x;
   float2 taps2[FZ_MAXL][14];
@@ -189,6 +192,7 @@ bool blur_pass_is_fast(const BlurPass &bp);
 bool blur_pass_prepare_fast(BlurPass *bp);
 cudaError_t launch_blur_pass_fast(const BlurPass &bp, cudaStream_t st);
 cudaError_t launch_blur_step(const BlurStep &step, cudaStream_t st);
+cudaError_t launch_widen_layer(const void *src, int w, int h, int pitch, float *dst, cudaStream_t st);
 /* groups consecutive layer passes of one octave into fused launches; false when a pass cannot be fused */
 bool fused_plan_octave(const BlurPass *passes, int n_pass, std::vector<FusedLaunch> *out);
 cudaError_t launch_fused(const FusedLaunch &F, cudaStream_t st);
