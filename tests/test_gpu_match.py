@@ -230,3 +230,26 @@ def test_match_against_blocks_batched_equals_oracle(api, oracle_mod):
         inst.upload_features(_feats(api, host[0]), 1)
         inst.match(0, 1)
         _check(inst.download_matches(), oracle_mod.match_descriptors(da, host[0]), "plain match afterwards")
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+def test_large_distances_follow_the_float_comparison(api, oracle_mod, impl):
+    """Beyond d^2 = 2^22 distinct squared distances round to the same float sqrt and the shader's strict '<' on floats keeps the
+    earlier scan position (Get2NearestNeighbors.comp:82-96).  Byte descriptors far apart (not SIFT descriptors: |a - b| >= 2048)
+    with squared distances that differ by one in that range must come out like the oracle, which compares floats."""
+    rng = np.random.default_rng(9)
+    na, nb = 40, 300
+    # d^2 = 73 * 255^2 + 68^2 + (v_a - v_b)^2 with v in {0, 1}: 4751449 and 4751450 have the same float square root (2179.782)
+    da = np.zeros((na, 128), np.uint8)
+    da[:, 127] = rng.integers(0, 2, na)
+    db = np.zeros((nb, 128), np.uint8)
+    db[:, :73] = 255
+    db[:, 73] = 68
+    db[:, 127] = rng.integers(0, 2, nb)
+    assert np.sqrt(np.float32(4751449)) == np.sqrt(np.float32(4751450))
+    exp = oracle_mod.match_descriptors(da, db)
+    sq = exp["dist_a_b2"].astype(np.float64) ** 2
+    assert sq.min() >= 2 ** 22
+    with api.Instance(max_nb_sift_per_buffer=1024) as inst:
+        got = _match(api, inst, da, db, impl)
+    _check(got, exp, "large distances impl %d" % impl)

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(EX_THREADS) extrema_kernel(const __grid_consta
 
 /* ---- ordered compaction ------------------------------------------------------------------------------------------ */
 #define RF_THREADS 64 /* small CTAs: most of a refinement is waiting for one lane's dependent loads */
-#define RF_CTAS 96    /* per octave */
+#define RF_CTAS 256   /* per octave: 16 k threads, one queued extremum each for all but pathological images */
 #define RQ_ACCEPTED (1ull << 63)
 
 /* strict extremum test straight from global memory: the slow path's twin of the shared-memory test in extrema_kernel */

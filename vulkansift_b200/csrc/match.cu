@@ -9,7 +9,9 @@
  * :69-96) == stable top-2 of B under the key (d, pos) with pos(0)=1, pos(1)=0,
  * pos(b)=b.  Distances are compared as squared integers, which orders exactly
  * like the shader's float sqrt while d^2 < 2^22 (|a-b| < 2048; SIFT descriptors
- * have |a-b|^2 <= 2*512^2 < 2^20).
+ * have |a-b|^2 <= 2*512^2 < 2^20); rows whose second neighbour lies beyond that are
+ * rescanned under the float key (match_merge_kernel), so the result is the shader's
+ * for any byte descriptors.
  */
 #include "vksift_internal.h"
 
@@ -98,7 +100,8 @@ __global__ void __launch_bounds__(MS_ROWS) match_simt_kernel(const uint8_t *__re
       for (int i = 0; i < 32; i++)
         dot = __dp4a(a[i], s_b[j][i], dot);
       const uint32_t d2 = my_na + s_nb[j] - 2u * dot;
-      top2_insert(((unsigned long long)d2 << 32) | match_pos(b0 + j), k1, k2);
+      /* key = (bits of sqrt(float(d^2)), pos): the shader's comparison, exact for every d^2 (non-negative floats order like their bits) */
+      top2_insert(((unsigned long long)__float_as_uint(vks_sqrt((float)d2)) << 32) | match_pos(b0 + j), k1, k2);
     }
     __syncthreads();
   }
@@ -108,8 +111,8 @@ __global__ void __launch_bounds__(MS_ROWS) match_simt_kernel(const uint8_t *__re
     m.idx_a = row;
     m.idx_b1 = match_pos((uint32_t)k1);
     m.idx_b2 = match_pos((uint32_t)k2);
-    m.dist_a_b1 = vks_sqrt((float)(uint32_t)(k1 >> 32));
-    m.dist_a_b2 = vks_sqrt((float)(uint32_t)(k2 >> 32));
+    m.dist_a_b1 = __uint_as_float((uint32_t)(k1 >> 32));
+    m.dist_a_b2 = __uint_as_float((uint32_t)(k2 >> 32));
     out[row] = m;
   }
 }

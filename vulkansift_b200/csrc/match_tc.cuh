@@ -484,6 +484,61 @@ __global__ void __launch_bounds__(32 * MG_WARPS) match_merge_kernel(const unsign
     if (cand < second)
       second = cand;
   }
+  /* The shader compares the float distances sqrt(float(d^2)) with a strict '<' (Get2NearestNeighbors.comp:82-96).  Below 2^22 the
+   * square root is injective on the integers, so the integer order above IS the shader's order.  From 2^22 on (only reachable
+   * with descriptors that are not SIFT descriptors: |a - b| >= 2048) distinct d^2 can round to the same float and the earlier
+   * scan position wins there: such a row is rescanned completely under the key (bits of sqrt(float(d^2)), pos). */
+  if ((uint32_t)(second >> 32) >= (1u << 22) && second != ~0ull)
+  {
+    uint4 fa[8];
+    {
+      const uint4 *pa = reinterpret_cast<const uint4 *>(da + (size_t)row * 128);
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        fa[i] = __ldg(pa + i);
+    }
+    unsigned long long s1 = ~0ull, s2 = ~0ull;
+    for (uint32_t b = (uint32_t)lane; b < nb; b += 32)
+    {
+      const uint4 *pb = reinterpret_cast<const uint4 *>(db + (size_t)b * 128);
+      uint32_t dot = 0, nbv = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+      {
+        const uint4 vb = __ldg(pb + i);
+        dot = __dp4a(fa[i].x, vb.x, dot);
+        dot = __dp4a(fa[i].y, vb.y, dot);
+        dot = __dp4a(fa[i].z, vb.z, dot);
+        dot = __dp4a(fa[i].w, vb.w, dot);
+        nbv = __dp4a(vb.x, vb.x, nbv);
+        nbv = __dp4a(vb.y, vb.y, nbv);
+        nbv = __dp4a(vb.z, vb.z, nbv);
+        nbv = __dp4a(vb.w, vb.w, nbv);
+      }
+      const float d = vks_sqrt((float)(my_na + nbv - 2u * dot));
+      const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | mt_pos(b);
+      if (key < s1)
+      {
+        s2 = s1;
+        s1 = key;
+      }
+      else if (key < s2)
+        s2 = key;
+    }
+    const unsigned long long b1 = warp_min_u64(s1);
+    const unsigned long long b2 = warp_min_u64(s1 == b1 ? s2 : s1);
+    if (lane == 0)
+    {
+      vksift_Match_2NN m;
+      m.idx_a = row;
+      m.idx_b1 = mt_pos((uint32_t)b1);
+      m.idx_b2 = mt_pos((uint32_t)b2);
+      m.dist_a_b1 = __uint_as_float((uint32_t)(b1 >> 32));
+      m.dist_a_b2 = __uint_as_float((uint32_t)(b2 >> 32));
+      out[row] = m;
+    }
+    return;
+  }
   if (lane == 0)
   {
     vksift_Match_2NN m;
