@@ -187,6 +187,8 @@ struct vksift_Instance_T
   vksift_Match_2NN *d_matches_rev = nullptr; /* B->A list of the cross-checked matcher */
   vksift_Match_2NN *d_matches_blocks = nullptr; /* [blocks_cap][max_nb_sift_per_buffer]: results of vksiftx_matchFeaturesAgainstBlocks */
   uint32_t blocks_cap = 0, blocks_n = 0, blocks_na = 0;
+  uint32_t *d_block_norms = nullptr; /* packed B-side norms of all blocks of such a call, one launch */
+  size_t block_norms_cap = 0;
   uint32_t *d_pairs = nullptr;               /* [2*max + 1]: filtered pairs, count at the end */
   uint32_t nb_matches = 0;
   int matcher_impl = 0;
@@ -697,6 +699,7 @@ void destroy_instance(vksift_Instance inst)
   cudaFree(inst->d_matches);
   cudaFree(inst->d_matches_rev);
   cudaFree(inst->d_matches_blocks);
+  cudaFree(inst->d_block_norms);
   cudaFree(inst->d_pairs);
   match_workspace_destroy(inst->match_ws);
   extrema_plan_destroy(inst->extrema_plan);
@@ -1653,10 +1656,13 @@ extern "C"
     }
   }
 
-  static bool ensure_norms(vksift_Instance inst, FeatureBuffer &fb, uint32_t n)
+  /* *fresh is set when the norms had to be computed now (the search that follows must not overlap earlier work then) */
+  static bool ensure_norms(vksift_Instance inst, FeatureBuffer &fb, uint32_t n, bool *fresh = nullptr)
   {
     if (fb.norms_valid && fb.norms_n == n)
       return true;
+    if (fresh)
+      *fresh = true;
     CU_TRY(launch_norms(fb.desc, n, fb.norm_plain, fb.norm_packed, inst->stream));
     inst->launches++;
     fb.norms_valid = true;
@@ -1671,7 +1677,12 @@ extern "C"
     bool ok = true, invalid = false;
     {
       DeviceGuard g(inst->device);
-      wait_pipelines(inst, true, true); /* vulkansift.c:427-428 */
+      /* vulkansift.c:427-428 waits for the detection AND the previous matching pipeline (one command buffer, one fence).  The
+       * detections are waited for here too (the feature counts come from them); a previous search is ordered before this one
+       * by the stream instead of by the host: searches enqueued back to back run back to back on the GPU, the next one's MMA
+       * phase overlapping the previous one's merge.  Results and every later blocking rule (downloads, detections into a
+       * buffer that a search still reads) are unchanged: they wait for the LAST search, which completes after all others. */
+      wait_pipelines(inst, true, false);
       const uint32_t na = buffer_count(inst, gpu_buffer_id_A, false);
       const uint32_t nb = d_desc_b ? nb_ext : buffer_count(inst, gpu_buffer_id_B, false);
       if (nb < 2 && na > 0)
@@ -1690,18 +1701,20 @@ extern "C"
           const bool prof = inst->profiling;
           if (prof)
             CU_TRY(cudaEventRecord(inst->ev[EV_M0], inst->stream));
-          if (na > 0 && !ensure_norms(inst, A, na))
+          bool fresh = false;
+          if (na > 0 && !ensure_norms(inst, A, na, &fresh))
             return false;
           const uint32_t *nb_cached = nullptr;
           if (na > 0 && !d_desc_b)
           {
             FeatureBuffer &B = inst->buffers[gpu_buffer_id_B];
-            if (!ensure_norms(inst, B, nb))
+            if (!ensure_norms(inst, B, nb, &fresh))
               return false;
             nb_cached = B.norm_packed;
           }
+          /* profiling brackets the kernels with events: no overlap then, the stage times stay per search */
           CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, A.norm_plain, b_desc, nb, nb_cached, inst->d_matches, inst->stream,
-                              prof ? inst->ev[EV_M1] : nullptr, &inst->launches));
+                              prof ? inst->ev[EV_M1] : nullptr, !fresh && !prof, &inst->launches));
           if (prof)
           {
             if (na == 0)
@@ -1794,6 +1807,28 @@ extern "C"
           return true;
         if (!ensure_norms(inst, A, na))
           return false;
+        /* |b|^2 of every block in one launch (blocks whose stride is a whole number of 128-row tiles, at most 64 of them) */
+        const uint32_t stride_rows = (uint32_t)(block_stride_bytes / 128u);
+        const bool batched_norms = n_blocks <= VKS_MAX_MATCH_BLOCKS && (stride_rows % 128u) == 0;
+        if (batched_norms)
+        {
+          const size_t need = (size_t)n_blocks * stride_rows;
+          if (need > inst->block_norms_cap)
+          {
+            if (inst->d_block_norms)
+              CU_TRY(cudaFree(inst->d_block_norms));
+            inst->d_block_norms = nullptr;
+            inst->block_norms_cap = 0;
+            CU_TRY(cudaMalloc(&inst->d_block_norms, sizeof(uint32_t) * need));
+            inst->block_norms_cap = need;
+          }
+          MatchBlockCounts bc;
+          for (uint32_t j = 0; j < VKS_MAX_MATCH_BLOCKS; j++)
+            bc.n[j] = (j < n_blocks && j != skip_block) ? counts[j] : 0u;
+          CU_TRY(launch_norms_blocks((const uint8_t *)d_blocks, bc, n_blocks, stride_rows, inst->d_block_norms, inst->stream));
+          inst->launches++;
+        }
+        bool first_search = true;
         for (uint32_t j = 0; j < n_blocks; j++)
         {
           vksift_Match_2NN *out = inst->d_matches_blocks + (size_t)j * maxf;
@@ -1804,8 +1839,10 @@ extern "C"
           }
           const uint8_t *b = (const uint8_t *)d_blocks + (size_t)j * block_stride_bytes;
           /* the searches share the workspace (B-side norms, partial keys): they are ordered by the stream */
-          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, A.norm_plain, b, counts[j], nullptr, out, inst->stream, nullptr,
+          CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, A.norm_plain, b, counts[j],
+                              batched_norms ? inst->d_block_norms + (size_t)j * stride_rows : nullptr, out, inst->stream, nullptr, !first_search,
                               &inst->launches));
+          first_search = false; /* the first search follows the norm launches, the others only earlier searches */
         }
         CU_TRY(cudaEventRecord(inst->ev_match_done, inst->stream));
         return true;
@@ -2087,12 +2124,13 @@ extern "C"
         FeatureBuffer &A = inst->buffers[gpu_buffer_id_A], &B = inst->buffers[gpu_buffer_id_B];
         const size_t maxf = inst->cfg.max_nb_sift_per_buffer;
         auto run = [&]() -> bool {
-          if (!ensure_norms(inst, A, na) || !ensure_norms(inst, B, nb))
+          bool fresh = false;
+          if (!ensure_norms(inst, A, na, &fresh) || !ensure_norms(inst, B, nb, &fresh))
             return false;
           CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, B.desc, nb, B.norm_plain, A.desc, na, A.norm_packed, inst->d_matches_rev, inst->stream,
-                              nullptr, &inst->launches));
+                              nullptr, !fresh, &inst->launches));
           CU_TRY(launch_match(inst->match_ws, inst->matcher_impl, A.desc, na, A.norm_plain, B.desc, nb, B.norm_packed, inst->d_matches, inst->stream,
-                              nullptr, &inst->launches));
+                              nullptr, true, &inst->launches));
           CU_TRY(launch_match_filter(inst->d_matches, na, inst->d_matches_rev, nb, lowe_ratio, inst->d_pairs, (uint32_t)maxf, inst->d_pairs + 2 * maxf,
                                      inst->stream));
           inst->launches++;

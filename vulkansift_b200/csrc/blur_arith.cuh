@@ -45,6 +45,21 @@ __device__ __forceinline__ pk2 pk_make(float lo, float hi)
   return d;
 }
 
+/* predicated 8-byte global stores: the vertical pass stores rows under `row < rows_valid`; as predicated instructions they
+ * cost nothing, as branches (what the compiler makes of an if around a store and its operands) three instructions per row */
+__device__ __forceinline__ void pk_stg_if(void *ptr, pk2 v, bool ok)
+{
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.b64 [%0], %1;\n\t}" ::"l"(ptr), "l"(v), "r"((uint32_t)ok) : "memory");
+}
+__device__ __forceinline__ void pk_stcs_if(void *ptr, pk2 v, bool ok)
+{
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.cs.b64 [%0], %1;\n\t}" ::"l"(ptr), "l"(v), "r"((uint32_t)ok) : "memory");
+}
+__device__ __forceinline__ void f32_stg_if(void *ptr, float v, bool ok)
+{
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(ptr), "f"(v), "r"((uint32_t)ok) : "memory");
+}
+
 /* fp16 precision mode: a value goes through binary16 (round to nearest even) on its way to memory */
 __device__ __forceinline__ float round_half1(float v) { return __half2float(__float2half_rn(v)); }
 __device__ __forceinline__ pk2 round_half2(pk2 v)

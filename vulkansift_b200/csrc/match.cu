@@ -242,6 +242,41 @@ __global__ void norms_both_kernel(const uint8_t *__restrict__ desc, uint32_t n, 
   }
 }
 
+/* packed B-side norms of several descriptor blocks (block j = counts.n[j] rows at desc + j * stride_rows * 128) in one launch:
+ * out[j * stride_rows + i] like norms_kernel(packed) of block j, rows past the block's count marked absent */
+__global__ void norms_blocks_kernel(const uint8_t *__restrict__ desc, const MatchBlockCounts counts, uint32_t n_blocks, uint32_t stride_rows,
+                                    uint32_t *__restrict__ out_packed)
+{
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_blocks * stride_rows)
+    return;
+  const uint32_t j = row / stride_rows, i = row - j * stride_rows;
+  if (i >= counts.n[j])
+  {
+    if (lane == 0)
+      out_packed[row] = NORM_PAD_VALUE;
+    return;
+  }
+  const uint32_t v = __ldg((const uint32_t *)(desc + (size_t)row * 128) + lane);
+  uint32_t s = __dp4a(v, v, 0u);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, d);
+  if (lane == 0)
+    out_packed[row] = s * 256u + (match_pos_host_device(i) & 255u);
+}
+
+cudaError_t launch_norms_blocks(const uint8_t *desc, const MatchBlockCounts &counts, uint32_t n_blocks, uint32_t stride_rows, uint32_t *out_packed,
+                                cudaStream_t st)
+{
+  const size_t rows = (size_t)n_blocks * stride_rows;
+  if (rows == 0)
+    return cudaSuccess;
+  norms_blocks_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(desc, counts, n_blocks, stride_rows, out_packed);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_norms(const uint8_t *desc, uint32_t n, uint32_t *out_plain, uint32_t *out_packed, cudaStream_t st)
 {
   const uint32_t n_pad = (n + 127u) & ~127u;
@@ -252,10 +287,14 @@ cudaError_t launch_norms(const uint8_t *desc, uint32_t n, uint32_t *out_plain, u
 }
 
 cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *da, uint32_t na, const uint32_t *norm_a, const uint8_t *db, uint32_t nb,
-                         const uint32_t *norm_b, vksift_Match_2NN *out, cudaStream_t st, cudaEvent_t ev_after_prepare, uint64_t *launch_count)
+                         const uint32_t *norm_b, vksift_Match_2NN *out, cudaStream_t st, cudaEvent_t ev_after_prepare, bool inputs_settled,
+                         uint64_t *launch_count)
 {
   if (na == 0)
     return cudaSuccess;
+  /* norms computed here are inputs written by the launch just before the search: no overlap with the previous search then */
+  if (!norm_a || !norm_b)
+    inputs_settled = false;
   const uint32_t nb_pad = (nb + 127u) & ~127u; /* the tensor-core path reads |b|^2 in tiles of 128 */
   if (!norm_a)
   {
@@ -280,7 +319,7 @@ cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *da, uint32
     *launch_count += 1;
     return cudaGetLastError();
   }
-  return match_tc_launch(ws->tc, da, na, norm_a, db, nb, norm_b, out, st, launch_count);
+  return match_tc_launch(ws->tc, da, na, norm_a, db, nb, norm_b, out, st, inputs_settled, launch_count);
 }
 
 } // namespace vks

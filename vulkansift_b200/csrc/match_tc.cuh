@@ -274,16 +274,25 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
     unsigned long long k1 = ~0ull, k2 = ~0ull;
     int32_t my_na = 0;
     uint32_t cur_rb = 0xffffffffu;
-    /* every (row block, segment, warpgroup) slot of this CTA is published, also when the warpgroup gets no
-     * tile of a short segment: start from "nothing found" and overwrite with the real result below */
-    if (my_tiles > 0)
-      for (uint32_t rb = rb_first; rb <= (u1 - 1) / n_tiles; rb++)
-      {
-        const uint32_t seg_slot = blockIdx.x - (rb * n_tiles) / units_per_cta;
-        const size_t slot = (((size_t)rb * max_segs + seg_slot) * 2 + wg) * MT_M + lrow;
-        partial[slot * 2 + 0] = ~0ull;
-        partial[slot * 2 + 1] = ~0ull;
-      }
+    /* Every (row block, segment, warpgroup) slot of this CTA is published, also when the warpgroup gets no tile of a short
+     * segment: "nothing found" first, the real results over it.  All of it happens behind griddepcontrol.wait, as late as
+     * possible: when the launch is programmatically dependent on the merge kernel of the PREVIOUS search (back-to-back
+     * searches, match_tc_launch), that kernel may still be reading the partial keys while this grid already runs its MMAs. */
+    bool published = false;
+    auto publish_init = [&]() {
+      if (published)
+        return;
+      published = true;
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      if (my_tiles > 0)
+        for (uint32_t rb = rb_first; rb <= (u1 - 1) / n_tiles; rb++)
+        {
+          const uint32_t seg_slot = blockIdx.x - (rb * n_tiles) / units_per_cta;
+          const size_t slot = (((size_t)rb * max_segs + seg_slot) * 2 + wg) * MT_M + lrow;
+          partial[slot * 2 + 0] = ~0ull;
+          partial[slot * 2 + 1] = ~0ull;
+        }
+    };
     for (uint32_t t = (uint32_t)wg; t < my_tiles; t += 2)
     {
       const uint32_t u = u0 + t, rb = u / n_tiles, tile = u - rb * n_tiles;
@@ -292,6 +301,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
         if (cur_rb != 0xffffffffu)
         {
           /* flush the finished segment */
+          publish_init();
           const uint32_t seg_slot = blockIdx.x - (cur_rb * n_tiles) / units_per_cta;
           const size_t slot = (((size_t)cur_rb * max_segs + seg_slot) * 2 + wg) * MT_M + lrow;
           partial[slot * 2 + 0] = k1;
@@ -379,6 +389,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
           k2 = key;
       }
     }
+    publish_init();
     if (cur_rb != 0xffffffffu)
     {
       const uint32_t seg_slot = blockIdx.x - (cur_rb * n_tiles) / units_per_cta;
@@ -419,6 +430,8 @@ __global__ void __launch_bounds__(32 * MG_WARPS) match_merge_kernel(const unsign
                                                                     vksift_Match_2NN *__restrict__ out)
 {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  /* the MMA kernel of the next search may start now (it touches the partial keys only after this grid has completed) */
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t row = blockIdx.x * MG_WARPS + (uint32_t)warp;
   if (row >= na)
     return;
@@ -612,8 +625,11 @@ static bool mt_make_map(MatchTc *tc, CUtensorMap *map, const uint8_t *base, uint
   return r == CUDA_SUCCESS;
 }
 
+/* overlap_previous: nothing this search reads (descriptors, norms) was written by the work enqueued just before it on `st`,
+ * so the MMA kernel is launched programmatically dependent: behind the merge kernel of a previous search it starts while that
+ * one still runs, and waits for it only before it publishes its partial keys. */
 static cudaError_t match_tc_launch(void *p, const uint8_t *da, uint32_t na, const uint32_t *norm_a, const uint8_t *db, uint32_t nb,
-                                   const uint32_t *norm_b, vksift_Match_2NN *out, cudaStream_t st, uint64_t *launch_count)
+                                   const uint32_t *norm_b, vksift_Match_2NN *out, cudaStream_t st, bool overlap_previous, uint64_t *launch_count)
 {
   MatchTc *tc = (MatchTc *)p;
   const uint32_t row_blocks = (na + MT_M - 1) / MT_M;
@@ -642,8 +658,22 @@ static cudaError_t match_tc_launch(void *p, const uint8_t *da, uint32_t na, cons
   CUtensorMap map_a, map_b;
   if (!mt_make_map(tc, &map_a, da, na, MT_M) || !mt_make_map(tc, &map_b, db, nb, MT_N))
     return cudaErrorInvalidValue;
-  match_tc_kernel<<<n_cta, MT_THREADS, MT_SMEM_BYTES, st>>>(map_a, map_b, norm_a, norm_b, na, n_tiles, units_per_cta, total_units, max_segs, tc->partial, -512);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_cta);
+    cfg.blockDim = dim3(MT_THREADS);
+    cfg.dynamicSmemBytes = MT_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap_previous ? 1 : 0;
+    unsigned long long *partial = tc->partial;
+    const int32_t key_scale = -512;
+    e = cudaLaunchKernelEx(&cfg, match_tc_kernel, map_a, map_b, norm_a, norm_b, na, n_tiles, units_per_cta, total_units, max_segs, partial, key_scale);
+  }
   if (e != cudaSuccess)
     return e;
   {

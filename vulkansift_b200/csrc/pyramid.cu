@@ -612,9 +612,9 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
       for (int j = 0; j < 4; j++)
       {
         const int q = qb + j;
-        if (q < nrows)
+        if (H16)
         {
-          if (H16)
+          if (q < nrows)
           {
             /* binary16 layers: one rounding to nearest even, the rounded value is what the DoG is taken from (it is what
              * the layer holds), half2 stores */
@@ -632,20 +632,24 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
               noff += npitch4;
             }
           }
-          else
-          {
-          *(pk2 *)(gbase + off) = acc[j];
+        }
+        else
+        {
+          /* stores as predicated instructions (rows past the image end in the last tile row); the operands are computed
+           * for every row: the DoG source row is in shared memory whether the output row exists or not */
+          const bool ok = q < nrows;
+          pk_stg_if(gbase + off, acc[j], ok);
           if (KIND != FT_KIND_SEED)
           {
-            pk2 d = pk_sub(acc[j], *(const pk2 *)(ccol + q * S));
-            __stcs((pk2 *)(dbase + off), d); /* streaming: the DoG layer is not read before the extrema scan, the L2 lines are better spent on G, which the next layer's launch reads back */
+            /* streaming: the DoG layer is not read before the extrema scan, the L2 lines are better spent on G, which the
+             * next layer's launch reads back */
+            pk_stcs_if(dbase + off, pk_sub(acc[j], *(const pk2 *)(ccol + q * S)), ok);
           }
           if (KIND == FT_KIND_NEXT && (q & 1))
           {
             /* x even, y odd: the odd column of the pair feeds next(x>>1, y>>1) */
-            *(float *)(nbase + noff) = pk_hi(acc[j]);
+            f32_stg_if(nbase + noff, pk_hi(acc[j]), ok);
             noff += npitch4;
-          }
           }
         }
         off += pitch4;

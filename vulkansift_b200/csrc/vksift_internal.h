@@ -226,9 +226,21 @@ cudaError_t match_workspace_create(MatchWorkspace **ws, uint32_t max_feats);
 void match_workspace_destroy(MatchWorkspace *ws);
 /* |x|^2 of n descriptors in both forms the matcher uses: plain (A side) and packed nbk (B side, padded to a multiple of 128 rows) */
 cudaError_t launch_norms(const uint8_t *desc, uint32_t n, uint32_t *out_plain, uint32_t *out_packed, cudaStream_t st);
-/* norm_a / norm_b: cached norms of the two sides (launch_norms) or nullptr, in which case they are computed into the workspace */
+/* norm_a / norm_b: cached norms of the two sides (launch_norms) or nullptr, in which case they are computed into the workspace.
+ * inputs_settled: descriptors and norms were NOT written by the work enqueued on `st` right before this call (cached norms of
+ * unchanged buffers); the search may then overlap the tail of a previous search on the same stream. */
 cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *desc_a, uint32_t na, const uint32_t *norm_a, const uint8_t *desc_b, uint32_t nb,
-                         const uint32_t *norm_b, vksift_Match_2NN *out, cudaStream_t st, cudaEvent_t ev_after_prepare, uint64_t *launch_count);
+                         const uint32_t *norm_b, vksift_Match_2NN *out, cudaStream_t st, cudaEvent_t ev_after_prepare, bool inputs_settled,
+                         uint64_t *launch_count);
+
+/* B-side norms of up to VKS_MAX_MATCH_BLOCKS descriptor blocks in one launch (all-pairs step) */
+#define VKS_MAX_MATCH_BLOCKS 64
+struct MatchBlockCounts
+{
+  uint32_t n[VKS_MAX_MATCH_BLOCKS];
+};
+cudaError_t launch_norms_blocks(const uint8_t *desc, const MatchBlockCounts &counts, uint32_t n_blocks, uint32_t stride_rows, uint32_t *out_packed,
+                                cudaStream_t st);
 
 cudaError_t launch_match_filter(const vksift_Match_2NN *m12, uint32_t na, const vksift_Match_2NN *m21, uint32_t nb, float ratio, uint32_t *pairs,
                                 uint32_t capacity, uint32_t *count, cudaStream_t st);
