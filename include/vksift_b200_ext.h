@@ -86,6 +86,31 @@ extern "C"
                                                         const uint32_t skip_block);
   VKSIFT_EXPORT void vksiftx_downloadMatchesBlocks(vksift_Instance instance, vksift_Match_2NN *matches, const uint32_t n_blocks);
 
+  /* Descriptor exchange between the GPUs of one node over NVLink peer memory (one process and one instance per GPU).  The
+   * reference has no multi-GPU path (one instance = one GPU, vulkansift.h:32-34); this is the exchange step of cross-image
+   * matching: every rank pushes the descriptors of one feature buffer straight into a receive slot on every peer (one kernel,
+   * posted NVLink stores, completion flags in peer memory) and then matches against the slots in place.
+   *   vksiftx_exchangeCreate      allocates this rank's receive region (2 x world_size slots of slot_rows descriptors,
+   *                               slot_rows >= max_nb_sift_per_buffer) and writes its 64-byte CUDA IPC handle to handle_out;
+   *   vksiftx_exchangeConnect     maps the peers' regions: `handles` = world_size x 64 bytes, rank order, gathered by the
+   *                               caller with whatever it has (MPI, torch.distributed, a file);
+   *   vksiftx_exchangeAllGather   COLLECTIVE: pushes the descriptors of gpu_buffer_id to every peer, waits until every peer's
+   *                               block of the same round has arrived, returns the row counts (counts[world_size]) and the
+   *                               device address / stride of the received blocks (block r = rank r's descriptors; the own
+   *                               block is not filled).  The blocks stay valid until the next-but-one exchange;
+   *   vksiftx_exchangeMatchAllPeers  the same followed by vksiftx_matchFeaturesAgainstBlocks(own buffer, received blocks,
+   *                               skip = own rank); fetch the result with vksiftx_downloadMatchesBlocks(world_size).
+   * Every rank must make the same sequence of exchange calls; a peer that does not show up within two seconds is reported
+   * through the error callback (VKSIFT_VULKAN_ERROR) instead of hanging the GPU.  All peers must have called Connect
+   * before the first AllGather, and Destroy only after the last one has completed everywhere (barriers are the caller's). */
+  VKSIFT_EXPORT bool vksiftx_exchangeCreate(vksift_Instance instance, const uint32_t rank, const uint32_t world_size, const uint32_t slot_rows,
+                                            void *handle_out);
+  VKSIFT_EXPORT bool vksiftx_exchangeConnect(vksift_Instance instance, const void *handles);
+  VKSIFT_EXPORT bool vksiftx_exchangeAllGather(vksift_Instance instance, const uint32_t gpu_buffer_id, uint32_t *counts, void **d_blocks,
+                                               uint64_t *block_stride_bytes);
+  VKSIFT_EXPORT bool vksiftx_exchangeMatchAllPeers(vksift_Instance instance, const uint32_t gpu_buffer_id, uint32_t *counts);
+  VKSIFT_EXPORT void vksiftx_exchangeDestroy(vksift_Instance instance);
+
   /* Device pointer of the last match result: vksift_getMatchesNumber() rows of vksift_Match_2NN. */
   VKSIFT_EXPORT void *vksiftx_getMatchesDevice(vksift_Instance instance);
 

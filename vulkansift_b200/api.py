@@ -102,6 +102,11 @@ def _load_library(path=LIB_PATH, analysis=False):
         "vksiftx_matchFeaturesAgainstDevice": (None, [I, u32, C.c_void_p, u32]),
         "vksiftx_matchFeaturesAgainstBlocks": (None, [I, u32, C.c_void_p, u32, C.c_uint64, P(u32), u32]),
         "vksiftx_downloadMatchesBlocks": (None, [I, C.c_void_p, u32]),
+        "vksiftx_exchangeCreate": (C.c_bool, [I, u32, u32, u32, C.c_void_p]),
+        "vksiftx_exchangeConnect": (C.c_bool, [I, C.c_void_p]),
+        "vksiftx_exchangeAllGather": (C.c_bool, [I, u32, P(u32), P(C.c_void_p), P(C.c_uint64)]),
+        "vksiftx_exchangeMatchAllPeers": (C.c_bool, [I, u32, P(u32)]),
+        "vksiftx_exchangeDestroy": (None, [I]),
         "vksiftx_setProfiling": (None, [I, C.c_bool]),
         "vksiftx_getStageTimesMs": (None, [I, P(C.c_float)]),
         "vksiftx_matchFeaturesCrossChecked": (C.c_uint32, [I, C.c_uint32, C.c_uint32, C.c_float, P(C.c_uint32), C.c_uint32]),
@@ -343,6 +348,42 @@ class Instance:
         self._lib.vksiftx_downloadMatchesBlocks(self._h, out.ctypes.data, nb)
         self._check("vksiftx_downloadMatchesBlocks")
         return out.reshape(-1)[:nb * n_rows].reshape(nb, n_rows)
+
+    # -- descriptor exchange over NVLink peer memory (one process per GPU; see vulkansift_b200.dist.PeerExchange) --
+    def exchange_create(self, rank, world, slot_rows):
+        """Allocate this rank's receive region; returns its 64-byte CUDA IPC handle (bytes)."""
+        h = (C.c_uint8 * 64)()
+        ok = self._lib.vksiftx_exchangeCreate(self._h, rank, world, slot_rows, C.cast(h, C.c_void_p))
+        self._check("vksiftx_exchangeCreate")
+        assert ok
+        self._xc_world = world
+        return bytes(h)
+
+    def exchange_connect(self, handles):
+        """handles: world x 64 bytes in rank order."""
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        ok = self._lib.vksiftx_exchangeConnect(self._h, C.cast(buf, C.c_void_p))
+        self._check("vksiftx_exchangeConnect")
+        assert ok
+
+    def exchange_allgather(self, buffer_id):
+        """Collective.  Returns (counts, device pointer of block 0, block stride in bytes)."""
+        counts = (C.c_uint32 * self._xc_world)()
+        ptr, stride = C.c_void_p(), C.c_uint64()
+        self._lib.vksiftx_exchangeAllGather(self._h, buffer_id, counts, C.byref(ptr), C.byref(stride))
+        self._check("vksiftx_exchangeAllGather")
+        return [int(c) for c in counts], ptr.value, int(stride.value)
+
+    def exchange_match_all_peers(self, buffer_id):
+        """Collective: exchange + searches against every peer block; fetch with download_matches_blocks().  Returns the counts."""
+        counts = (C.c_uint32 * self._xc_world)()
+        self._lib.vksiftx_exchangeMatchAllPeers(self._h, buffer_id, counts)
+        self._check("vksiftx_exchangeMatchAllPeers")
+        self._n_blocks = self._xc_world
+        return [int(c) for c in counts]
+
+    def exchange_destroy(self):
+        self._lib.vksiftx_exchangeDestroy(self._h)
 
     def matches_device(self):
         return self._lib.vksiftx_getMatchesDevice(self._h)

@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, "lib", "libvulkansift.so")
 # same sources with -DVKS_ANALYSIS: adds vksiftx_setDebugSkip (stage ablation, invalid results).  Only tools/ablation.py and
 # bench.py's marginal-cost measurement load it; every timed or parity-checked detection runs on LIB, which has no such switch.
 LIB_ANALYSIS = os.path.join(HERE, "lib", "libvulkansift_analysis.so")
-SOURCES = ["api.cu", "plan.cu", "pyramid.cu", "pyramid_strip.cu", "extrema.cu", "describe.cu", "match.cu"]
+SOURCES = ["api.cu", "plan.cu", "pyramid.cu", "pyramid_strip.cu", "extrema.cu", "describe.cu", "match.cu", "exchange.cu"]
 HEADERS = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [
     os.path.join(ROOT, "include", "vksift_arith.h"), os.path.join(ROOT, "include", "vksift_b200_ext.h"),
     os.path.join(ROOT, "include", "vulkansift", "vulkansift.h"), os.path.join(ROOT, "include", "vulkansift", "vulkansift_types.h")]

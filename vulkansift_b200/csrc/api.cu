@@ -188,6 +188,7 @@ struct vksift_Instance_T
   vksift_Match_2NN *d_matches_blocks = nullptr; /* [blocks_cap][max_nb_sift_per_buffer]: results of vksiftx_matchFeaturesAgainstBlocks */
   uint32_t blocks_cap = 0, blocks_n = 0, blocks_na = 0;
   uint32_t *d_block_norms = nullptr; /* packed B-side norms of all blocks of such a call, one launch */
+  PeerExchange *exchange = nullptr;  /* NVLink peer-memory all-gather of descriptor blocks (vksiftx_exchange*) */
   size_t block_norms_cap = 0;
   uint32_t *d_pairs = nullptr;               /* [2*max + 1]: filtered pairs, count at the end */
   uint32_t nb_matches = 0;
@@ -700,6 +701,8 @@ void destroy_instance(vksift_Instance inst)
   cudaFree(inst->d_matches_rev);
   cudaFree(inst->d_matches_blocks);
   cudaFree(inst->d_block_norms);
+  exchange_destroy(inst->exchange);
+  inst->exchange = nullptr;
   cudaFree(inst->d_pairs);
   match_workspace_destroy(inst->match_ws);
   extrema_plan_destroy(inst->extrema_plan);
@@ -1888,6 +1891,113 @@ extern "C"
       LOGE(TAG, "vksiftx_downloadMatchesBlocks() error when downloading SIFT matches from GPU memory.");
       inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
     }
+  }
+
+  /* ---- descriptor exchange between the GPUs of a node over NVLink peer memory (exchange.cu) ---- */
+  bool vksiftx_exchangeCreate(vksift_Instance inst, const uint32_t rank, const uint32_t world_size, const uint32_t slot_rows, void *handle_out)
+  {
+    if (handle_out == NULL || inst->exchange != nullptr || slot_rows < inst->cfg.max_nb_sift_per_buffer)
+    {
+      LOGE(TAG, "vksiftx_exchangeCreate() error: invalid input (one exchange per instance, slots of at least max_nb_sift_per_buffer rows).");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return false;
+    }
+    DeviceGuard g(inst->device);
+    const uint32_t rows = (slot_rows + 127u) & ~127u;
+    cudaError_t e = exchange_create(&inst->exchange, (int)rank, (int)world_size, rows, handle_out);
+    if (e != cudaSuccess)
+    {
+      LOGE(TAG, "vksiftx_exchangeCreate() error: %s (rank %u of %u, at most %d ranks).", cudaGetErrorName(e), rank, world_size, VKS_MAX_PEERS);
+      inst->cfg.on_error_callback_function(e == cudaErrorInvalidValue ? VKSIFT_INVALID_INPUT_ERROR : VKSIFT_VULKAN_ERROR);
+      return false;
+    }
+    return true;
+  }
+
+  bool vksiftx_exchangeConnect(vksift_Instance inst, const void *handles)
+  {
+    if (handles == NULL || inst->exchange == nullptr)
+    {
+      LOGE(TAG, "vksiftx_exchangeConnect() error: invalid input (no exchange created).");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return false;
+    }
+    DeviceGuard g(inst->device);
+    cudaError_t e = exchange_connect(inst->exchange, handles);
+    if (e != cudaSuccess)
+    {
+      LOGE(TAG, "vksiftx_exchangeConnect() error: cannot map a peer's exchange memory (%s).", cudaGetErrorName(e));
+      inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
+      return false;
+    }
+    return true;
+  }
+
+  bool vksiftx_exchangeAllGather(vksift_Instance inst, const uint32_t gpu_buffer_id, uint32_t *counts, void **d_blocks, uint64_t *block_stride_bytes)
+  {
+    if (!buffer_idx_valid(inst, gpu_buffer_id) || inst->exchange == nullptr || counts == NULL)
+    {
+      LOGE(TAG, "vksiftx_exchangeAllGather() error: invalid input (buffer index, or no exchange created).");
+      inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
+      return false;
+    }
+    bool ok = true;
+    uint32_t late = 0;
+    {
+      DeviceGuard g(inst->device);
+      wait_pipelines(inst, true, false); /* the feature count comes from the detection; earlier searches are ordered by the stream */
+      const uint32_t n = buffer_count(inst, gpu_buffer_id, false);
+      FeatureBuffer &fb = inst->buffers[gpu_buffer_id];
+      auto run = [&]() -> bool {
+        MarkerRegion mr(inst, "DescriptorExchange");
+        CU_TRY(exchange_allgather(inst->exchange, fb.desc, n, inst->stream, &inst->launches));
+        CU_TRY(cudaStreamSynchronize(inst->stream));
+        return true;
+      };
+      ok = run();
+      if (ok)
+      {
+        late = exchange_timeout_mask(inst->exchange);
+        const uint32_t *hc = exchange_host_counts(inst->exchange);
+        for (int p = 0; p < exchange_world(inst->exchange); p++)
+          counts[p] = hc[p];
+        uint64_t stride = 0;
+        const uint8_t *blocks = exchange_blocks(inst->exchange, &stride);
+        if (d_blocks)
+          *d_blocks = (void *)blocks;
+        if (block_stride_bytes)
+          *block_stride_bytes = stride;
+      }
+    }
+    if (!ok || late != 0)
+    {
+      if (late != 0)
+        LOGE(TAG, "vksiftx_exchangeAllGather() error: peers (mask 0x%x) did not publish their descriptors within two seconds.", late);
+      else
+        LOGE(TAG, "vksiftx_exchangeAllGather() error: Failed to run the descriptor exchange.");
+      inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
+      return false;
+    }
+    return true;
+  }
+
+  bool vksiftx_exchangeMatchAllPeers(vksift_Instance inst, const uint32_t gpu_buffer_id, uint32_t *counts)
+  {
+    void *blocks = nullptr;
+    uint64_t stride = 0;
+    if (!vksiftx_exchangeAllGather(inst, gpu_buffer_id, counts, &blocks, &stride))
+      return false;
+    vksiftx_matchFeaturesAgainstBlocks(inst, gpu_buffer_id, blocks, (uint32_t)exchange_world(inst->exchange), stride, counts,
+                                       (uint32_t)exchange_rank(inst->exchange));
+    return true;
+  }
+
+  void vksiftx_exchangeDestroy(vksift_Instance inst)
+  {
+    DeviceGuard g(inst->device);
+    cudaDeviceSynchronize();
+    exchange_destroy(inst->exchange);
+    inst->exchange = nullptr;
   }
 
   uint32_t vksift_getMatchesNumber(vksift_Instance inst) { return inst->nb_matches; }

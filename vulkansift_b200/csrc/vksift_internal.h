@@ -245,4 +245,17 @@ cudaError_t launch_norms_blocks(const uint8_t *desc, const MatchBlockCounts &cou
 cudaError_t launch_match_filter(const vksift_Match_2NN *m12, uint32_t na, const vksift_Match_2NN *m21, uint32_t nb, float ratio, uint32_t *pairs,
                                 uint32_t capacity, uint32_t *count, cudaStream_t st);
 
+/* descriptor all-gather over NVLink peer memory (exchange.cu) */
+#define VKS_MAX_PEERS 16
+struct PeerExchange;
+cudaError_t exchange_create(PeerExchange **out, int rank, int world, uint32_t slot_rows, void *handle64);
+cudaError_t exchange_connect(PeerExchange *x, const void *handles);
+cudaError_t exchange_allgather(PeerExchange *x, const uint8_t *desc, uint32_t n, cudaStream_t st, uint64_t *launch_count);
+const uint32_t *exchange_host_counts(const PeerExchange *x);
+uint32_t exchange_timeout_mask(const PeerExchange *x);
+const uint8_t *exchange_blocks(const PeerExchange *x, uint64_t *stride_bytes);
+int exchange_world(const PeerExchange *x);
+int exchange_rank(const PeerExchange *x);
+void exchange_destroy(PeerExchange *x);
+
 } // namespace vks

@@ -2,9 +2,14 @@
 
 One process per GPU (torchrun).  Detection shards by image with no data-path collective
 (SURVEY 8e); all-pairs matching has exactly one exchange step: every rank contributes its
-descriptor block and receives everyone else's (all-gather, NCCL over NVLink on the GPU box).
-The functions below only move tensors, so the same code runs on CPU tensors with the gloo
-backend in the tests; the CUDA-specific glue is `gather_instance_descriptors`.
+descriptor block and receives everyone else's.  Two implementations:
+
+* `PeerExchange` (the product path on a GPU node): the library's own exchange over NVLink peer memory
+  (csrc/exchange.cu: every rank pushes its block into a slot on every peer with one kernel, flags in peer
+  memory, blocks matched in place).  torch.distributed only carries the 64-byte IPC handles once, at setup.
+* `gather_instance_descriptors` + `match_against_peers_batched`: one NCCL all-gather plus a count read-back
+  (round 1; kept as the baseline `bench.py` times next to the peer-memory path).  These functions only move
+  tensors, so the same code runs on CPU tensors with the gloo backend in the tests.
 """
 import torch
 import torch.distributed as dist
@@ -132,3 +137,39 @@ def match_against_peers(inst, buffer_a, scratch_buffer, counts, blocks, rank, wo
             inst.match(buffer_a, scratch_buffer)
         out[j] = inst.download_matches() if download else None
     return out
+
+
+class PeerExchange:
+    """All-pairs exchange step through the library's NVLink peer-memory all-gather (vksiftx_exchange*).
+
+    Setup (once): every rank allocates its receive region, the 64-byte CUDA IPC handles are all-gathered with
+    torch.distributed (any backend: the handles travel as a CPU or CUDA uint8 tensor), every rank maps its peers.
+    Step: `match_all_peers(buffer)` = ONE library call (push + wait + searches against the seven received blocks in place)
+    and ONE download.  Collective: every rank must call it the same number of times."""
+
+    def __init__(self, inst, slot_rows, group=None):
+        self.inst, self.group = inst, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        handle = inst.exchange_create(self.rank, self.world, slot_rows)
+        backend = dist.get_backend(group)
+        dev = torch.device("cuda", inst.device_index) if backend == "nccl" else torch.device("cpu")
+        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
+        every = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(every.view(-1), mine, group=group)
+        inst.exchange_connect(every.cpu().numpy().tobytes())
+        dist.barrier(group)  # every region exists and is mapped everywhere before the first push
+
+    def allgather(self, buffer_id):
+        """(counts, device pointer of block 0, stride in bytes): the peers' descriptor blocks, in place in this rank's region."""
+        return self.inst.exchange_allgather(buffer_id)
+
+    def match_all_peers(self, buffer_id, out=None):
+        """{peer: matches or None (peer holds fewer than 2 descriptors)} of the local features against every peer's."""
+        n_a = self.inst.features_number(buffer_id)
+        counts = self.inst.exchange_match_all_peers(buffer_id)
+        res = self.inst.download_matches_blocks(n_a, out=out)
+        return counts, {j: (res[j] if counts[j] >= 2 else None) for j in range(self.world) if j != self.rank}
+
+    def close(self):
+        dist.barrier(self.group)  # nobody pushes into a region that is about to be unmapped
+        self.inst.exchange_destroy()
