@@ -90,8 +90,8 @@ extern "C"
    * reference has no multi-GPU path (one instance = one GPU, vulkansift.h:32-34); this is the exchange step of cross-image
    * matching: every rank pushes the descriptors of one feature buffer straight into a receive slot on every peer (one kernel,
    * posted NVLink stores, completion flags in peer memory) and then matches against the slots in place.
-   *   vksiftx_exchangeCreate      allocates this rank's receive region (2 x world_size slots of slot_rows descriptors,
-   *                               slot_rows >= max_nb_sift_per_buffer) and writes its 64-byte CUDA IPC handle to handle_out;
+   *   vksiftx_exchangeCreate      allocates this rank's receive region (2 x world_size slots of slot_rows descriptors:
+   *                               the most a rank may hold when it exchanges) and writes its 64-byte CUDA IPC handle to handle_out;
    *   vksiftx_exchangeConnect     maps the peers' regions: `handles` = world_size x 64 bytes, rank order, gathered by the
    *                               caller with whatever it has (MPI, torch.distributed, a file);
    *   vksiftx_exchangeAllGather   COLLECTIVE: pushes the descriptors of gpu_buffer_id to every peer, waits until every peer's

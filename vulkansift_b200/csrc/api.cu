@@ -1896,9 +1896,9 @@ extern "C"
   /* ---- descriptor exchange between the GPUs of a node over NVLink peer memory (exchange.cu) ---- */
   bool vksiftx_exchangeCreate(vksift_Instance inst, const uint32_t rank, const uint32_t world_size, const uint32_t slot_rows, void *handle_out)
   {
-    if (handle_out == NULL || inst->exchange != nullptr || slot_rows < inst->cfg.max_nb_sift_per_buffer)
+    if (handle_out == NULL || inst->exchange != nullptr || slot_rows == 0)
     {
-      LOGE(TAG, "vksiftx_exchangeCreate() error: invalid input (one exchange per instance, slots of at least max_nb_sift_per_buffer rows).");
+      LOGE(TAG, "vksiftx_exchangeCreate() error: invalid input (one exchange per instance, slots of at least one row).");
       inst->cfg.on_error_callback_function(VKSIFT_INVALID_INPUT_ERROR);
       return false;
     }
@@ -1950,6 +1950,11 @@ extern "C"
       FeatureBuffer &fb = inst->buffers[gpu_buffer_id];
       auto run = [&]() -> bool {
         MarkerRegion mr(inst, "DescriptorExchange");
+        if (n > exchange_slot_rows(inst->exchange))
+        {
+          LOGE(TAG, "vksiftx_exchangeAllGather() error: the buffer holds %u features, an exchange slot %u rows.", n, exchange_slot_rows(inst->exchange));
+          return false;
+        }
         CU_TRY(exchange_allgather(inst->exchange, fb.desc, n, inst->stream, &inst->launches));
         CU_TRY(cudaStreamSynchronize(inst->stream));
         return true;

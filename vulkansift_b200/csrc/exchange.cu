@@ -233,6 +233,7 @@ const uint8_t *exchange_blocks(const PeerExchange *x, uint64_t *stride_bytes)
   return x->local + xc_block_off(x->world, x->slot_rows, x->epoch & 1u, 0);
 }
 int exchange_world(const PeerExchange *x) { return x->world; }
+uint32_t exchange_slot_rows(const PeerExchange *x) { return x->slot_rows; }
 int exchange_rank(const PeerExchange *x) { return x->rank; }
 
 void exchange_destroy(PeerExchange *x)

@@ -255,6 +255,7 @@ const uint32_t *exchange_host_counts(const PeerExchange *x);
 uint32_t exchange_timeout_mask(const PeerExchange *x);
 const uint8_t *exchange_blocks(const PeerExchange *x, uint64_t *stride_bytes);
 int exchange_world(const PeerExchange *x);
+uint32_t exchange_slot_rows(const PeerExchange *x);
 int exchange_rank(const PeerExchange *x);
 void exchange_destroy(PeerExchange *x);
 
