@@ -110,7 +110,7 @@ def dominant_kernel_roofline(trace_acc, octaves, ns, hbm, peak_src):
                     "each traced launch"}
 
 
-def tmem_drain_roofline(na, nb, kernel_ms, clocks):
+def tmem_drain_roofline(na, nb, kernel_ms, clocks, stream_ms=None):
     """What actually bounds the tensor-core matcher: every one of the na x nb fp32/s32 accumulators has to leave
     tensor memory through tcgen05.ld, 64 bytes per clock and SM (B300_MICROARCH.md, TMEM table), whatever the MMA rate."""
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
@@ -118,9 +118,13 @@ def tmem_drain_roofline(na, nb, kernel_ms, clocks):
     nbytes = 4.0 * pad(na) * pad(nb)
     peak = 64.0 * 148 * sm_mhz * 1e6 / 1e9  # GB/s
     ach = nbytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
-    return {"bound": "tmem_read", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "accumulator_bytes": nbytes,
-            "note": "kernel_ms covers the MMA kernel AND the merge kernel (about 22 + 10 us at 10k x 10k); the MMA kernel alone sits on this bound "
-                    "(profiles/match_r2.txt)"}
+    out = {"bound": "tmem_read", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "accumulator_bytes": nbytes,
+           "note": "kernel_ms = one search alone, MMA kernel AND merge kernel (about 22 + 10 us at 10k x 10k); the MMA kernel alone sits on this "
+                   "bound (profiles/match_r2.txt).  frac_back_to_back = the same bytes over ms_per_match_call: consecutive searches are stream "
+                   "ordered and the next MMA kernel overlaps the previous merge"}
+    if stream_ms:
+        out["frac_back_to_back"] = nbytes / (stream_ms * 1e-3) / 1e9 / peak
+    return out
 
 
 class ClockSampler:
@@ -538,6 +542,31 @@ def main():
     one.close()
     sinst.close()
 
+    # ---------------- texture-rich image (not a configs[] row): no cliff when an image yields 20x the features ----------------
+    dense = None
+    if not args.quick and world == 1:
+        rng = np.random.default_rng(77)
+        dimg = np.kron(rng.integers(0, 256, (h // 3, w // 3), dtype=np.uint8), np.ones((3, 3), np.uint8))  # 3x3 blocks of noise, 1080p
+        dimg = np.ascontiguousarray(dimg[:h, :w])
+        d_dense = torch.from_numpy(dimg).cuda()
+        for b in range(2 * NBUF):
+            inst.detect_device(d_dense.data_ptr(), w, h, b % NBUF)
+        inst.wait_idle()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_dense = 24
+        e0.record(stream)
+        for b in range(n_dense):
+            inst.detect_device(d_dense.data_ptr(), w, h, b % NBUF)
+        inst.join_lanes()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        got = inst.download_features(NBUF - 1)
+        check(got, orc.detect(dimg), "texture-rich image")
+        parity["detect_buffers_checked"] += 1
+        dense = {"workload": "1920x1080 field of 3x3 noise blocks, same configuration, %d lanes, device resident" % inst.lane_count(),
+                 "features_per_image": int(len(got)), "ms_per_image": e0.elapsed_time(e1) / n_dense,
+                 "features_per_s": len(got) * n_dense / (e0.elapsed_time(e1) * 1e-3), "parity": "checked against the oracle"}
+
     # ---------------- matcher (configs[3]); N > 1: A rows split over the ranks, B replicated ----------------
     da, db = random_descriptors(MATCH_N, 1234), random_descriptors(MATCH_N, 1235)
     a_lo, a_hi = vdist.shard_range(MATCH_N, rank, world)
@@ -704,7 +733,7 @@ def main():
                       "roofline": {"bound": "tensor", "achieved": m_ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": m_ach / tf_burst,
                                    "flops_per_gpu": 2.0 * len(fa) * MATCH_N * 128, "flops": flops,
                                    "peak_source": peak_src + " bf16 dense burst (SURVEY 8d denominator)"},
-                      "roofline_tmem_drain": tmem_drain_roofline(len(fa), MATCH_N, match_kernel_ms, clocks)},
+                      "roofline_tmem_drain": tmem_drain_roofline(len(fa), MATCH_N, match_kernel_ms, clocks, match_ms)},
             "clocks": clocks,
             "small_images": {"workload": "configs[2]: %d x 640x480 (upsampled, default config) sharded over %d GPU(s) with dist.shard_range, 8 lanes per GPU, "
                                          "images resident in HBM, CUDA events, max over ranks" % (C3_IMAGES, world),
@@ -728,6 +757,8 @@ def main():
                                                     frac=alg / (m_ms * 1e-3) / 1e9 / hbm, algorithmic_bytes=alg, peak_source=peak_src)
         if allpairs:
             line["allpairs"] = allpairs
+        if dense:
+            line["texture_rich_image"] = dense
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_port_baseline(images, args, threads=os.cpu_count() or 1)
             line["cpu_baseline"] = cb

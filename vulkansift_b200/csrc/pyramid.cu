@@ -703,9 +703,9 @@ __global__ void __launch_bounds__(FT_THREADS, ft_ctas_per_sm(R)) blur_pass_fast_
     tma_mbar_fence_init();
   }
   __syncthreads(); /* barriers initialised before anybody polls them */
-  const int t = (int)blockIdx.x;
-  const int x0 = (t % P.p.tiles_x) * FT_W;
-  const int y0 = (t / P.p.tiles_x) * TH;
+  /* grid = (tiles_x, tiles_y): no division on the way to the tile origin */
+  const int x0 = (int)blockIdx.x * FT_W;
+  const int y0 = (int)blockIdx.y * TH;
   blur_tile<R, KIND, TH, BAR_OFF, H16>(P.p, &P.p.tmap, P.taps2, ft_smem, x0, y0, 0u, true);
 }
 
@@ -865,10 +865,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) octave_fused_kernel(const __gri
 /* launch with programmatic stream serialization: the kernel may be scheduled before the previous kernel of the
  * stream has finished; it orders itself with pdl_wait() */
 template <typename P>
-static cudaError_t launch_pdl(void (*kernel)(P), int grid, int block, size_t smem, cudaStream_t st, const P &params)
+static cudaError_t launch_pdl(void (*kernel)(P), dim3 grid, int block, size_t smem, cudaStream_t st, const P &params)
 {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
+  cfg.gridDim = grid;
   cfg.blockDim = dim3((unsigned)block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -954,7 +954,7 @@ cudaError_t launch_fused(const FusedLaunch &F, cudaStream_t st)
     attr_done[dev] = true;
   }
   const int tiles = F.tiles_x * ((F.h + FZ_T - 1) / FZ_T);
-  return launch_pdl(octave_fused_kernel, tiles, FZ_THREADS, FZ_SMEM, st, F);
+  return launch_pdl(octave_fused_kernel, dim3((unsigned)tiles), FZ_THREADS, FZ_SMEM, st, F);
 }
 
 /* A pass goes to the fast per-layer kernel when its radius is covered and the layer is large enough for
@@ -1005,7 +1005,7 @@ bool blur_pass_prepare_fast(BlurPass *bpp)
 }
 
 template <int R, int KIND, bool H16>
-static cudaError_t launch_fast_rkh(const BlurPassFast &F, int n_tiles, cudaStream_t st)
+static cudaError_t launch_fast_rkh(const BlurPassFast &F, dim3 n_tiles, cudaStream_t st)
 {
   static bool attr_done[64] = {false};
   int dev = 0;
@@ -1022,13 +1022,13 @@ static cudaError_t launch_fast_rkh(const BlurPassFast &F, int n_tiles, cudaStrea
 }
 
 template <int R, int KIND>
-static cudaError_t launch_fast_rk(const BlurPassFast &F, int n_tiles, cudaStream_t st)
+static cudaError_t launch_fast_rk(const BlurPassFast &F, dim3 n_tiles, cudaStream_t st)
 {
   return F.p.fp16 ? launch_fast_rkh<R, KIND, true>(F, n_tiles, st) : launch_fast_rkh<R, KIND, false>(F, n_tiles, st);
 }
 
 template <int R>
-static cudaError_t launch_fast_r(const BlurPassFast &F, int n_tiles, cudaStream_t st)
+static cudaError_t launch_fast_r(const BlurPassFast &F, dim3 n_tiles, cudaStream_t st)
 {
   if (F.p.src_kind != BLUR_SRC_LAYER)
     return launch_fast_rk<R, FT_KIND_SEED>(F, n_tiles, st);
@@ -1046,7 +1046,7 @@ cudaError_t launch_blur_pass_fast(const BlurPass &bp, cudaStream_t st)
     const float v = (k <= bp.radius) ? bp.taps[k] : 0.f;
     F.taps2[k] = make_float2(v, v);
   }
-  const int n_tiles = bp.tiles_x * bp.tiles_y;
+  const dim3 n_tiles((unsigned)bp.tiles_x, (unsigned)bp.tiles_y);
   switch (ft_even(bp.radius))
   {
   case 2:
