@@ -253,3 +253,31 @@ def test_large_distances_follow_the_float_comparison(api, oracle_mod, impl):
     with api.Instance(max_nb_sift_per_buffer=1024) as inst:
         got = _match(api, inst, da, db, impl)
     _check(got, exp, "large distances impl %d" % impl)
+
+
+def test_back_to_back_searches_are_stream_ordered(api, oracle_mod):
+    """vksift_matchFeatures no longer waits for the previous search on the host: searches issued back to back overlap on the GPU
+    (the next MMA kernel starts under the previous merge).  The retained result is the last search's, an upload into a buffer a
+    pending search reads waits for it, and every intermediate result is still correct when fetched in between."""
+    from vulkansift_b200.synth import random_descriptors
+    d = [random_descriptors(n, 300 + i) for i, n in enumerate((1500, 2100, 900, 2600))]
+    exp = {(a, b): oracle_mod.match_descriptors(d[a], d[b]) for a, b in ((0, 1), (1, 0), (2, 3), (3, 2), (0, 3))}
+    with api.Instance(max_nb_sift_per_buffer=4096, sift_buffer_count=4, input_image_max_size=1 << 20) as inst:
+        for i in range(4):
+            inst.upload_features(_feats(api, d[i]), i)
+        for rep in range(3):  # norms cached from the second repetition on: every search may overlap its predecessor
+            for a, b in ((0, 1), (1, 0), (2, 3), (3, 2), (0, 3)):
+                inst.match(a, b)
+            assert inst.matches_number() == len(d[0])
+            _check(inst.download_matches(), exp[(0, 3)], "last of five searches, repetition %d" % rep)
+        # results fetched in between
+        for a, b in ((2, 3), (0, 1), (3, 2)):
+            inst.match(a, b)
+            _check(inst.download_matches(), exp[(a, b)], "search (%d, %d)" % (a, b))
+        # an upload into B right behind the search: the search still sees the old descriptors
+        inst.match(0, 1)
+        inst.match(1, 0)
+        inst.upload_features(_feats(api, d[2]), 0)
+        _check(inst.download_matches(), exp[(1, 0)], "search pending during an upload")
+        inst.match(0, 3)
+        _check(inst.download_matches(), oracle_mod.match_descriptors(d[2], d[3]), "search after the upload")
