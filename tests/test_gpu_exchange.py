@@ -1,7 +1,8 @@
-"""The library's descriptor exchange over peer memory (csrc/exchange.cu, vksiftx_exchange*): two processes (gloo only carries
-the 64-byte IPC handles and the barriers) share ONE GPU here -- the protocol (push into the peer's slot, flag, wait, match in
-place, double buffering over several rounds) is the same as between two GPUs over NVLink; bench.py --gpus N checks the real
-multi-GPU case against the oracle on every rank."""
+"""The library's descriptor exchange over peer memory (csrc/exchange.cu, vksiftx_exchange*): three processes (gloo only carries
+the 64-byte IPC handles and the barriers) share ONE GPU here -- the protocol (push into the peers' slots, flag, wait, zero the
+padding, ONE search against all received blocks in place, double buffering over several rounds with ragged and degenerate block
+sizes, so that slots hold stale rows of earlier, larger blocks) is the same as between GPUs over NVLink; bench.py --gpus N checks
+the real multi-GPU case against the oracle on every rank."""
 import os
 import socket
 import sys
@@ -21,7 +22,8 @@ def api():
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ROUNDS = 4
-COUNTS = [[700, 900], [1024, 2], [1, 333], [513, 640]]  # per round, per rank (a block of one row is not matched against)
+WORLD = 3
+COUNTS = [[700, 900, 300], [1024, 2, 513], [1, 333, 640], [513, 640, 129]]  # per round, per rank (a block of one row is not matched against)
 
 
 def _free_port():
@@ -57,12 +59,14 @@ def _worker(rank, world, port, out_dir):
             inst.upload_features(f, 0)
             counts, res = px.match_all_peers(0)
             assert counts == COUNTS[rnd], (counts, COUNTS[rnd])
-            peer = 1 - rank
-            if res[peer] is None:
-                assert counts[peer] < 2
-                np.save(os.path.join(out_dir, "m%d_%d.npy" % (rnd, rank)), np.zeros(0, api.MATCH_DTYPE))
-            else:
-                np.save(os.path.join(out_dir, "m%d_%d.npy" % (rnd, rank)), res[peer])
+            for peer in range(world):
+                if peer == rank:
+                    continue
+                if res[peer] is None:
+                    assert counts[peer] < 2
+                    np.save(os.path.join(out_dir, "m%d_%d_%d.npy" % (rnd, rank, peer)), np.zeros(0, api.MATCH_DTYPE))
+                else:
+                    np.save(os.path.join(out_dir, "m%d_%d_%d.npy" % (rnd, rank, peer)), res[peer])
         # the exchange alone: counts and the peer's rows, in place
         counts, ptr, stride = px.allgather(0)
         assert counts == COUNTS[ROUNDS - 1] and stride == 1024 * 128 and ptr % 128 == 0
@@ -71,18 +75,21 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_peer_memory_exchange_two_processes_match_oracle(tmp_path, oracle_mod):
+def test_peer_memory_exchange_three_processes_match_oracle(tmp_path, oracle_mod):
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(WORLD, _free_port(), str(tmp_path)), nprocs=WORLD, join=True)
     for rnd in range(ROUNDS):
-        d = [_desc(rnd, 0), _desc(rnd, 1)]
-        for rank in range(2):
-            got = np.load(tmp_path / ("m%d_%d.npy" % (rnd, rank)))
-            if len(d[1 - rank]) < 2:
-                assert len(got) == 0
-                continue
-            exp = oracle_mod.match_descriptors(d[rank], d[1 - rank])
-            assert got.dtype == exp.dtype and got.tobytes() == exp.tobytes(), "round %d rank %d" % (rnd, rank)
+        d = [_desc(rnd, r) for r in range(WORLD)]
+        for rank in range(WORLD):
+            for peer in range(WORLD):
+                if peer == rank:
+                    continue
+                got = np.load(tmp_path / ("m%d_%d_%d.npy" % (rnd, rank, peer)))
+                if len(d[peer]) < 2:
+                    assert len(got) == 0
+                    continue
+                exp = oracle_mod.match_descriptors(d[rank], d[peer])
+                assert got.dtype == exp.dtype and got.tobytes() == exp.tobytes(), "round %d rank %d peer %d" % (rnd, rank, peer)
 
 
 def test_exchange_reports_a_missing_peer_instead_of_hanging(api):

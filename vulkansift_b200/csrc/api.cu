@@ -1770,8 +1770,10 @@ extern "C"
     match_common(inst, gpu_buffer_id_A, 0, (const uint8_t *)d_descriptors_B, nb_feats_B, "vksiftx_matchFeaturesAgainstDevice");
   }
 
-  void vksiftx_matchFeaturesAgainstBlocks(vksift_Instance inst, const uint32_t gpu_buffer_id_A, const void *d_blocks, const uint32_t n_blocks,
-                                          const uint64_t block_stride_bytes, const uint32_t *counts, const uint32_t skip_block)
+  /* zero_padded: the caller guarantees zeros between every block's count and the largest count rounded up to 128 rows (the
+   * exchange does): all blocks are then searched by ONE launch of the tensor-core kernel instead of one per block */
+  static void match_blocks_common(vksift_Instance inst, const uint32_t gpu_buffer_id_A, const void *d_blocks, const uint32_t n_blocks,
+                                  const uint64_t block_stride_bytes, const uint32_t *counts, const uint32_t skip_block, const bool zero_padded)
   {
     if (!buffer_idx_valid(inst, gpu_buffer_id_A) || d_blocks == NULL || counts == NULL || n_blocks == 0 || n_blocks > 1024u ||
         ((uintptr_t)d_blocks & 127u) != 0 || (block_stride_bytes & 127u) != 0)
@@ -1831,6 +1833,24 @@ extern "C"
           CU_TRY(launch_norms_blocks((const uint8_t *)d_blocks, bc, n_blocks, stride_rows, inst->d_block_norms, inst->stream));
           inst->launches++;
         }
+        if (batched_norms && zero_padded && inst->matcher_impl == 0)
+        {
+          uint32_t blk[VKS_MAX_MATCH_BLOCKS], cnt[VKS_MAX_MATCH_BLOCKS], n_groups = 0;
+          for (uint32_t j = 0; j < n_blocks; j++)
+          {
+            if (j == skip_block || counts[j] < 2)
+            {
+              CU_TRY(cudaMemsetAsync(inst->d_matches_blocks + (size_t)j * maxf, 0, sizeof(vksift_Match_2NN) * (size_t)na, inst->stream));
+              continue;
+            }
+            blk[n_groups] = j;
+            cnt[n_groups++] = counts[j];
+          }
+          CU_TRY(launch_match_blocks(inst->match_ws, A.desc, na, A.norm_plain, (const uint8_t *)d_blocks, inst->d_block_norms, stride_rows, blk, cnt,
+                                     n_groups, inst->d_matches_blocks, (uint32_t)maxf, inst->stream, false, &inst->launches));
+          CU_TRY(cudaEventRecord(inst->ev_match_done, inst->stream));
+          return true;
+        }
         bool first_search = true;
         for (uint32_t j = 0; j < n_blocks; j++)
         {
@@ -1859,6 +1879,12 @@ extern "C"
       LOGE(TAG, "vksiftx_matchFeaturesAgainstBlocks() error: Failed to start the matching pipeline.");
       inst->cfg.on_error_callback_function(VKSIFT_VULKAN_ERROR);
     }
+  }
+
+  void vksiftx_matchFeaturesAgainstBlocks(vksift_Instance inst, const uint32_t gpu_buffer_id_A, const void *d_blocks, const uint32_t n_blocks,
+                                          const uint64_t block_stride_bytes, const uint32_t *counts, const uint32_t skip_block)
+  {
+    match_blocks_common(inst, gpu_buffer_id_A, d_blocks, n_blocks, block_stride_bytes, counts, skip_block, false);
   }
 
   void vksiftx_downloadMatchesBlocks(vksift_Instance inst, vksift_Match_2NN *matches, const uint32_t n_blocks)
@@ -1992,8 +2018,8 @@ extern "C"
     uint64_t stride = 0;
     if (!vksiftx_exchangeAllGather(inst, gpu_buffer_id, counts, &blocks, &stride))
       return false;
-    vksiftx_matchFeaturesAgainstBlocks(inst, gpu_buffer_id, blocks, (uint32_t)exchange_world(inst->exchange), stride, counts,
-                                       (uint32_t)exchange_rank(inst->exchange));
+    match_blocks_common(inst, gpu_buffer_id, blocks, (uint32_t)exchange_world(inst->exchange), stride, counts, (uint32_t)exchange_rank(inst->exchange),
+                        true);
     return true;
   }
 

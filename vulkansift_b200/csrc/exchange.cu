@@ -149,6 +149,27 @@ __global__ void exchange_wait_kernel(uint8_t *__restrict__ local, const int worl
   }
 }
 
+/* After the wait: zero the rows of every received block between its count and the largest count rounded up to a 128-row tile.
+ * One search then covers all blocks with one tensor map (launch_match_blocks), and a slot keeps rows of earlier, larger blocks. */
+__global__ void __launch_bounds__(XC_THREADS) exchange_pad_kernel(uint8_t *__restrict__ local, const int rank, const int world, const uint32_t slot_rows,
+                                                                  const uint32_t epoch)
+{
+  const int p = (int)blockIdx.x;
+  if (p == rank)
+    return;
+  const uint32_t half = epoch & 1u;
+  const uint32_t *cnt = reinterpret_cast<const uint32_t *>(local + xc_counts_off(world, slot_rows, half));
+  uint32_t mx = 0;
+  for (int q = 0; q < world; q++)
+    if (q != rank)
+      mx = max(mx, cnt[q]);
+  const uint32_t pad_to = min(slot_rows, (mx + 127u) & ~127u), n = min(cnt[p], pad_to);
+  uint4 *dst = reinterpret_cast<uint4 *>(local + xc_block_off(world, slot_rows, half, p) + (size_t)n * 128);
+  const uint32_t n16 = (pad_to - n) * 8u;
+  for (uint32_t i = threadIdx.x; i < n16; i += XC_THREADS)
+    dst[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 cudaError_t exchange_create(PeerExchange **out, int rank, int world, uint32_t slot_rows, void *handle)
 {
   if (world < 1 || world > VKS_MAX_PEERS || rank < 0 || rank >= world || slot_rows == 0 || (slot_rows % 128u) != 0)
@@ -221,7 +242,8 @@ cudaError_t exchange_allgather(PeerExchange *x, const uint8_t *desc, uint32_t n,
   exchange_publish_kernel<<<dim3(chunks, (unsigned)x->world), XC_THREADS, 0, st>>>(peers, x->rank, x->world, x->slot_rows, x->epoch, desc, n, rows_per_cta,
                                                                                    x->d_done);
   exchange_wait_kernel<<<1, 32, 0, st>>>(x->local, x->world, x->slot_rows, x->epoch, x->h_counts_dev);
-  *launch_count += 2;
+  exchange_pad_kernel<<<(unsigned)x->world, XC_THREADS, 0, st>>>(x->local, x->rank, x->world, x->slot_rows, x->epoch);
+  *launch_count += 3;
   return cudaGetLastError();
 }
 

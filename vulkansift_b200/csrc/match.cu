@@ -322,4 +322,25 @@ cudaError_t launch_match(MatchWorkspace *ws, int impl, const uint8_t *da, uint32
   return match_tc_launch(ws->tc, da, na, norm_a, db, nb, norm_b, out, st, inputs_settled, launch_count);
 }
 
+cudaError_t launch_match_blocks(MatchWorkspace *ws, const uint8_t *da, uint32_t na, const uint32_t *norm_a, const uint8_t *blocks,
+                                const uint32_t *norm_blocks, uint32_t stride_rows, const uint32_t *blk, const uint32_t *cnt, uint32_t n_groups,
+                                vksift_Match_2NN *out, uint32_t out_stride, cudaStream_t st, bool inputs_settled, uint64_t *launch_count)
+{
+  if (na == 0 || n_groups == 0)
+    return cudaSuccess;
+  if (n_groups > MT_MAX_GROUPS || (stride_rows % MT_N) != 0)
+    return cudaErrorInvalidValue;
+  MatchGroups G;
+  memset(&G, 0, sizeof(G));
+  G.n_groups = n_groups;
+  G.stride_rows = stride_rows;
+  G.out_stride = out_stride;
+  for (uint32_t g = 0; g < n_groups; g++)
+  {
+    G.blk[g] = blk[g];
+    G.cnt[g] = cnt[g];
+  }
+  return match_tc_launch_groups(ws->tc, da, na, norm_a, blocks, norm_blocks, out, G, st, inputs_settled, launch_count);
+}
+
 } // namespace vks

@@ -144,6 +144,21 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr)
 
 __device__ __forceinline__ uint32_t mt_pos(uint32_t b) { return b < 2u ? (b ^ 1u) : b; }
 
+/* One launch searches buffer A against up to MT_MAX_GROUPS descriptor blocks ("groups") that lie in one allocation at a
+ * common stride: the all-pairs step (A against the blocks received from every peer).  A "virtual row block" v = (group g,
+ * row block rb) takes the A tile of rb and the B tiles of block blk[g]; everything that was indexed by the row block
+ * (segments, partial keys) is indexed by v.  A single search is one group at block 0. */
+#define MT_MAX_GROUPS 64
+struct MatchGroups
+{
+  uint32_t n_groups;
+  uint32_t stride_rows;        /* rows between the starts of consecutive blocks (multiple of MT_N) */
+  uint32_t out_stride;         /* records between the result lists of consecutive blocks */
+  uint32_t row_blocks;         /* row blocks of A */
+  uint32_t blk[MT_MAX_GROUPS]; /* block index of group g */
+  uint32_t cnt[MT_MAX_GROUPS]; /* rows of that block */
+};
+
 /* ---- main kernel ----------------------------------------------------------
  * Work unit = (row block of 128 A rows, B tile of 128 rows); units are numbered row-block major and cut into
  * equal contiguous ranges, one per CTA, so that 2 CTAs per SM all carry the same load whatever nA/128 is.
@@ -152,7 +167,7 @@ __device__ __forceinline__ uint32_t mt_pos(uint32_t b) { return b < 2u ? (b ^ 1u
 __global__ void __launch_bounds__(MT_THREADS, 2)
     match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const uint32_t *__restrict__ norm_a,
                     const uint32_t *__restrict__ norm_b, uint32_t na, uint32_t n_tiles, uint32_t units_per_cta, uint32_t total_units,
-                    uint32_t max_segs, unsigned long long *__restrict__ partial, int32_t key_scale)
+                    uint32_t max_segs, unsigned long long *__restrict__ partial, int32_t key_scale, const __grid_constant__ MatchGroups G)
 {
   extern __shared__ uint8_t smem_raw[];
   /* 1024-byte alignment required by SWIZZLE_128B */
@@ -216,17 +231,18 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
       for (uint32_t t = 0; t < my_tiles; t++)
       {
-        const uint32_t u = u0 + t, rb = u / n_tiles, tile = u - rb * n_tiles;
+        const uint32_t u = u0 + t, rb = u / n_tiles, tile = u - rb * n_tiles; /* rb: VIRTUAL row block (group, row block of A) */
+        const uint32_t grp = rb / G.row_blocks;
         if (t == 0 || tile == 0)
         {
           const uint32_t seg = rb - rb_first;
           mbar_wait(BAR_EMPTY_A, (seg & 1u) ^ 1u); /* previous segment's MMAs are done with the A tile */
           mbar_expect_tx(BAR_FULL_A, MT_M * 128);
-          tma_load_2d(smem_u32(s_a), &map_a, 0, (int)(rb * MT_M), BAR_FULL_A);
+          tma_load_2d(smem_u32(s_a), &map_a, 0, (int)((rb - grp * G.row_blocks) * MT_M), BAR_FULL_A);
         }
         const uint32_t st = t % MT_STAGES, ph = (t / MT_STAGES) & 1u;
         mbar_wait(BAR_EMPTY_B(st), ph ^ 1u);
-        const uint32_t b0 = tile * MT_N;
+        const uint32_t b0 = G.blk[grp] * G.stride_rows + tile * MT_N; /* row of the tile in the allocation of all blocks */
         mbar_expect_tx(BAR_FULL_B(st), MT_TILE_BYTES + MT_N * 4);
         tma_load_2d(smem_u32(s_b + st * MT_TILE_BYTES), &map_b, 0, (int)b0, BAR_FULL_B(st));
         bulk_load_1d(smem_u32(s_nb + st * MT_N), norm_b + b0, MT_N * 4, BAR_FULL_B(st));
@@ -309,7 +325,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2)
           k1 = k2 = ~0ull;
         }
         cur_rb = rb;
-        const uint32_t row = rb * MT_M + lrow;
+        const uint32_t row = (rb % G.row_blocks) * MT_M + lrow;
         my_na = (row < na) ? (int32_t)norm_a[row] : 0;
       }
       const uint32_t st = t % MT_STAGES, ph = (t / MT_STAGES) & 1u;
@@ -424,10 +440,10 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k)
 
 #define MG_WARPS 8
 __global__ void __launch_bounds__(32 * MG_WARPS) match_merge_kernel(const unsigned long long *__restrict__ partial, uint32_t n_tiles,
-                                                                    uint32_t units_per_cta, uint32_t max_segs, uint32_t na, uint32_t nb,
-                                                                    const uint8_t *__restrict__ da, const uint8_t *__restrict__ db,
-                                                                    const uint32_t *__restrict__ norm_a, const uint32_t *__restrict__ norm_b,
-                                                                    vksift_Match_2NN *__restrict__ out)
+                                                                    uint32_t units_per_cta, uint32_t max_segs, uint32_t na,
+                                                                    const uint8_t *__restrict__ da, const uint8_t *__restrict__ db_all,
+                                                                    const uint32_t *__restrict__ norm_a, const uint32_t *__restrict__ norm_b_all,
+                                                                    vksift_Match_2NN *__restrict__ out_all, const __grid_constant__ MatchGroups G)
 {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   /* the MMA kernel of the next search may start now (it touches the partial keys only after this grid has completed) */
@@ -435,6 +451,11 @@ __global__ void __launch_bounds__(32 * MG_WARPS) match_merge_kernel(const unsign
   const uint32_t row = blockIdx.x * MG_WARPS + (uint32_t)warp;
   if (row >= na)
     return;
+  /* blockIdx.y = group: the block of B this list is for */
+  const uint32_t grp = blockIdx.y, blk = G.blk[grp], nb = G.cnt[grp];
+  const uint8_t *__restrict__ db = db_all + (size_t)blk * G.stride_rows * 128;
+  const uint32_t *__restrict__ norm_b = norm_b_all + (size_t)blk * G.stride_rows;
+  vksift_Match_2NN *__restrict__ out = out_all + (size_t)blk * G.out_stride;
   const int half = lane & 1;
   /* this lane's half of the A row, for the rescan below: independent of the fold, so the loads go out first */
   uint4 va[4];
@@ -446,7 +467,7 @@ __global__ void __launch_bounds__(32 * MG_WARPS) match_merge_kernel(const unsign
   }
   const uint32_t my_na = __ldg(norm_a + row);
   asm volatile("griddepcontrol.wait;" ::: "memory"); /* everything above only reads inputs of the match call */
-  const uint32_t rb = row / MT_M, lrow = row - rb * MT_M;
+  const uint32_t rb = grp * G.row_blocks + row / MT_M, lrow = row % MT_M; /* virtual row block, like the MMA kernel */
   const uint32_t first_cta = (rb * n_tiles) / units_per_cta, last_cta = ((rb + 1) * n_tiles - 1) / units_per_cta;
   const uint32_t n_keys = (last_cta - first_cta + 1) * 2 * 2; /* segments x warpgroups x (k1, k2) */
   /* every lane folds its share of the partial keys (one key per lane unless a row block has more than 8 segments) */
@@ -625,24 +646,38 @@ static bool mt_make_map(MatchTc *tc, CUtensorMap *map, const uint8_t *base, uint
   return r == CUDA_SUCCESS;
 }
 
-/* overlap_previous: nothing this search reads (descriptors, norms) was written by the work enqueued just before it on `st`,
+/* groups: the blocks of B to search (MatchGroups: n_groups, blk[], cnt[], stride_rows, out_stride filled by the caller).  db_all /
+ * norm_b_all / out_all address block 0.  With more than one group the rows of every block between its count and the largest
+ * count rounded up to a tile MUST be zero (the tensor map spans all blocks, so TMA does not zero them): the caller's contract.
+ * overlap_previous: nothing this search reads (descriptors, norms) was written by the work enqueued just before it on `st`,
  * so the MMA kernel is launched programmatically dependent: behind the merge kernel of a previous search it starts while that
  * one still runs, and waits for it only before it publishes its partial keys. */
-static cudaError_t match_tc_launch(void *p, const uint8_t *da, uint32_t na, const uint32_t *norm_a, const uint8_t *db, uint32_t nb,
-                                   const uint32_t *norm_b, vksift_Match_2NN *out, cudaStream_t st, bool overlap_previous, uint64_t *launch_count)
+static cudaError_t match_tc_launch_groups(void *p, const uint8_t *da, uint32_t na, const uint32_t *norm_a, const uint8_t *db_all,
+                                          const uint32_t *norm_b_all, vksift_Match_2NN *out_all, MatchGroups G, cudaStream_t st, bool overlap_previous,
+                                          uint64_t *launch_count)
 {
   MatchTc *tc = (MatchTc *)p;
+  if (G.n_groups == 0 || G.n_groups > MT_MAX_GROUPS)
+    return cudaErrorInvalidValue;
   const uint32_t row_blocks = (na + MT_M - 1) / MT_M;
-  const uint32_t n_tiles = (nb + MT_N - 1) / MT_N;
+  uint32_t max_cnt = 0, max_blk = 0;
+  for (uint32_t g = 0; g < G.n_groups; g++)
+  {
+    max_cnt = G.cnt[g] > max_cnt ? G.cnt[g] : max_cnt;
+    max_blk = G.blk[g] > max_blk ? G.blk[g] : max_blk;
+  }
+  const uint32_t n_tiles = (max_cnt + MT_N - 1) / MT_N;
+  G.row_blocks = row_blocks;
+  const uint32_t v_blocks = G.n_groups * row_blocks; /* virtual row blocks */
   /* two CTAs are resident per SM: one full wave of equally loaded CTAs */
-  const uint32_t total_units = row_blocks * n_tiles;
+  const uint32_t total_units = v_blocks * n_tiles;
   uint32_t n_cta = 2u * (uint32_t)tc->sm_count;
   if (n_cta > total_units)
     n_cta = total_units;
   const uint32_t units_per_cta = (total_units + n_cta - 1) / n_cta;
   n_cta = (total_units + units_per_cta - 1) / units_per_cta;
   const uint32_t max_segs = (n_tiles + units_per_cta - 1) / units_per_cta + 1;
-  const size_t need = (size_t)row_blocks * max_segs * 2 * MT_M * 2;
+  const size_t need = (size_t)v_blocks * max_segs * 2 * MT_M * 2;
   if (need > tc->partial_elems)
   {
     /* grows only when a larger problem shows up; stream-ordered with respect to earlier matches */
@@ -655,8 +690,11 @@ static cudaError_t match_tc_launch(void *p, const uint8_t *da, uint32_t na, cons
       return e;
     tc->partial_elems = need;
   }
+  /* one group: the map ends at the block's last row and TMA zero-fills the rest of its last tile; several groups: the map spans
+   * every block up to the last tile any of them needs */
+  const uint32_t map_b_rows = G.n_groups == 1 ? G.blk[0] * G.stride_rows + G.cnt[0] : max_blk * G.stride_rows + n_tiles * MT_N;
   CUtensorMap map_a, map_b;
-  if (!mt_make_map(tc, &map_a, da, na, MT_M) || !mt_make_map(tc, &map_b, db, nb, MT_N))
+  if (!mt_make_map(tc, &map_a, da, na, MT_M) || !mt_make_map(tc, &map_b, db_all, map_b_rows, MT_N))
     return cudaErrorInvalidValue;
   cudaError_t e;
   {
@@ -672,13 +710,14 @@ static cudaError_t match_tc_launch(void *p, const uint8_t *da, uint32_t na, cons
     cfg.numAttrs = overlap_previous ? 1 : 0;
     unsigned long long *partial = tc->partial;
     const int32_t key_scale = -512;
-    e = cudaLaunchKernelEx(&cfg, match_tc_kernel, map_a, map_b, norm_a, norm_b, na, n_tiles, units_per_cta, total_units, max_segs, partial, key_scale);
+    e = cudaLaunchKernelEx(&cfg, match_tc_kernel, map_a, map_b, norm_a, norm_b_all, na, n_tiles, units_per_cta, total_units, max_segs, partial,
+                           key_scale, G);
   }
   if (e != cudaSuccess)
     return e;
   {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((na + MG_WARPS - 1) / MG_WARPS);
+    cfg.gridDim = dim3((na + MG_WARPS - 1) / MG_WARPS, G.n_groups);
     cfg.blockDim = dim3(32 * MG_WARPS);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -687,10 +726,20 @@ static cudaError_t match_tc_launch(void *p, const uint8_t *da, uint32_t na, cons
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const unsigned long long *partial_c = tc->partial;
-    e = cudaLaunchKernelEx(&cfg, match_merge_kernel, partial_c, n_tiles, units_per_cta, max_segs, na, nb, da, db, norm_a, norm_b, out);
+    e = cudaLaunchKernelEx(&cfg, match_merge_kernel, partial_c, n_tiles, units_per_cta, max_segs, na, da, db_all, norm_a, norm_b_all, out_all, G);
   }
   *launch_count += 2;
   return e;
+}
+
+static cudaError_t match_tc_launch(void *p, const uint8_t *da, uint32_t na, const uint32_t *norm_a, const uint8_t *db, uint32_t nb,
+                                   const uint32_t *norm_b, vksift_Match_2NN *out, cudaStream_t st, bool overlap_previous, uint64_t *launch_count)
+{
+  MatchGroups G;
+  memset(&G, 0, sizeof(G));
+  G.n_groups = 1;
+  G.cnt[0] = nb;
+  return match_tc_launch_groups(p, da, na, norm_a, db, norm_b, out, G, st, overlap_previous, launch_count);
 }
 
 } // namespace vks

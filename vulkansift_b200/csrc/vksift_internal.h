@@ -242,6 +242,13 @@ struct MatchBlockCounts
 cudaError_t launch_norms_blocks(const uint8_t *desc, const MatchBlockCounts &counts, uint32_t n_blocks, uint32_t stride_rows, uint32_t *out_packed,
                                 cudaStream_t st);
 
+/* ONE search of A against n_groups of the blocks (group g = block blk[g] with cnt[g] rows, blocks at a common stride of
+ * stride_rows rows, packed norms laid out the same way; result list of block j at out + j * out_stride).  Tensor-core path only.
+ * Contract: in every searched block the rows between its count and the largest count rounded up to 128 are ZERO. */
+cudaError_t launch_match_blocks(MatchWorkspace *ws, const uint8_t *desc_a, uint32_t na, const uint32_t *norm_a, const uint8_t *blocks,
+                                const uint32_t *norm_blocks, uint32_t stride_rows, const uint32_t *blk, const uint32_t *cnt, uint32_t n_groups,
+                                vksift_Match_2NN *out, uint32_t out_stride, cudaStream_t st, bool inputs_settled, uint64_t *launch_count);
+
 cudaError_t launch_match_filter(const vksift_Match_2NN *m12, uint32_t na, const vksift_Match_2NN *m21, uint32_t nb, float ratio, uint32_t *pairs,
                                 uint32_t capacity, uint32_t *count, cudaStream_t st);
 
@@ -250,6 +257,8 @@ cudaError_t launch_match_filter(const vksift_Match_2NN *m12, uint32_t na, const 
 struct PeerExchange;
 cudaError_t exchange_create(PeerExchange **out, int rank, int world, uint32_t slot_rows, void *handle64);
 cudaError_t exchange_connect(PeerExchange *x, const void *handles);
+/* push + wait; the rows of every received block between its count and the largest count rounded up to 128 are zeroed
+ * (launch_match_blocks relies on it) */
 cudaError_t exchange_allgather(PeerExchange *x, const uint8_t *desc, uint32_t n, cudaStream_t st, uint64_t *launch_count);
 const uint32_t *exchange_host_counts(const PeerExchange *x);
 uint32_t exchange_timeout_mask(const PeerExchange *x);
