@@ -681,7 +681,7 @@ def main():
         dist.all_reduce(rows, op=dist.ReduceOp.SUM)
         allpairs = {"workload": "one 1920x1080 image per GPU; every GPU pushes its descriptor block into a 4096-row slot on every peer over NVLink "
                                 "peer memory (one kernel, completion flags in peer memory: vksiftx_exchangeMatchAllPeers) and matches its features "
-                                "against each of the %d received blocks in place, one enqueue and one download (ordered pairs: %d); wall clock, "
+                                "against the %d received blocks in place with ONE launch of the tensor-core search and one download (ordered pairs: %d); wall clock, "
                                 "median of %d, max over ranks" % (world - 1, world * (world - 1), reps),
                     "value": rows.item() / ap[3].item(), "unit": "matches/s", "ms_total": 1e3 * ap[3].item(),
                     "ms_gather": 1e3 * ap[4].item(), "ms_match_and_download": 1e3 * (ap[3].item() - ap[4].item()), "matched_rows": rows.item(),
