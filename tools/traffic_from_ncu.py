@@ -24,7 +24,7 @@ def main(rep, out):
         grid = r[idx["Grid Size"]]
         targs = name.split("<")[1].split(">")[0].split(",") if "<" in name else []
         is_layer = len(targs) >= 2 and targs[1].strip().lstrip("(int)") != "0"  # template arguments <R, KIND, H16>: KIND 0 = seed pass
-        if "blur_pass_fast_kernel" in name and is_layer and "2040" in grid:  # octave 0 = 60 x 34 tiles
+        if "blur_pass_fast_kernel" in name and is_layer and ("2040" in grid or "(60, 34" in grid):  # octave 0 = 60 x 34 tiles
             per.append({"kernel": name.split("(")[0], "read": mb(r, "dram__bytes_read.sum"), "write": mb(r, "dram__bytes_write.sum"),
                         "us": float(r[idx["gpu__time_duration.sum"]].replace(",", ""))})
     res = {"source": rep, "launches": per}
