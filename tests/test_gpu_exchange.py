@@ -21,9 +21,9 @@ def api():
     return a
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ROUNDS = 4
+ROUNDS = 5
 WORLD = 3
-COUNTS = [[700, 900, 300], [1024, 2, 513], [1, 333, 640], [513, 640, 129]]  # per round, per rank (a block of one row is not matched against)
+COUNTS = [[700, 900, 300], [1024, 2, 513], [1, 333, 640], [513, 640, 129], [40, 300, 170]]  # per round, per rank (a block of one row is not matched against)
 
 
 def _free_port():
@@ -37,7 +37,18 @@ def _free_port():
 def _desc(rnd, rank):
     sys.path.insert(0, ROOT)
     from vulkansift_b200.synth import random_descriptors
-    return random_descriptors(COUNTS[rnd][rank], 1000 + 10 * rnd + rank)
+    n = COUNTS[rnd][rank]
+    if rnd == 4:
+        # distances beyond d^2 = 2^22 with float-sqrt collisions (test_large_distances_follow_the_float_comparison): rank 0 against the
+        # others goes through the float-order rescan of the grouped search
+        rng = np.random.default_rng(40 + rank)
+        d = np.zeros((n, 128), np.uint8)
+        if rank > 0:
+            d[:, :73] = 255
+            d[:, 73] = 68
+        d[:, 127] = rng.integers(0, 2, n)
+        return d
+    return random_descriptors(n, 1000 + 10 * rnd + rank)
 
 
 def _worker(rank, world, port, out_dir):
