@@ -238,15 +238,17 @@ __host__ __device__ constexpr int ft_in_h(int R, int TH = FT_H) { return TH + 2 
 #define FT_BOX_H 8 /* rows per TMA request: 8 rows of a stride that is a multiple of 4 floats keep every destination 128-byte aligned */
 __host__ __device__ constexpr int ft_n_box(int R, int TH = FT_H) { return (ft_in_h(R, TH) + FT_BOX_H - 1) / FT_BOX_H; }
 __host__ __device__ constexpr int ft_in_ha(int R, int TH = FT_H) { return ft_n_box(R, TH) * FT_BOX_H; } /* rows allocated for the source tile */
-/* Tile height of the per-layer launches.  A tile runs in phases (TMA wait, horizontal pass, barrier, vertical pass) and only other
- * CTAs of the SM fill the gaps, so residency decides: 64 rows for R <= 8 (four CTAs per SM; 96-row tiles would leave three).  For
- * R >= 10 the registers allow three CTAs either way, and 96 rows win: 25 % halo rows instead of 37 %, 15 eight-row units of the
- * horizontal pass over 8 warps (94 % balanced) instead of 11 (69 %), 10 % fewer instructions; measured with 8 detections in
- * flight 0.3125 against 0.3151 ms per image (64 rows everywhere) and 0.3131 (96 rows from R = 8 on). */
-__host__ __device__ constexpr int ft_tile_h(int R) { return R >= 10 ? 96 : 64; }
-__host__ __device__ constexpr int ft_ctas_per_sm(int R) { return R <= 8 ? 4 : 3; }
+/* Tile height and residency of the per-layer launches.  A tile runs in phases (TMA wait, horizontal pass, barrier, vertical
+ * pass) and only other CTAs of the SM fill the gaps, so residency decides (measured with 8 detections in flight, ms per
+ * 1920x1080 image): 64-row tiles with 4 / 4 / 3 CTAs per SM for R = 4 / 6-8 / 10-12: 0.3151;  96-row tiles for R >= 10 (fewer
+ * halo rows, balanced horizontal pass, still 3 CTAs): 0.3125;  five CTAs for R = 4 (48 registers, 41 KB): 0.3080;  64-row tiles
+ * and FOUR CTAs for R >= 10 (64 registers without spills, 55-57 KB): 0.3046 -- occupancy beats the 12 % of instructions the
+ * taller tiles save. */
+__host__ __device__ constexpr int ft_tile_h(int R) { return R >= 0 ? 64 : 64; }
+__host__ __device__ constexpr int ft_ctas_per_sm(int R) { return R <= 4 ? 5 : 4; }
 __host__ __device__ constexpr int ft_bar_off(int R, int TH) { return ft_in_ha(R, TH) * ft_s(R) + ft_in_h(R, TH) * FT_MS; }
-__host__ __device__ constexpr int ft_smem_bytes(int R, int TH) { return 4 * ft_bar_off(R, TH) + 8 * FT_NB + 1024; }
+/* the 1 KB UNORM table only exists in the seed pass: without it four CTAs of the R = 12 layer kernel fit an SM (57 344 bytes each) */
+__host__ __device__ constexpr int ft_smem_bytes(int R, int TH, int KIND) { return 4 * ft_bar_off(R, TH) + 8 * FT_NB + (KIND == 0 ? 1024 : 0); }
 /* source tile, horizontal-pass result, TMA barriers, UNORM table of the seed pass */
 /* one shared-memory layout for every radius (a persistent CTA runs tiles of several layers): source tile and
  * horizontal-pass result sized by R inside the first FT_BAR_OFF floats, then the TMA barriers and the UNORM table */
@@ -1014,12 +1016,12 @@ static cudaError_t launch_fast_rkh(const BlurPassFast &F, dim3 n_tiles, cudaStre
   if (dev < 64 && !attr_done[dev])
   {
     cudaError_t e =
-        cudaFuncSetAttribute(blur_pass_fast_kernel<R, KIND, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes(R, ft_tile_h(R)));
+        cudaFuncSetAttribute(blur_pass_fast_kernel<R, KIND, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ft_smem_bytes(R, ft_tile_h(R), KIND));
     if (e != cudaSuccess)
       return e;
     attr_done[dev] = true;
   }
-  return launch_pdl(blur_pass_fast_kernel<R, KIND, H16>, n_tiles, FT_THREADS, ft_smem_bytes(R, ft_tile_h(R)), st, F);
+  return launch_pdl(blur_pass_fast_kernel<R, KIND, H16>, n_tiles, FT_THREADS, ft_smem_bytes(R, ft_tile_h(R), KIND), st, F);
 }
 
 template <int R, int KIND>
