@@ -188,6 +188,7 @@ struct vksift_Instance_T
   vksift_Match_2NN *d_matches_blocks = nullptr; /* [blocks_cap][max_nb_sift_per_buffer]: results of vksiftx_matchFeaturesAgainstBlocks */
   uint32_t blocks_cap = 0, blocks_n = 0, blocks_na = 0;
   uint32_t *d_block_norms = nullptr; /* packed B-side norms of all blocks of such a call, one launch */
+  int ori_ctas = 4;                  /* resident CTAs per SM of the orientation kernel */
   PeerExchange *exchange = nullptr;  /* NVLink peer-memory all-gather of descriptor blocks (vksiftx_exchange*) */
   size_t block_norms_cap = 0;
   uint32_t *d_pairs = nullptr;               /* [2*max + 1]: filtered pairs, count at the end */
@@ -799,6 +800,7 @@ bool create_resources(vksift_Instance inst)
     const char *nsp = getenv("VKSIFT_NO_SPLIT");
     inst->no_split = (nsp && nsp[0] == '1');
     inst->use_graph = (g ? g[0] == '1' : n_lanes > 1);
+    inst->ori_ctas = n_lanes > 1 ? 2 : 4; /* throughput with several detections in flight, latency with one (launch_orientation) */
     if (inst->primary)
       inst->use_graph = inst->primary->use_graph;
   }
@@ -1011,7 +1013,7 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
       CU_TRY(launch_extrema(Q, inst->extrema_plan, fb.cnt, inst->prim, s, &inst->launches));
     }
     if (!(VKS_SKIP(inst) & 2))
-      CU_TRY(launch_orientation(Q, fb.cnt, inst->prim, inst->ori, inst->n_ori, s));
+      CU_TRY(launch_orientation(Q, fb.cnt, inst->prim, inst->ori, inst->n_ori, s, inst->ori_ctas));
     inst->launches += 1;
     return true;
   };
@@ -1158,7 +1160,7 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D2], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   if (!(VKS_SKIP(inst) & 2))
-    CU_TRY(launch_orientation(PA, fb.cnt, inst->prim, inst->ori, inst->n_ori, st));
+    CU_TRY(launch_orientation(PA, fb.cnt, inst->prim, inst->ori, inst->n_ori, st, inst->ori_ctas));
   inst->launches++;
   if (split)
   {

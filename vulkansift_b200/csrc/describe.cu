@@ -28,7 +28,7 @@ __device__ __forceinline__ float gauss_at(const void *__restrict__ L, int fp16, 
 }
 
 /* ---- orientation --------------------------------------------------------- */
-#define ORI_THREADS 128
+#define ORI_THREADS 64
 #define ORI_TERMS 2048 /* terms of the fixed-point scale staged per chunk */
 
 /* One CTA per keypoint.  The reference runs one 32-thread work group per keypoint in which EVERY thread
@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(ORI_THREADS) orientation_kernel(const __grid_c
       if (tid < 36)
         hist[tid] = 0;
       __syncthreads();
-      m = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+      m = 0.f;
+#pragma unroll
+      for (int k = 0; k < ORI_THREADS / 32; k++)
+        m += s_part[k];
       const float frac = __uint_as_float((__float_as_uint(m) & 0x007fffffu) | 0x3f800000u); /* mantissa as a value in [1, 2) */
       const float delta = 1e-4f + (float)n_terms * 2.4e-7f;
       if (!(frac > 1.f + delta && frac < 2.f - 2.f * delta))
@@ -214,16 +217,22 @@ __global__ void __launch_bounds__(ORI_THREADS) orientation_kernel(const __grid_c
   }
 }
 
-cudaError_t launch_orientation(const DetectParams &P, DetectCounters *cnt, const FeatHead *prim, float *ori, uint32_t *n_ori, cudaStream_t st)
+/* ctas_per_sm: the grid is persistent (a CTA walks the keypoints with the grid's stride).  A keypoint is a latency chain that leaves its
+ * CTA's slots mostly idle, so MORE resident CTAs take issue and thread slots from the kernels of the other detections in flight:
+ * measured with 8 lanes 0.3015 / 0.2968 / 0.2947 / 0.2934 / 0.2920 ms per image for 32 / 16 / 8 / 4 / 2 CTAs of 64 threads per SM; a
+ * detection alone is fastest with 3-4 (0.450 ms against 0.470 with 2). */
+cudaError_t launch_orientation(const DetectParams &P, DetectCounters *cnt, const FeatHead *prim, float *ori, uint32_t *n_ori, cudaStream_t st,
+                               int ctas_per_sm)
 {
-  static int per_sm = 0;
-  if (per_sm == 0)
+  static int env_per_sm = -1;
+  if (env_per_sm < 0)
   {
     const char *e = getenv("VKSIFT_ORI_CTAS");
-    per_sm = e ? atoi(e) : 8;
-    if (per_sm < 1 || per_sm > 16)
-      per_sm = 8;
+    env_per_sm = e ? atoi(e) : 0;
+    if (env_per_sm < 0 || env_per_sm > 32)
+      env_per_sm = 0;
   }
+  const int per_sm = env_per_sm ? env_per_sm : (ctas_per_sm >= 1 && ctas_per_sm <= 32 ? ctas_per_sm : 4);
   orientation_kernel<<<148 * per_sm, ORI_THREADS, 0, st>>>(P, cnt, prim, ori, n_ori);
   return cudaGetLastError();
 }

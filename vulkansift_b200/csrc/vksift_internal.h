@@ -209,7 +209,8 @@ cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectC
 /* also: the octaves' shares (q_off / q_cap) of an extrema queue of queue_total entries */
 void extrema_layout(DetectParams *P, size_t *bm_words, size_t *rows, size_t *queue_entries, uint32_t queue_total);
 bool extrema_scales_supported(int ns);
-cudaError_t launch_orientation(const DetectParams &P, DetectCounters *cnt, const FeatHead *prim, float *ori, uint32_t *n_ori, cudaStream_t st);
+cudaError_t launch_orientation(const DetectParams &P, DetectCounters *cnt, const FeatHead *prim, float *ori, uint32_t *n_ori, cudaStream_t st,
+                               int ctas_per_sm);
 cudaError_t launch_assemble(const DetectParams &P, DetectCounters *cnt, const uint32_t *n_ori, uint32_t *feat_src, uint32_t *host_counts,
                             cudaStream_t st);
 /* table of the descriptor's fixed-point scale sums M(R/2) (ComputeDescriptors.comp:116-124 only depends on the window radius) */
