@@ -189,6 +189,11 @@ struct vksift_Instance_T
   uint32_t blocks_cap = 0, blocks_n = 0, blocks_na = 0;
   uint32_t *d_block_norms = nullptr; /* packed B-side norms of all blocks of such a call, one launch */
   int ori_ctas = 4;                  /* resident CTAs per SM of the orientation kernel */
+  int scan_ctas = 0;                 /* persistent CTAs of the extrema scan, 0 = two per SM */
+  /* Set per detection: other lanes hold detections the caller has not waited for, i.e. the GPU is shared.  The latency-bound
+   * kernels then run on small grids (scan_ctas, ori_ctas) and leave the SMs to the issue-bound kernels of the other detections;
+   * a detection that has the GPU to itself uses the full grids.  Either mode produces the same results. */
+  bool crowded = false;
   PeerExchange *exchange = nullptr;  /* NVLink peer-memory all-gather of descriptor blocks (vksiftx_exchange*) */
   size_t block_norms_cap = 0;
   uint32_t *d_pairs = nullptr;               /* [2*max + 1]: filtered pairs, count at the end */
@@ -801,6 +806,8 @@ bool create_resources(vksift_Instance inst)
     inst->no_split = (nsp && nsp[0] == '1');
     inst->use_graph = (g ? g[0] == '1' : n_lanes > 1);
     inst->ori_ctas = n_lanes > 1 ? 2 : 4; /* throughput with several detections in flight, latency with one (launch_orientation) */
+    /* extrema scan CTAs (launch_extrema): 296 alone, 74 with two lanes, 37 with four, 24 from six lanes on */
+    inst->scan_ctas = n_lanes > 1 ? (int)(148u / n_lanes > 24u ? 148u / n_lanes : 24u) : 0;
     if (inst->primary)
       inst->use_graph = inst->primary->use_graph;
   }
@@ -848,7 +855,7 @@ bool create_resources(vksift_Instance inst)
     CU_TRY(cudaMemcpy(inst->desc_m_table, h_table, sizeof(h_table), cudaMemcpyHostToDevice));
   }
   CU_TRY(cudaMalloc(&inst->d_aos, sizeof(vksift_Feature) * maxf));
-  inst->graphs.resize(c.sift_buffer_count);
+  inst->graphs.resize(2 * (size_t)c.sift_buffer_count);
   if (inst->primary)
   {
     /* a secondary lane: detection only, on the primary's feature buffers */
@@ -1010,10 +1017,10 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
     Q.oe = oe;
     if (!(VKS_SKIP(inst) & 4))
     {
-      CU_TRY(launch_extrema(Q, inst->extrema_plan, fb.cnt, inst->prim, s, &inst->launches));
+      CU_TRY(launch_extrema(Q, inst->extrema_plan, fb.cnt, inst->prim, s, &inst->launches, inst->crowded ? inst->scan_ctas : 0));
     }
     if (!(VKS_SKIP(inst) & 2))
-      CU_TRY(launch_orientation(Q, fb.cnt, inst->prim, inst->ori, inst->n_ori, s, inst->ori_ctas));
+      CU_TRY(launch_orientation(Q, fb.cnt, inst->prim, inst->ori, inst->n_ori, s, inst->crowded ? inst->ori_ctas : 4));
     inst->launches += 1;
     return true;
   };
@@ -1155,12 +1162,12 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
   MarkerRegion mr_feat(inst, "ExtractKeypoints + ComputeOrientation + ComputeDescriptors + CopySiftCount");
   if (!(VKS_SKIP(inst) & 4))
   {
-    CU_TRY(launch_extrema(PA, inst->extrema_plan, fb.cnt, inst->prim, st, &inst->launches));
+    CU_TRY(launch_extrema(PA, inst->extrema_plan, fb.cnt, inst->prim, st, &inst->launches, inst->crowded ? inst->scan_ctas : 0));
   }
   if (prof)
     CU_TRY(cudaEventRecordWithFlags(inst->ev[EV_D2], st, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   if (!(VKS_SKIP(inst) & 2))
-    CU_TRY(launch_orientation(PA, fb.cnt, inst->prim, inst->ori, inst->n_ori, st, inst->ori_ctas));
+    CU_TRY(launch_orientation(PA, fb.cnt, inst->prim, inst->ori, inst->n_ori, st, inst->crowded ? inst->ori_ctas : 4));
   inst->launches++;
   if (split)
   {
@@ -1197,7 +1204,7 @@ bool enqueue_detection(vksift_Instance inst, const uint8_t *d_image, uint32_t bu
   FeatureBuffer &fb = inst->buffers[buf];
   cudaStream_t st = inst->stream;
   *inst->h_src_slot = d_image;
-  auto &g = inst->graphs[buf];
+  auto &g = inst->graphs[2 * buf + (inst->crowded ? 1 : 0)]; /* one graph per grid policy */
   /* stage profiling and launch tracing are analysis modes of the eager schedule (the one a single-lane instance runs) */
   const bool want_graph = inst->use_graph && !inst->trace && !inst->profiling;
   if (g.exec && (g.prof != inst->profiling || !want_graph))
@@ -1286,6 +1293,10 @@ bool detect_common(vksift_Instance inst, const uint8_t *host_image, const uint8_
       CU_TRY(cudaEventRecord(lane->ev_h2d, lane->stream));
     src = lane->d_image;
   }
+  lane->crowded = false;
+  for (vksift_Instance other : inst->lanes)
+    if (other != lane && other->detect_pending)
+      lane->crowded = true;
   const bool ok = enqueue_detection(lane, src, buf);
   if (direct)
     CU_TRY(cudaEventSynchronize(lane->ev_h2d));

@@ -541,7 +541,8 @@ void extrema_layout(DetectParams *P, size_t *bm_words, size_t *rows, size_t *que
   *queue_entries = qn;
 }
 
-cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectCounters *cnt, FeatHead *prim, cudaStream_t st, uint64_t *launch_count)
+cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectCounters *cnt, FeatHead *prim, cudaStream_t st, uint64_t *launch_count,
+                           int scan_ctas)
 {
   if (!pl || !pl->valid || pl->n_tiles == 0 || P.oe <= P.ob)
     return cudaSuccess;
@@ -581,7 +582,22 @@ cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectC
   }
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int per_sm = (int)((220 * 1024) / smem) < 1 ? 1 : (int)((220 * 1024) / smem);
+  /* Persistent scan CTAs (each holds a double-buffered 100 KB tile): two per SM scan a layer set at 4 TB/s, which is what one
+   * detection alone wants.  With several detections in flight the scan is not on the critical path of the GPU (it moves bytes,
+   * the blur and descriptor kernels of the other lanes need the issue slots and the shared memory), and FEWER scan CTAs give the
+   * higher throughput: 8 lanes, ms per 1920x1080 image, 296 / 148 / 74 / 48 / 24 / 16 CTAs: 0.2919 / 0.2874 / 0.2833 / 0.2806 /
+   * 0.2784 / 0.2799; 2 lanes: 0.3401 / 0.3296 / 0.3281 for 296 / 148 / 74.  The caller passes the count for its lane count. */
+  static int env_grid = -1;
+  if (env_grid < 0)
+  {
+    const char *e = getenv("VKSIFT_EX_GRID");
+    env_grid = e ? atoi(e) : 0;
+  }
   int grid = sms * (per_sm > 2 ? 2 : per_sm);
+  if (scan_ctas > 0 && scan_ctas < grid)
+    grid = scan_ctas;
+  if (env_grid > 0)
+    grid = env_grid;
   if (grid > t_end - t_begin)
     grid = t_end - t_begin;
   if (threads == 256 && fp16)

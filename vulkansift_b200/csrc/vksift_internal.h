@@ -204,7 +204,9 @@ struct ExtremaPlan; /* TMA tensor maps over the DoG layers of the current pyrami
 cudaError_t extrema_plan_build(const DetectParams &P, ExtremaPlan **plan_io);
 void extrema_plan_destroy(ExtremaPlan *pl);
 /* scan + refinement + ordered compaction of the octaves [P.ob, P.oe): prim[sec_off[o] + rank] for rank < cap[o] */
-cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectCounters *cnt, FeatHead *prim, cudaStream_t st, uint64_t *launch_count);
+/* scan_ctas: persistent CTAs of the extrema scan (0 = two per SM, the choice for one detection at a time) */
+cudaError_t launch_extrema(const DetectParams &P, const ExtremaPlan *pl, DetectCounters *cnt, FeatHead *prim, cudaStream_t st, uint64_t *launch_count,
+                           int scan_ctas);
 /* words of each bitmap and rows of row_cnt the current pyramid needs; fills bm_off / bm_rw / row_off of P */
 /* also: the octaves' shares (q_off / q_cap) of an extrema queue of queue_total entries */
 void extrema_layout(DetectParams *P, size_t *bm_words, size_t *rows, size_t *queue_entries, uint32_t queue_total);
