@@ -348,6 +348,7 @@ cudaError_t launch_assemble(const DetectParams &P, DetectCounters *cnt, const ui
  *   for i<hr { m += e(i,i)*sqrt2; for j in (i, hr) m += e(i,j)*sqrt2*2 },  e(i,j) = exp(-0.125*(i*i+j*j))
  * in the shader's sequential fp32 order.  The sum only depends on the window radius, so it is tabulated once per instance (on the
  * host, api.cu) instead of being rebuilt (2*hr block barriers and a serial sum) for every feature. */
+template <bool H16>
 __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_constant__ DetectParams P, DetectCounters *__restrict__ cnt,
                                                                   const float *__restrict__ m_table, const FeatHead *__restrict__ prim,
                                                                   const float *__restrict__ ori,
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
     kp.orientation = ori[(size_t)pi * P.ori_stride + k];
     const OctaveView &ov = P.oct[o];
     const void *__restrict__ L = layer_ptr(ov.G, (size_t)kp.scale_idx * ov.layer_stride, ov.fp16);
-    const int f16 = ov.fp16;
+    constexpr int f16 = H16 ? 1 : 0; /* compile-time: the four loads of a sample carry no format branch */
 
     s_desc[tid] = 0;
     const float sf = vks_pow2i(kp.octave_idx);
@@ -632,7 +633,10 @@ cudaError_t launch_descriptors(const DetectParams &P, DetectCounters *cnt, const
     if (per_sm < 1 || per_sm > 16)
       per_sm = 12;
   }
-  descriptor_kernel<<<148 * per_sm, DESC_THREADS, 0, st>>>(P, cnt, m_table, prim, ori, feat_src, out_heads, out_desc);
+  if (P.oct[0].fp16)
+    descriptor_kernel<true><<<148 * per_sm, DESC_THREADS, 0, st>>>(P, cnt, m_table, prim, ori, feat_src, out_heads, out_desc);
+  else
+    descriptor_kernel<false><<<148 * per_sm, DESC_THREADS, 0, st>>>(P, cnt, m_table, prim, ori, feat_src, out_heads, out_desc);
   return cudaGetLastError();
 }
 
