@@ -35,6 +35,7 @@ __device__ __forceinline__ float gauss_at(const void *__restrict__ L, int fp16, 
  * recomputes the (2r+1)^2-term fixed-point scale (:75-81); here 128 threads evaluate the terms once into
  * shared memory, one thread adds them in the reference's (i outer, j inner) fp32 order, and all four warps
  * share the pixel loop. */
+template <bool H16>
 __global__ void __launch_bounds__(ORI_THREADS) orientation_kernel(const __grid_constant__ DetectParams P, const DetectCounters *__restrict__ cnt,
                                                                   const FeatHead *__restrict__ prim, float *__restrict__ ori,
                                                                   uint32_t *__restrict__ n_ori)
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(ORI_THREADS) orientation_kernel(const __grid_c
     const FeatHead kp = prim[slot];
     const OctaveView &ov = P.oct[o];
     const void *__restrict__ L = layer_ptr(ov.G, (size_t)kp.scale_idx * ov.layer_stride, ov.fp16);
-    const int f16 = ov.fp16;
+    constexpr int f16 = H16 ? 1 : 0;
 
     const float sf = vks_pow2i(kp.octave_idx);
     const float lambda = 1.5f * (kp.sigma / sf);
@@ -78,13 +79,24 @@ __global__ void __launch_bounds__(ORI_THREADS) orientation_kernel(const __grid_c
      * n * 2^-24 relative of the exact value (positive terms; n <= 1369 with the default configuration: 8e-5), hence they fall
      * between the same two powers of two unless the parallel sum lies within delta = 1e-4 + 4 n 2^-24 of one; only then (a few
      * keypoints in 1000) is the reference-order sum evaluated. */
+    /* (row, column) of this thread's first cell of the box and the step of ORI_THREADS cells: no division in the two loops */
+    const int step_r = ORI_THREADS / box, step_c = ORI_THREADS - step_r * box;
+    const int row0 = tid / box, col0 = tid - row0 * box;
     float m;
     {
       float part = 0.f;
+      int row = row0, col = col0;
       for (int q = tid; q < n_terms; q += ORI_THREADS)
       {
-        const int i = q / box - r, j = q - (q / box) * box - r;
+        const int i = row - r, j = col - r;
         part += vks_expf(es * (float)((i * i) + (j * j))) * VKS_SQRT2_F;
+        col += step_c;
+        row += step_r;
+        if (col >= box)
+        {
+          col -= box;
+          row++;
+        }
       }
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1)
@@ -131,9 +143,17 @@ __global__ void __launch_bounds__(ORI_THREADS) orientation_kernel(const __grid_c
     const float rsx = vks_rint(kp.scale_x), rsy = vks_rint(kp.scale_y);
     const int cx = (int)rsx, cy = (int)rsy;
     const float r2 = (float)(r * r);
+    int prow = row0, pcol = col0;
     for (int pix = tid; pix < n_terms; pix += ORI_THREADS)
     {
-      const int dy = pix / box - r, dx = pix % box - r;
+      const int dy = prow - r, dx = pcol - r;
+      pcol += step_c;
+      prow += step_r;
+      if (pcol >= box)
+      {
+        pcol -= box;
+        prow++;
+      }
       const int gx = cx + dx, gy = cy + dy;
       const float sdx = (rsx + (float)dx) - kp.scale_x;
       const float sdy = (rsy + (float)dy) - kp.scale_y;
@@ -233,7 +253,10 @@ cudaError_t launch_orientation(const DetectParams &P, DetectCounters *cnt, const
       env_per_sm = 0;
   }
   const int per_sm = env_per_sm ? env_per_sm : (ctas_per_sm >= 1 && ctas_per_sm <= 32 ? ctas_per_sm : 4);
-  orientation_kernel<<<148 * per_sm, ORI_THREADS, 0, st>>>(P, cnt, prim, ori, n_ori);
+  if (P.oct[P.ob].fp16)
+    orientation_kernel<true><<<148 * per_sm, ORI_THREADS, 0, st>>>(P, cnt, prim, ori, n_ori);
+  else
+    orientation_kernel<false><<<148 * per_sm, ORI_THREADS, 0, st>>>(P, cnt, prim, ori, n_ori);
   return cudaGetLastError();
 }
 
