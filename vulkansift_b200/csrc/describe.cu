@@ -498,20 +498,23 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
        * reductions: integer adds commute, so the histogram does not depend on the order of the lanes */
       const float wx[2] = {fabsf(1.f - rx), fabsf(rx)}, wy[2] = {fabsf(1.f - ry), fabsf(ry)}, wb[2] = {fabsf(1.f - rb), fabsf(rb)};
       const uint32_t b0 = (uint32_t)hb & 7u, b1 = (uint32_t)(hb + 1) & 7u; /* non-negative modulo (SURVEY B-D7) */
-#pragma unroll
-      for (int j = 0; j < 2; j++)
-#pragma unroll
-        for (int i = 0; i < 2; i++)
-        {
-          const uint32_t ok = ((uint32_t)(i + hx) < 4u && (uint32_t)(j + hy) < 4u) ? 1u : 0u;
-          const float wxy = wx[i] * wy[j];
-          const uint32_t v0 = (uint32_t)(((wxy * wb[0]) * mag) * fp), v1 = (uint32_t)(((wxy * wb[1]) * mag) * fp);
-          const uint32_t cell = s_desc_addr + (uint32_t)(((j + hy) * 32 + (i + hx) * 8) * 4);
-          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t@p red.shared.add.u32 [%2], %4;\n\t}" ::"r"(
-                           cell + b0 * 4u),
-                       "r"(v0), "r"(cell + b1 * 4u), "r"(ok), "r"(v1)
-                       : "memory");
-        }
+      /* addresses of the two orientation bins in cell (hx, hy); the four cells of a sample are immediate offsets from them */
+      const uint32_t a0 = s_desc_addr + (uint32_t)((hy * 32 + hx * 8) * 4) + b0 * 4u;
+      const uint32_t a1 = s_desc_addr + (uint32_t)((hy * 32 + hx * 8) * 4) + b1 * 4u;
+#define DESC_CELL(J, I)                                                                                                                              \
+  {                                                                                                                                                  \
+    const uint32_t ok = ((uint32_t)((I) + hx) < 4u && (uint32_t)((J) + hy) < 4u) ? 1u : 0u;                                                           \
+    const float wxy = wx[I] * wy[J];                                                                                                                 \
+    const uint32_t v0 = (uint32_t)(((wxy * wb[0]) * mag) * fp), v1 = (uint32_t)(((wxy * wb[1]) * mag) * fp);                                        \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p red.shared.add.u32 [%0+%5], %1;\n\t@p red.shared.add.u32 [%2+%5], %4;\n\t}" ::"r"(a0), \
+                 "r"(v0), "r"(a1), "r"(ok), "r"(v1), "n"(((J) * 32 + (I) * 8) * 4)                                                                  \
+                 : "memory");                                                                                                                        \
+  }
+      DESC_CELL(0, 0)
+      DESC_CELL(0, 1)
+      DESC_CELL(1, 0)
+      DESC_CELL(1, 1)
+#undef DESC_CELL
     };
     if (box <= DESC_MAXBOX)
     {
