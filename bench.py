@@ -378,6 +378,9 @@ def main():
     for i in range(max(W, 3 * NBUF)):  # every lane captures its CUDA graph on the second use of a buffer
         inst.detect_device(d_images[i % N_IMAGES].data_ptr(), w, h, i % NBUF)
     inst.wait_idle()
+    for i in range(3):  # and the graph of the other grid policy (a detection that finds every lane idle), so no capture lands in a timed loop
+        inst.detect_device(d_images[0].data_ptr(), w, h, 0)
+        inst.wait_idle()
     counts = {i: len(expected[i]) for i in range(N_IMAGES)}
     octaves = [inst.octave_resolution(o) for o in range(inst.nb_octaves())]
     ns = inst.config.nb_scales_per_octave
