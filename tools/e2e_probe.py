@@ -9,7 +9,7 @@ from vulkansift_b200.synth import blob_image, C2
 api.load(); api.lib.vksift_setLogLevel(api.VKSIFT_LOG_WARNING)
 imgs = [blob_image(**dict(C2, seed=C2["seed"] + i)) for i in range(4)]
 h, w = imgs[0].shape
-NB = 8
+NB = int(os.environ.get("E2E_NB", "8"))
 inst = api.Instance(input_image_max_size=w * h, sift_buffer_count=NB)
 dev = [torch.from_numpy(im).cuda() for im in imgs]
 pin = [torch.from_numpy(im).pin_memory() for im in imgs]
