@@ -479,6 +479,12 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
       const int off = iy * pitch + ix; /* 32-bit index: a layer has fewer than 2^31 cells */
       const float gX = 0.5f * (layer_ld(L, (size_t)(off + 1), f16) - layer_ld(L, (size_t)(off - 1), f16));
       const float gY = 0.5f * (layer_ld(L, (size_t)(off + pitch), f16) - layer_ld(L, (size_t)(off - pitch), f16));
+      const float mag = vks_expf(es * ((ox * ox) + (oy * oy))) * vks_sqrt((gX * gX) + (gY * gY));
+      /* Every contribution is (uint32)(((wx*wy)*wb)*mag*fp) with weights <= 1 (up to an ulp) and fp a power of two: below
+       * mag*fp = 0.99 all eight truncate to zero, so the sample adds nothing and its angle is not needed (flat or weakly
+       * textured pixels under the tail of the Gaussian window). */
+      if (mag * fp < 0.99f)
+        return;
       float th = vks_atan2f(gY, gX);
       if (th < 0.f)
         th += VKS_TWO_PI_F;
@@ -489,7 +495,6 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
         th += VKS_TWO_PI_F;
       else if (th > VKS_TWO_PI_F)
         th -= VKS_TWO_PI_F;
-      const float mag = vks_expf(es * ((ox * ox) + (oy * oy))) * vks_sqrt((gX * gX) + (gY * gY));
       const float fb = P.vlfeat ? ((th * 8.f) / VKS_TWO_PI_F) : ((-th * 8.f) / VKS_TWO_PI_F);
       const int hb = (int)floorf(fb);
       const float rx = fx - ((float)hx + 0.5f), ry = fy - ((float)hy + 0.5f), rb = fb - (float)hb;
