@@ -40,8 +40,10 @@ extern "C"
    * one scale space and one command buffer (vulkansift.c:326-327).  This build gives the instance min(sift_buffer_count, 8)
    * lanes (environment override VKSIFT_LANES=n), each with its own scale space, scratch memory and streams; a detection
    * into buffer b runs on lane b % lanes and waits for that lane only, so detections into different buffers overlap on the
-   * GPU.  Results are identical to the one-lane schedule.  vksift_getScaleSpace* / vksift_download*Image show the scale
-   * space of the most recent detection.
+   * GPU.  Results are identical to the one-lane schedule.  A detection enqueued while other lanes hold detections the caller
+   * has not waited for runs its latency-bound kernels (extrema scan, orientation) on small grids, which leaves the SMs to the
+   * other detections' kernels (throughput); one that finds every lane idle uses the full grids (latency).
+   * vksift_getScaleSpace* / vksift_download*Image show the scale space of the most recent detection.
    * vksiftx_joinLanes makes the instance stream (vksiftx_getStream) wait, on the device, for every detection enqueued so
    * far: an event recorded on that stream afterwards times them all. */
   VKSIFT_EXPORT uint32_t vksiftx_getLaneCount(vksift_Instance instance);
