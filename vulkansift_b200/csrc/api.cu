@@ -188,6 +188,9 @@ struct vksift_Instance_T
   vksift_Match_2NN *d_matches_blocks = nullptr; /* [blocks_cap][max_nb_sift_per_buffer]: results of vksiftx_matchFeaturesAgainstBlocks */
   uint32_t blocks_cap = 0, blocks_n = 0, blocks_na = 0;
   uint32_t *d_block_norms = nullptr; /* packed B-side norms of all blocks of such a call, one launch */
+  float *d_expanded = nullptr;       /* the input image as fp32 at octave-0 resolution (launch_expand_input), source of the first blur */
+  size_t expanded_bytes = 0;
+  bool use_expand = false;           /* octave 0 runs on the fast kernels with fp32 storage: expand once, then an ordinary layer launch */
   int ori_ctas = 4;                  /* resident CTAs per SM of the orientation kernel */
   int scan_ctas = 0;                 /* persistent CTAs of the extrema scan, 0 = two per SM */
   /* Set per detection: other lanes hold detections the caller has not waited for, i.e. the GPU is shared.  The latency-bound
@@ -419,12 +422,31 @@ bool build_blur_plan(vksift_Instance inst)
     if (!fast)
       break;
   }
+  inst->use_expand = false;
   for (int o = 0; o < k; o++)
   {
     std::vector<BlurPass> passes;
     for (int s = (o == 0 ? 0 : 1); s < ns + 3; s++)
     {
       BlurPass bp = make_pass((uint32_t)o, s);
+      if (o == 0 && s == 0 && !bp.fp16 && !getenv("VKSIFT_NO_EXPAND"))
+      {
+        /* large image: conversion and 2x blit by a kernel of their own, the first blur reads the expanded image through TMA */
+        const size_t need = (size_t)p.pitch[0] * p.h[0] * sizeof(float);
+        if (need > inst->expanded_bytes)
+        {
+          if (inst->d_expanded)
+            CU_TRY(cudaFree(inst->d_expanded));
+          inst->d_expanded = nullptr;
+          inst->expanded_bytes = 0;
+          CU_TRY(cudaMalloc(&inst->d_expanded, need));
+          inst->expanded_bytes = need;
+        }
+        inst->use_expand = true;
+        bp.src = inst->d_expanded;
+        bp.src_kind = BLUR_SRC_LAYER;
+        bp.src_pitch = (int)p.pitch[0];
+      }
       if (!blur_pass_prepare_fast(&bp))
       {
         LOGE(TAG, "cuTensorMapEncodeTiled failed for a scale-space layer (%dx%d)", bp.w, bp.h);
@@ -707,6 +729,7 @@ void destroy_instance(vksift_Instance inst)
   cudaFree(inst->d_matches_rev);
   cudaFree(inst->d_matches_blocks);
   cudaFree(inst->d_block_norms);
+  cudaFree(inst->d_expanded);
   exchange_destroy(inst->exchange);
   inst->exchange = nullptr;
   cudaFree(inst->d_pairs);
@@ -1032,9 +1055,16 @@ bool record_detection(vksift_Instance inst, uint32_t buf)
     const bool strips = !inst->strip_oct[o].empty();
     for (BlurPass &bp : inst->fast_oct[o])
     {
-      const bool is_seed = (bp.src_kind != BLUR_SRC_LAYER);
+      const bool is_seed = (bp.src_kind != BLUR_SRC_LAYER) || bp.dst_d == nullptr; /* layer 0 of octave 0 */
       if (strips && !is_seed)
         break; /* layers >= 1 come from the strip launches below */
+      if (is_seed && inst->use_expand && !(VKS_SKIP(inst) & 8))
+      {
+        TraceScope ts(inst, so, "expand o%d r%d", o, 0);
+        CU_TRY(launch_expand_input(inst->d_src_slot, (int)inst->cur_w, (int)inst->cur_h, inst->cfg.use_input_upsampling ? 1 : 0, inst->d_expanded,
+                                   (int)inst->pyr.pitch[0], (int)inst->pyr.w[0], (int)inst->pyr.h[0], so));
+        inst->launches++;
+      }
       if (!(VKS_SKIP(inst) & 8))
       {
         TraceScope ts(inst, so, is_seed ? "seed o%d r%d" : "fast o%d r%d", o, bp.radius);

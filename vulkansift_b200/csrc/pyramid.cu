@@ -228,8 +228,10 @@ enum
 {
   FT_KIND_SEED = 0, /* u8 source (octave 0, layer 0): no DoG */
   FT_KIND_LAYER = 1, /* float source, G + DoG */
-  FT_KIND_NEXT = 2   /* float source, G + DoG + decimated seed of the next octave (layer ns) */
+  FT_KIND_NEXT = 2,  /* float source, G + DoG + decimated seed of the next octave (layer ns) */
+  FT_KIND_FIRST = 3  /* float source (the expanded input image, expand_input_kernel), G only: layer 0 of octave 0 */
 };
+__host__ __device__ constexpr bool ft_has_dog(int KIND) { return KIND == FT_KIND_LAYER || KIND == FT_KIND_NEXT; }
 
 __host__ __device__ constexpr int ft_rx(int R) { return (R + 3) & ~3; } /* x halo rounded to float4 */
 /* source tile row stride (= TMA box width), floats: covers 64 + 2 halos, stride/4 odd -> LDS.128 down a column is conflict free */
@@ -624,7 +626,7 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
             const __half2 hg = __floats2half2_rn(pk_lo(acc[j]), pk_hi(acc[j]));
             *reinterpret_cast<__half2 *>(gbase + (off >> 1)) = hg;
             const float2 fg = __half22float2(hg);
-            if (KIND != FT_KIND_SEED)
+            if (ft_has_dog(KIND))
             {
               const pk2 d = pk_sub(pk_make(fg.x, fg.y), *(const pk2 *)(ccol + q * S));
               __stcs(reinterpret_cast<__half2 *>(dbase + (off >> 1)), __floats2half2_rn(pk_lo(d), pk_hi(d)));
@@ -642,7 +644,7 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
            * for every row: the DoG source row is in shared memory whether the output row exists or not */
           const bool ok = q < nrows;
           pk_stg_if(gbase + off, acc[j], ok);
-          if (KIND != FT_KIND_SEED)
+          if (ft_has_dog(KIND))
           {
             /* streaming: the DoG layer is not read before the extrema scan, the L2 lines are better spent on G, which the
              * next layer's launch reads back */
@@ -675,7 +677,7 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
       if (H16)
         acc = round_half1(acc);
       layer_st(p.dst_g, (size_t)y * p.dst_pitch + x, acc, H16);
-      if (KIND != FT_KIND_SEED)
+      if (ft_has_dog(KIND))
         layer_st(p.dst_d, (size_t)y * p.dst_pitch + x, vks_sub(acc, s_in[(R + ry + q) * S + RX + col]), H16);
       if (KIND == FT_KIND_NEXT && (x & 1) && (y & 1))
       {
@@ -1035,9 +1037,78 @@ static cudaError_t launch_fast_r(const BlurPassFast &F, dim3 n_tiles, cudaStream
 {
   if (F.p.src_kind != BLUR_SRC_LAYER)
     return launch_fast_rk<R, FT_KIND_SEED>(F, n_tiles, st);
+  if (!F.p.dst_d)
+    return launch_fast_rkh<R, FT_KIND_FIRST, false>(F, n_tiles, st); /* the expanded input is fp32 (blur_plan only uses it without binary16 storage) */
   if (F.p.dst_next)
     return launch_fast_rk<R, FT_KIND_NEXT>(F, n_tiles, st);
   return launch_fast_rk<R, FT_KIND_LAYER>(F, n_tiles, st);
+}
+
+/* ---- input expansion --------------------------------------------------------
+ * Layer 0 of octave 0 is the blur of the input image after the UNORM conversion and (with upsampling) the LINEAR 2x blit
+ * (sift_detector.c:860-953).  The fused seed pass above does conversion + blit + blur per tile and spends two thirds of its
+ * instructions on staging the u8 window and on the blit; with several detections in flight instructions are what counts, so
+ * for large images the expanded fp32 image is written once by this kernel (5.5 instructions per pixel) and the first blur is
+ * an ordinary TMA-fed layer launch without a DoG output (FT_KIND_FIRST).  Same operation sequence per pixel as fetch_u8_up2:
+ * horizontal lerp of the two rows, then the vertical one.  One thread = one output column pair, eight output rows. */
+#define XP_ROWS 32
+__global__ void __launch_bounds__(256) expand_input_kernel(const uint8_t *const *__restrict__ src_slot, const int sw, const int sh, const int up,
+                                                           float *__restrict__ dst, const int pitch, const int w, const int h)
+{
+  __shared__ float lut[256];
+  lut[threadIdx.x] = vks_unorm8((uint8_t)threadIdx.x);
+  pdl_launch_dependents();
+  __syncthreads();
+  const uint8_t *__restrict__ img = *src_slot;
+  const int cp = blockIdx.x * blockDim.x + threadIdx.x; /* column pair */
+  const int x = 2 * cp, y0 = (int)blockIdx.y * XP_ROWS;
+  if (x >= w)
+    return;
+  if (!up)
+  {
+    for (int y = y0; y < min(h, y0 + XP_ROWS); y++)
+    {
+      const uint8_t *row = img + (size_t)y * sw;
+      float *o = dst + (size_t)y * pitch + x;
+      o[0] = lut[row[x]];
+      if (x + 1 < w)
+        o[1] = lut[row[x + 1]];
+    }
+    return;
+  }
+  /* destination columns (x, x+1) = (2k, 2k+1): sources (k-1, k) with f = .75 and (k, k+1) with f = .25, clamped to the image
+   * (w = 2 sw is even: a column pair is always complete) */
+  const int k = x >> 1;
+  const int c0 = max(k - 1, 0), c1 = k, c2 = min(k + 1, sw - 1);
+  auto hrow = [&](int sy, float &he, float &ho) {
+    const uint8_t *row = img + (uint32_t)(min(max(sy, 0), sh - 1) * sw);
+    const float a0 = lut[row[c0]], a1 = lut[row[c1]], a2 = lut[row[c2]];
+    he = vks_lerp(a0, a1, 0.75f);
+    ho = vks_lerp(a1, a2, 0.25f);
+  };
+  /* destination rows (2j, 2j+1): source rows (j-1, j) with f = .75 and (j, j+1) with f = .25 */
+  const int j0 = y0 >> 1;
+  const int n_pairs = min(XP_ROWS, h - y0) >> 1; /* h = 2 sh is even */
+  float he0, ho0, he1, ho1, he2, ho2;
+  hrow(j0 - 1, he0, ho0);
+  hrow(j0, he1, ho1);
+  float *o = dst + (size_t)y0 * pitch + x;
+#pragma unroll 4
+  for (int jj = 0; jj < n_pairs; jj++)
+  {
+    hrow(j0 + jj + 1, he2, ho2);
+    *reinterpret_cast<float2 *>(o) = make_float2(vks_lerp(he0, he1, 0.75f), vks_lerp(ho0, ho1, 0.75f));
+    *reinterpret_cast<float2 *>(o + pitch) = make_float2(vks_lerp(he1, he2, 0.25f), vks_lerp(ho1, ho2, 0.25f));
+    o += 2 * pitch;
+    he0 = he1, ho0 = ho1, he1 = he2, ho1 = ho2;
+  }
+}
+
+cudaError_t launch_expand_input(const void *src_slot, int sw, int sh, int up, float *dst, int pitch, int w, int h, cudaStream_t st)
+{
+  const dim3 grid((unsigned)(((w + 1) / 2 + 255) / 256), (unsigned)((h + XP_ROWS - 1) / XP_ROWS));
+  expand_input_kernel<<<grid, 256, 0, st>>>((const uint8_t *const *)src_slot, sw, sh, up, dst, pitch, w, h);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_blur_pass_fast(const BlurPass &bp, cudaStream_t st)

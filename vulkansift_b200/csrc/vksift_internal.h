@@ -190,6 +190,8 @@ bool blur_step_tiles(BlurStep *step);
 bool blur_pass_is_fast(const BlurPass &bp);
 /* tile geometry + TMA tensor map of a pass for the fast kernel */
 bool blur_pass_prepare_fast(BlurPass *bp);
+/* the input image as fp32 at the resolution of octave 0 (UNORM conversion, LINEAR 2x blit when `up`): source of the first blur */
+cudaError_t launch_expand_input(const void *src_slot, int sw, int sh, int up, float *dst, int pitch, int w, int h, cudaStream_t st);
 cudaError_t launch_blur_pass_fast(const BlurPass &bp, cudaStream_t st);
 cudaError_t launch_blur_step(const BlurStep &step, cudaStream_t st);
 cudaError_t launch_widen_layer(const void *src, int w, int h, int pitch, float *dst, cudaStream_t st);
