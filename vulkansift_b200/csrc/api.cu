@@ -794,7 +794,9 @@ bool create_resources(vksift_Instance inst)
   }
   CU_TRY(cudaEventCreateWithFlags(&inst->ev_detect_done, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&inst->ev_match_done, cudaEventDisableTiming));
-  CU_TRY(cudaEventCreateWithFlags(&inst->ev_h2d, cudaEventDisableTiming | cudaEventBlockingSync));
+  /* waited for inside vksift_detectFeatures while a 2 MB copy runs (tens of microseconds): spin, a blocking wait costs a sleep and a
+   * late wake-up per image and makes the end-to-end loop sensitive to the host's scheduler */
+  CU_TRY(cudaEventCreateWithFlags(&inst->ev_h2d, cudaEventDisableTiming));
   for (int i = 0; i < EV_COUNT; i++)
     CU_TRY(cudaEventCreate(&inst->ev[i]));
 
