@@ -663,7 +663,9 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
   }
   else
   {
-    /* last tile column of a layer whose width is not a multiple of 64: plain scalar loop */
+    /* last tile column of a layer whose width is not a multiple of 64: plain scalar loop, kept rolled (it runs in one tile
+     * column of some layers and must not take instruction-cache space from the path above) */
+#pragma unroll 1
     for (int idx = lane; idx < FT_W * nrows; idx += 32)
     {
       const int col = idx & (FT_W - 1), q = idx >> 6;
@@ -672,6 +674,7 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
         continue;
       const float *mc = s_mid + (ry + q + R) * FT_MS + col;
       float acc = vks_mul(mc[0], taps2[0].x);
+#pragma unroll 1
       for (int i = 1; i <= R; i++)
         acc = vks_blur_tap(acc, mc[i * FT_MS], mc[-i * FT_MS], taps2[i].x);
       if (H16)
