@@ -365,6 +365,7 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
       const int r_lo = max(0, -cy), r_hi = min(rows_in, p.h - cy); /* rows inside the image */
       if (ncol > 0)
       {
+#pragma unroll 1
         for (int i = tid; i < (r_hi - r_lo) * ncol; i += FT_THREADS)
         {
           const int rr = i / ncol, k = i - rr * ncol;
@@ -378,6 +379,7 @@ __device__ __forceinline__ void blur_tile(const BlurPass &p, const CUtensorMap *
       const int nrow = r_lo + (rows_in - r_hi);
       if (nrow > 0)
       {
+#pragma unroll 1
         for (int i = tid; i < nrow * (S / 4); i += FT_THREADS)
         {
           const int k = i / (S / 4), c4 = i - k * (S / 4);
