@@ -441,7 +441,8 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
         if (tid == 0)
         {
           const int c = min(DESC_THREADS, hr - j0);
-          for (int q = 0; q < c; q++)
+#pragma unroll 1
+          for (int q = 0; q < c; q++) /* rare (windows beyond the host table): rolled, it must not take instruction-cache space */
             m += s_terms[q];
         }
         __syncthreads();
@@ -618,6 +619,7 @@ __global__ void __launch_bounds__(DESC_THREADS) descriptor_kernel(const __grid_c
     }
     else
     {
+#pragma unroll 1
       for (int pix = tid; pix < box * box; pix += DESC_THREADS)
         add_pixel(pix % box - R, pix / box - R);
     }
