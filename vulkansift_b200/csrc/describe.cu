@@ -128,8 +128,8 @@ __global__ void __launch_bounds__(ORI_THREADS) orientation_kernel(const __grid_c
           __syncthreads();
           if (tid == 0)
           {
-#pragma unroll 8
-            for (int t = 0; t < nt; t++)
+#pragma unroll 1
+            for (int t = 0; t < nt; t++) /* rare path: rolled */
               m += s_terms[t];
             s_m = m;
           }
