@@ -202,23 +202,25 @@ __global__ void __launch_bounds__(256) blur_step_small_kernel(const __grid_const
  *
  * Measured on B200 (tools/ubench/fp32_rate.cu): FFMA2/FADD2 retire the same number of fp32 results per
  * cycle as FFMA/FADD (128 per SM), they only halve the issue slots.  A blur pass needs 2(2R+1) fp32
- * operations per pixel, which puts the fp32 pipe of the late scales at the same cost as the HBM writes of
- * the layer; everything that is not a blur operation therefore has to fit into the issue slots the packed
- * instructions leave free:
- *   - 64x128 output tile, 256 threads, two CTAs per SM (one loads/stores while the other computes)
+ * operations per pixel; the kernel is bound by issue slots, the FMA pipe and, above all, by how many of its
+ * CTAs an SM holds, not by HBM:
+ *   - 64x64 output tile, 256 threads, five (R = 4) or four CTAs per SM: a tile runs in phases (TMA wait,
+ *     horizontal pass, barrier, vertical pass) and only the other CTAs of the SM fill the gaps
  *   - the source tile + halo arrives by TMA (cp.async.bulk.tensor.2d, zero thread instructions) in four
  *     row bands with one mbarrier each, so the horizontal pass starts when the first band has landed;
  *     tiles on the image border get their MIRRORED_REPEAT halo patched in shared memory
  *   - horizontal pass: one thread = 1 row x 16 columns, window in registers straight from LDS.128.
  *     Output pairs (x, x+1): even taps use the aligned register pairs of the window (FADD2), odd taps add
  *     the two scalars into a fresh pair (2 FADD), both feed one FFMA2 -- no register shuffles
- *   - vertical pass: one thread = 2 columns x 16 rows, pairs (x, x+1), sliding window of LDS.64;
- *     writes G, DoG = G - centre (from the source tile) and the decimated seed with 64-bit stores
+ *   - vertical pass: one thread = 2 columns x 8 rows, pairs (x, x+1), sliding window of LDS.64;
+ *     writes G, DoG = G - centre (from the source tile) and the decimated seed with predicated 64-bit stores
  *   - one launch = one layer, one kernel per (radius, kind): every parameter and tap is a constant operand
+ *   - everything that runs rarely (border patch, partial tile columns) is kept in rolled loops: the kernels of
+ *     five to ten launches share an SM's instruction cache, and straight-line cold code cost 1.4 % of the image time
  * Per-pixel operation sequence is the one of vksift_arith.h; add/fma.rn.f32x2 are two IEEE operations.
  * ========================================================================== */
 #define FT_W 64
-#define FT_H 128
+#define FT_H 128 /* only the unit of the "large enough" test in blur_pass_is_fast; tiles are ft_tile_h(R) = 64 rows high */
 #define FT_THREADS 256
 #define FT_MS (FT_W + 4) /* row stride of the horizontal-pass result, floats (stride/4 odd) */
 #define FT_VR 16         /* output rows per thread in the vertical pass = FT_H / warps */
@@ -266,7 +268,7 @@ struct BlurPassFast
 
 #define FT_TAP(i) (*reinterpret_cast<const pk2 *>(&taps2[i]))
 
-/* One 64x128 tile of one layer.  The TMA barriers at the end of the shared memory block are initialised by the
+/* One 64 x TH tile of one layer.  The TMA barriers at the end of the shared memory block are initialised by the
  * caller; `parity` is the phase they complete next (a persistent caller flips it for every float-source tile).
  * `taps2` must point into the kernel parameters at a compile-time offset (constant operands). */
 template <int R, int KIND, int TH, int BAR_OFF, bool H16>
@@ -968,7 +970,7 @@ cudaError_t launch_fused(const FusedLaunch &F, cudaStream_t st)
 }
 
 /* A pass goes to the fast per-layer kernel when its radius is covered and the layer is large enough for
- * throughput to matter (one 64x128 tile per SM or more); smaller octaves are latency bound and take the
+ * throughput to matter (at least 24 blocks of 64x128 pixels); smaller octaves are latency bound and take the
  * fused kernel (or, when their radii do not fit it, the compact kernel). */
 bool blur_pass_is_fast(const BlurPass &bp)
 {
