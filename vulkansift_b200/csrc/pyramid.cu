@@ -223,7 +223,6 @@ __global__ void __launch_bounds__(256) blur_step_small_kernel(const __grid_const
 #define FT_H 128 /* only the unit of the "large enough" test in blur_pass_is_fast; tiles are ft_tile_h(R) = 64 rows high */
 #define FT_THREADS 256
 #define FT_MS (FT_W + 4) /* row stride of the horizontal-pass result, floats (stride/4 odd) */
-#define FT_VR 16         /* output rows per thread in the vertical pass = FT_H / warps */
 #define FT_NB 4          /* TMA row bands per tile */
 
 enum
