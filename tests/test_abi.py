@@ -120,7 +120,7 @@ def test_plain_c_caller_links_against_the_library(tmp_path):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     lib_dir = os.path.join(root, "vulkansift_b200", "lib")
-    for name in ("detect_match", "perf_runtime", "perf_matching"):  # the README-style caller and the port of the reference's perf_sift_runtime driver
+    for name in ("detect_match", "perf_runtime", "perf_matching", "exchange_pairs"):  # the README-style caller and the port of the reference's perf_sift_runtime driver
         out = tmp_path / name
         r = subprocess.run(["gcc", "-std=c11", os.path.join(root, "examples", name + ".c"), "-I" + os.path.join(root, "include"), "-L" + lib_dir,
                             "-lvulkansift", "-Wl,-rpath," + lib_dir, "-lm", "-o", str(out)], capture_output=True, text=True)

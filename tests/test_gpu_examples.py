@@ -55,3 +55,12 @@ def test_cpp_caller_throws_through_the_error_callback(tmp_path):
     r = subprocess.run([_build(tmp_path, "error_handling", cxx=True)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "buffer 5: std::invalid_argument caught" in r.stdout and "error_handling: ok" in r.stdout, r.stdout
+
+
+def test_exchange_example_three_processes_from_plain_c(tmp_path):
+    """examples/exchange_pairs.c: three forked workers (pipes for the IPC handles and barriers, no MPI, no torch) detect on their own
+    image, exchange descriptors through vksiftx_exchangeMatchAllPeers and check the records they get for every peer."""
+    r = subprocess.run([_build(tmp_path, "exchange_pairs")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "exchange_pairs: ok" in r.stdout, r.stdout
+    assert len(re.findall(r"rank \d \(\d+ features\) vs rank \d \(\d+ features\): \d+ matches passing the ratio test", r.stdout)) == 6, r.stdout
