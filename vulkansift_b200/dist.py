@@ -150,14 +150,31 @@ class PeerExchange:
     def __init__(self, inst, slot_rows, group=None):
         self.inst, self.group = inst, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        handle = inst.exchange_create(self.rank, self.world, slot_rows)
         backend = dist.get_backend(group)
         dev = torch.device("cuda", inst.device_index) if backend == "nccl" else torch.device("cpu")
+        # every step below is followed by an agreement on its outcome: a rank that cannot allocate or map (no peer access, IPC not
+        # permitted in this container) must not leave the others waiting in the next collective
+        err, handle = None, bytes(64)
+        try:
+            handle = inst.exchange_create(self.rank, self.world, slot_rows)
+        except Exception as e:  # VksiftError from the library's error callback
+            err = e
         mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
         every = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(every.view(-1), mine, group=group)
-        inst.exchange_connect(every.cpu().numpy().tobytes())
-        dist.barrier(group)  # every region exists and is mapped everywhere before the first push
+        if err is None:
+            try:
+                inst.exchange_connect(every.cpu().numpy().tobytes())
+            except Exception as e:
+                err = e
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # also the barrier: every region is mapped everywhere before the first push
+        if int(ok.item()) == 0:
+            try:
+                inst.exchange_destroy()
+            except Exception:
+                pass
+            raise RuntimeError("descriptor exchange over peer memory is not available on this node: %s" % (err or "a peer could not map the regions"))
 
     def allgather(self, buffer_id):
         """(counts, device pointer of block 0, stride in bytes): the peers' descriptor blocks, in place in this rank's region."""
